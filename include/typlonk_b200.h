@@ -1,0 +1,168 @@
+/*
+ * typlonk_b200 -- C ABI of the B200-native PLONK proving backend.
+ *
+ * This is the drop-in boundary under fabrizio-m/TyPLONK's unchanged Rust API.  The
+ * reference has no FFI of its own (it is 100% Rust on arkworks 0.3); each entry point
+ * below replaces the body of the cited reference function, and a thin Rust shim
+ *  forwards the reference's public functions to it.
+ *
+ * Conventions
+ *  - every function returns an int status (TP_OK == 0); nothing throws across the ABI;
+ *    the Rust shim turns a non-zero status into `panic!` where the reference panics.
+ *  - Fr is 4 x u64, Fq is 6 x u64, little-endian limbs, MONTGOMERY form (R = 2^256 /
+ *    2^384) -- byte-identical to ark_ff::Fp256 / Fp384 in memory, so buffers cross the
+ *    boundary without conversion.
+ *  - an affine G1 point is 97 bytes: x (48 B) | y (48 B) Montgomery limbs | 1 byte
+ *    infinity flag (ark_ec GroupAffine {x, y, infinity}, packed; when the flag is 1,
+ *    (x, y) = (0, 1) in Montgomery form like `GroupAffine::zero()`).
+ *  - SRS G1 points cross as packed 96-byte (x | y) records; the all-zero record encodes
+ *    the point at infinity.
+ *  - pointers are HOST pointers unless the function name ends in `_dev`.
+ *  - one in-flight call per tp_ctx (the reference is single-threaded).
+ *  - there is no CPU fallback: without a CUDA device tp_ctx_create fails with
+ *    TP_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef TYPLONK_B200_H
+#define TYPLONK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tp_ctx tp_ctx;
+typedef struct tp_srs tp_srs;
+typedef struct tp_circuit tp_circuit;
+
+enum {
+  TP_OK = 0,
+  TP_ERR_INVALID_ARG = 1,
+  TP_ERR_CUDA = 2,
+  TP_ERR_SRS_TOO_SHORT = 3,   /* assert!(srs.len() > polynomial.degree())   kzg/src/lib.rs:43 */
+  TP_ERR_EMPTY_POLY = 4,      /* .expect("at least 1")                      kzg/src/lib.rs:58 */
+  TP_ERR_ZERO_DENOMINATOR = 5,/* Fr division by zero panics                 permutation/src/proving.rs:21 */
+  TP_ERR_GATE_UNSATISFIED = 6,/* vanishes() assert                          plonk/src/proof.rs:321,361,504-508 */
+  TP_ERR_NO_DEVICE = 7,
+  TP_ERR_COLLECTIVE = 8,
+  TP_ERR_BUFFER_TOO_SMALL = 9
+};
+
+#define TP_G1_BYTES 97
+#define TP_PROOF_FIXED_BYTES 1472 /* 13 G1 x 96 + 7 Fr x 32 (uncompressed ark-serialize 0.3 layout) */
+
+/* ---- context ------------------------------------------------------------------------ */
+
+/* Binds to CUDA device `device`.  `stream` is a cudaStream_t to run on (e.g. the caller's
+ * torch stream) or NULL to create a private one. */
+int tp_ctx_create(int device, void* stream, tp_ctx** out);
+int tp_ctx_destroy(tp_ctx* ctx);
+const char* tp_last_error(tp_ctx* ctx);
+int tp_sync(tp_ctx* ctx);
+
+/* Multi-GPU (one process per GPU).  Every MSM is sharded by contiguous point range over
+ * `world` ranks; each rank produces a partial Jacobian point (3 x 48 B Montgomery) and calls
+ * `allgather(user, send[144 B], recv[world x 144 B], 144)` -- the host language wires this to
+ * NCCL (torch.distributed.all_gather over NVLink).  rank/world = 0/1 disables sharding. */
+typedef int (*tp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
+int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user);
+
+/* Per-phase device timers (CUDA events on the ctx stream).  Phase ids: TP_PHASE_*. */
+enum {
+  TP_PHASE_MSM_TOTAL = 0,
+  TP_PHASE_MSM_SORT = 1,       /* digit extraction + counting sort */
+  TP_PHASE_MSM_ACCUM = 2,      /* bucket accumulation kernel (dominant) */
+  TP_PHASE_MSM_REDUCE = 3,     /* boundary merge + bucket reduction */
+  TP_PHASE_NTT = 4,
+  TP_PHASE_QUOTIENT = 5,       /* pointwise numerator + division by Z_H */
+  TP_PHASE_PERM = 6,           /* grand product */
+  TP_PHASE_SCAN = 7,           /* openings: Horner + division by (X - z) */
+  TP_PHASE_COUNT = 8
+};
+int tp_prof_enable(tp_ctx* ctx, int on);
+int tp_prof_reset(tp_ctx* ctx);
+/* ms[TP_PHASE_COUNT], launches[TP_PHASE_COUNT]: accumulated since the last reset. */
+int tp_prof_get(tp_ctx* ctx, double* ms, uint64_t* launches);
+/* total number of kernels this library launched on ctx since creation */
+int tp_launch_count(tp_ctx* ctx, uint64_t* out);
+
+/* ---- SRS  (kzg/src/srs.rs) ------------------------------------------------------------ */
+
+/* Srs::from_secret(s, gates) (srs.rs:30-34): gates + 3 powers [G, sG, s^2 G, ...] generated
+ * on the device (fixed-base windowed multiplication + batched affine normalisation). */
+int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out);
+/* Adopt an existing Vec<G1Affine> (srs.rs:43-45 g1_ref), packed to 96 B / point. */
+int tp_srs_upload(tp_ctx* ctx, const uint8_t* g1_xy, size_t len, tp_srs** out);
+int tp_srs_len(const tp_srs* srs, size_t* len);
+int tp_srs_g1_download(tp_ctx* ctx, const tp_srs* srs, size_t offset, size_t count, uint8_t* out_xy);
+int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs);
+
+/* ---- KZG  (kzg/src/lib.rs) ------------------------------------------------------------- */
+
+/* KzgScheme::commit (lib.rs:37-54): sum_i coeffs[i] * srs[i].  len == 0 -> infinity.
+ * len > srs length -> TP_ERR_SRS_TOO_SHORT. */
+int tp_commit(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, uint8_t out[TP_G1_BYTES]);
+int tp_commit_dev(tp_ctx* ctx, const tp_srs* srs, const void* coeffs_dev, size_t len, uint8_t out[TP_G1_BYTES]);
+/* KzgScheme::open (lib.rs:55-64): y = p(z), W = commit((p - y) / (X - z)).
+ * len == 0 -> TP_ERR_EMPTY_POLY. */
+int tp_open(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, const uint64_t z[4],
+            uint8_t w_out[TP_G1_BYTES], uint64_t y_out[4]);
+
+/* ---- NTT  (ark-poly Evaluations::interpolate / evaluate_over_domain; call sites
+ *      plonk/src/proof.rs:50,106,115,125,128,337,415; builder.rs:85; permutation/src/lib.rs:171,188) */
+
+/* In place, natural order in and out, size 2^log_n (1 <= log_n <= 28).  inverse != 0 scales by
+ * n^-1.  coset != NULL: forward evaluates on coset*H (input scaled by coset^i); inverse
+ * interpolates from coset*H (output scaled by coset^-i). */
+int tp_ntt(tp_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, const uint64_t* coset);
+int tp_ntt_dev(tp_ctx* ctx, void* data_dev, unsigned log_n, int inverse, const uint64_t* coset);
+
+/* ---- permutation argument  (permutation/src/proving.rs:7-31) -------------------------- */
+
+/* CompiledPermutation::prove: out[0] = 1, out[j+1] = out[j] * prod_i (v_ij + beta id_ij + gamma) /
+ * (v_ij + beta sigma_ij + gamma); writes n + 1 values.  A zero denominator ->
+ * TP_ERR_ZERO_DENOMINATOR. */
+int tp_perm_prove(tp_ctx* ctx, const uint64_t* const values[3], const uint64_t* const id[3],
+                  const uint64_t* const sigma[3], size_t n, const uint64_t beta[4], const uint64_t gamma[4],
+                  uint64_t* out);
+
+/* ---- circuit + prover  (plonk/src/lib.rs:18-35, plonk/src/proof.rs:96-194) ------------- */
+
+/* Upload a CompiledCircuit: 5 selector polynomials in COEFFICIENT form (q_l q_r q_o q_m q_c,
+ * each zero-padded to n), the permutation columns `cols` split into id[i][j] and sigma[i][j]
+ * (evaluation form, n each), and the three coset representatives k_i (permutation/src/lib.rs:141-154).
+ * Caches what the reference recomputes per proof (sigma coefficient forms, 4n-domain evaluations). */
+int tp_circuit_load(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selectors[5],
+                    const uint64_t* const id[3], const uint64_t* const sigma[3], const uint64_t cosets[3][4],
+                    size_t n, tp_circuit** out);
+/* Setup path (CircuitBuilder::compile numerics, plonk/src/builder.rs:70-88 + Permutation::compile,
+ * permutation/src/lib.rs:101-128): selector EVALUATIONS (n each) and the flat permutation
+ * `perm[3n]` (index = j + i*n) -> device sigma/id tables, selector interpolation, and the five
+ * fixed commitments (5 x 97 B). */
+int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selector_evals[5],
+                       const uint64_t* perm, size_t n, tp_circuit** out, uint8_t fixed_commitments[5 * TP_G1_BYTES]);
+int tp_circuit_destroy(tp_ctx* ctx, tp_circuit* c);
+/* sigma commitments / evaluations the verifier recomputes per call (permutation/src/lib.rs:165-194). */
+int tp_circuit_sigma_commitments(tp_ctx* ctx, tp_circuit* c, uint8_t out[3 * TP_G1_BYTES]);
+
+/* prove() (proof.rs:96-194) from the three witness columns in EVALUATION form (n each, the
+ * last three rows already hold the blinders, proof.rs:43-49) and the n-padded public inputs.
+ * Writes TP_PROOF_FIXED_BYTES bytes: a.com a.W a.y | b.. | c.. | z.com z.W z.y zw.W zw.y |
+ * evaluation_point | t0 t1 t2 | r.W r.y  (G1 = ark-serialize 0.3 uncompressed 96 B, Fr = 32 B LE
+ * canonical).  The gate equation failing on any row -> TP_ERR_GATE_UNSATISFIED. */
+int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+             uint8_t* proof_out, size_t proof_cap);
+int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
+                 uint8_t* proof_out, size_t proof_cap);
+
+/* ---- helpers ---------------------------------------------------------------------------- */
+/* Measured dependent-free IMAD throughput of this device (instructions/s), for rooflines. */
+int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
+/* Self-test of the device field/curve arithmetic against host arithmetic; 0 failures expected. */
+int tp_selftest(tp_ctx* ctx, int* failures);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

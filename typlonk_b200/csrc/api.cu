@@ -1,0 +1,592 @@
+// extern "C" surface of libtyplonk_b200 (include/typlonk_b200.h) and the device-resident
+// prover driver that replaces plonk/src/proof.rs:96-194 (`prove`), :292-375
+// (`quotient_polynomial`), :376-439 (`linearisation_poly`) and the setup numerics of
+// plonk/src/builder.rs:70-88.  The host only sequences kernels, derives the Fiat-Shamir
+// challenges (transcript.h) and does the O(1) scalar algebra between rounds.
+#include "common.cuh"
+#include "transcript.h"
+
+using namespace tp;
+using tph::HFr;
+
+namespace tp {
+tph::HFr omega_for_log(unsigned log_n);
+}
+
+struct tp_circuit {
+  size_t n = 0;
+  unsigned log_n = 0;
+  const tp_srs* srs = nullptr;
+  Fr* sel_coef[5] = {0};
+  Fr* sel_eval[5] = {0};
+  Fr* sel4[5] = {0};
+  Fr* id[3] = {0};
+  Fr* sig_eval[3] = {0};
+  Fr* sig_coef[3] = {0};
+  Fr* sig4[3] = {0};
+  Fr* l0_4 = nullptr;
+  HFr k[3];
+  // per-proof work buffers
+  Fr* adv_eval[3] = {0};
+  Fr* adv_coef[3] = {0};
+  Fr* pi_eval = nullptr;
+  Fr* pi_coef = nullptr;
+  Fr* z_eval = nullptr;  // n + 1
+  Fr* z_coef = nullptr;
+  Fr* buf4[6] = {0};     // a4 b4 c4 z4 pi4 num4
+  Fr* t = nullptr;       // 3n
+  Fr* q = nullptr;       // n
+  Fr* r = nullptr;       // n
+  std::vector<void*> allocs;
+};
+
+static int dmalloc(tp_ctx* ctx, tp_circuit* c, Fr** p, size_t count) {
+  void* v = nullptr;
+  TP_CUDA_OK(ctx, cudaMalloc(&v, count * sizeof(Fr)));
+  c->allocs.push_back(v);
+  *p = (Fr*)v;
+  return TP_OK;
+}
+static int h2d(tp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return TP_OK;
+}
+static int d2h_sync(tp_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TP_OK;
+}
+static unsigned log2_exact(size_t n) {
+  unsigned l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}
+
+extern "C" {
+
+// ---- context ------------------------------------------------------------------------------
+int tp_ctx_create(int device, void* stream, tp_ctx** out) {
+  if (!out) return TP_ERR_INVALID_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count) return TP_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return TP_ERR_NO_DEVICE;
+  tp_ctx* ctx = new tp_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ctx;
+      return TP_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+  }
+  ctx->pinned_cap = 1 << 16;
+  if (cudaMallocHost(&ctx->pinned, ctx->pinned_cap) != cudaSuccess) {
+    delete ctx;
+    return TP_ERR_CUDA;
+  }
+  *out = ctx;
+  return TP_OK;
+}
+
+int tp_ctx_destroy(tp_ctx* ctx) {
+  if (!ctx) return TP_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.tw);
+  for (auto& c : ctx->coset_tables) {
+    cudaFree(c.lo);
+    cudaFree(c.hi);
+  }
+  DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_sorted,
+                    &ctx->msm_sorted_keys, &ctx->msm_hist, &ctx->msm_offsets, &ctx->msm_blocksums, &ctx->msm_buckets,
+                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->flag};
+  for (auto* b : bufs) release(*b);
+  for (auto& b : ctx->scan_tmp) release(b);
+  for (auto& b : ctx->misc) release(b);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  for (auto& p : ctx->pending) {
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
+  }
+  if (ctx->fixed_base) cudaFree(ctx->fixed_base);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return TP_OK;
+}
+
+const char* tp_last_error(tp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int tp_sync(tp_ctx* ctx) {
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TP_OK;
+}
+
+int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user) {
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, TP_ERR_INVALID_ARG, "set_shard: bad rank/world");
+  if (world > 1 && !allgather) return fail(ctx, TP_ERR_INVALID_ARG, "set_shard: world > 1 needs an all-gather");
+  ctx->rank = rank;
+  ctx->world = world;
+  ctx->allgather = allgather;
+  ctx->allgather_user = user;
+  return TP_OK;
+}
+
+static int prof_collect(tp_ctx* ctx) {
+  if (ctx->pending.empty()) return TP_OK;
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& p : ctx->pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    ctx->prof_ms[p.phase] += ms;
+    ctx->prof_launch[p.phase] += p.launches;
+    ctx->event_pool.push_back(p.a);
+    ctx->event_pool.push_back(p.b);
+  }
+  ctx->pending.clear();
+  return TP_OK;
+}
+int tp_prof_enable(tp_ctx* ctx, int on) {
+  TP_TRY(prof_collect(ctx));
+  ctx->prof = on != 0;
+  return TP_OK;
+}
+int tp_prof_reset(tp_ctx* ctx) {
+  TP_TRY(prof_collect(ctx));
+  for (int i = 0; i < TP_PHASE_COUNT; i++) {
+    ctx->prof_ms[i] = 0;
+    ctx->prof_launch[i] = 0;
+  }
+  return TP_OK;
+}
+int tp_prof_get(tp_ctx* ctx, double* ms, uint64_t* launches) {
+  TP_TRY(prof_collect(ctx));
+  for (int i = 0; i < TP_PHASE_COUNT; i++) {
+    if (ms) ms[i] = ctx->prof_ms[i];
+    if (launches) launches[i] = ctx->prof_launch[i];
+  }
+  return TP_OK;
+}
+int tp_launch_count(tp_ctx* ctx, uint64_t* out) {
+  *out = ctx->launches;
+  return TP_OK;
+}
+
+// ---- SRS ------------------------------------------------------------------------------------
+int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out) {
+  if (!out || !tau) return fail(ctx, TP_ERR_INVALID_ARG, "srs_from_secret: null argument");
+  size_t len = gates + 3;
+  tp_srs* s = new tp_srs();
+  cudaError_t e = cudaMalloc(&s->g1, len * sizeof(G1Affine));
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(ctx, TP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  s->len = len;
+  HFr t;
+  memcpy(t.v, tau, 32);
+  int rc = srs_generate_dev(ctx, t, len, s->g1);
+  if (rc != TP_OK) {
+    cudaFree(s->g1);
+    delete s;
+    return rc;
+  }
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = s;
+  return TP_OK;
+}
+int tp_srs_upload(tp_ctx* ctx, const uint8_t* g1_xy, size_t len, tp_srs** out) {
+  if (!out || (!g1_xy && len)) return fail(ctx, TP_ERR_INVALID_ARG, "srs_upload: null argument");
+  tp_srs* s = new tp_srs();
+  cudaError_t e = cudaMalloc(&s->g1, (len ? len : 1) * sizeof(G1Affine));
+  if (e != cudaSuccess) {
+    delete s;
+    return fail(ctx, TP_ERR_CUDA, cudaGetErrorString(e));
+  }
+  s->len = len;
+  TP_TRY(h2d(ctx, s->g1, g1_xy, len * 96));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = s;
+  return TP_OK;
+}
+int tp_srs_len(const tp_srs* srs, size_t* len) {
+  if (!srs || !len) return TP_ERR_INVALID_ARG;
+  *len = srs->len;
+  return TP_OK;
+}
+int tp_srs_g1_download(tp_ctx* ctx, const tp_srs* srs, size_t offset, size_t count, uint8_t* out_xy) {
+  if (offset + count > srs->len) return fail(ctx, TP_ERR_INVALID_ARG, "srs_download: range out of bounds");
+  return d2h_sync(ctx, out_xy, srs->g1 + offset, count * 96);
+}
+int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs) {
+  if (!srs) return TP_OK;
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(srs->g1);
+  delete srs;
+  return TP_OK;
+}
+
+// ---- KZG ------------------------------------------------------------------------------------
+int tp_commit_dev(tp_ctx* ctx, const tp_srs* srs, const void* coeffs_dev, size_t len, uint8_t out[TP_G1_BYTES]) {
+  return msm_dev(ctx, srs, (const Fr*)coeffs_dev, len, out);
+}
+int tp_commit(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, uint8_t out[TP_G1_BYTES]) {
+  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
+  TP_TRY(ensure(ctx, ctx->msm_scalars, (len ? len : 1) * sizeof(Fr)));
+  TP_TRY(h2d(ctx, ctx->msm_scalars.p, coeffs, len * sizeof(Fr)));
+  return msm_dev(ctx, srs, (const Fr*)ctx->msm_scalars.p, len, out);
+}
+int tp_open(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, const uint64_t z[4],
+            uint8_t w_out[TP_G1_BYTES], uint64_t y_out[4]) {
+  if (len == 0) return fail(ctx, TP_ERR_EMPTY_POLY, "open: empty polynomial");
+  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "open: polynomial longer than the SRS");
+  TP_TRY(ensure(ctx, ctx->msm_scalars, len * sizeof(Fr)));
+  TP_TRY(ensure(ctx, ctx->misc[3], len * sizeof(Fr)));
+  TP_TRY(h2d(ctx, ctx->misc[3].p, coeffs, len * sizeof(Fr)));
+  Fr zd;
+  memcpy(zd.v, z, 32);
+  HFr y;
+  TP_TRY(poly_open_dev(ctx, (const Fr*)ctx->misc[3].p, len, zd, (Fr*)ctx->msm_scalars.p, &y));
+  memcpy(y_out, y.v, 32);
+  return msm_dev(ctx, srs, (const Fr*)ctx->msm_scalars.p, len - 1, w_out);
+}
+
+// ---- NTT ------------------------------------------------------------------------------------
+int tp_ntt_dev(tp_ctx* ctx, void* data_dev, unsigned log_n, int inverse, const uint64_t* coset) {
+  return ntt_dev(ctx, (const Fr*)data_dev, (Fr*)data_dev, log_n, inverse != 0, coset);
+}
+int tp_ntt(tp_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, const uint64_t* coset) {
+  if (log_n > 28) return fail(ctx, TP_ERR_INVALID_ARG, "ntt: log_n > 28");
+  size_t n = (size_t)1 << log_n;
+  TP_TRY(ensure(ctx, ctx->misc[3], n * sizeof(Fr)));
+  TP_TRY(h2d(ctx, ctx->misc[3].p, data, n * sizeof(Fr)));
+  TP_TRY(ntt_dev(ctx, (const Fr*)ctx->misc[3].p, (Fr*)ctx->misc[3].p, log_n, inverse != 0, coset));
+  return d2h_sync(ctx, data, ctx->misc[3].p, n * sizeof(Fr));
+}
+
+// ---- permutation ------------------------------------------------------------------------------
+int tp_perm_prove(tp_ctx* ctx, const uint64_t* const values[3], const uint64_t* const id[3],
+                  const uint64_t* const sigma[3], size_t n, const uint64_t beta[4], const uint64_t gamma[4],
+                  uint64_t* out) {
+  if (n == 0) return fail(ctx, TP_ERR_INVALID_ARG, "perm_prove: n == 0");
+  TP_TRY(ensure(ctx, ctx->misc[4], 9 * n * sizeof(Fr)));
+  TP_TRY(ensure(ctx, ctx->misc[5], (n + 1) * sizeof(Fr)));
+  Fr* base = (Fr*)ctx->misc[4].p;
+  const Fr *v[3], *i_[3], *s[3];
+  for (int k = 0; k < 3; k++) {
+    TP_TRY(h2d(ctx, base + (size_t)k * n, values[k], n * sizeof(Fr)));
+    TP_TRY(h2d(ctx, base + (size_t)(3 + k) * n, id[k], n * sizeof(Fr)));
+    TP_TRY(h2d(ctx, base + (size_t)(6 + k) * n, sigma[k], n * sizeof(Fr)));
+    v[k] = base + (size_t)k * n;
+    i_[k] = base + (size_t)(3 + k) * n;
+    s[k] = base + (size_t)(6 + k) * n;
+  }
+  Fr b, g;
+  memcpy(b.v, beta, 32);
+  memcpy(g.v, gamma, 32);
+  TP_TRY(perm_grand_product_dev(ctx, v, i_, s, n, b, g, (Fr*)ctx->misc[5].p));
+  return d2h_sync(ctx, out, ctx->misc[5].p, (n + 1) * sizeof(Fr));
+}
+
+// ---- circuit ------------------------------------------------------------------------------------
+static int circuit_alloc(tp_ctx* ctx, tp_circuit* c) {
+  size_t n = c->n;
+  for (int i = 0; i < 5; i++) {
+    TP_TRY(dmalloc(ctx, c, &c->sel_coef[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->sel_eval[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->sel4[i], 4 * n));
+  }
+  for (int i = 0; i < 3; i++) {
+    TP_TRY(dmalloc(ctx, c, &c->id[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->sig_eval[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->sig_coef[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->sig4[i], 4 * n));
+    TP_TRY(dmalloc(ctx, c, &c->adv_eval[i], n));
+    TP_TRY(dmalloc(ctx, c, &c->adv_coef[i], n));
+  }
+  TP_TRY(dmalloc(ctx, c, &c->l0_4, 4 * n));
+  TP_TRY(dmalloc(ctx, c, &c->pi_eval, n));
+  TP_TRY(dmalloc(ctx, c, &c->pi_coef, n));
+  TP_TRY(dmalloc(ctx, c, &c->z_eval, n + 1));
+  TP_TRY(dmalloc(ctx, c, &c->z_coef, n));
+  for (int i = 0; i < 6; i++) TP_TRY(dmalloc(ctx, c, &c->buf4[i], 4 * n));
+  TP_TRY(dmalloc(ctx, c, &c->t, 3 * n));
+  TP_TRY(dmalloc(ctx, c, &c->q, n));
+  TP_TRY(dmalloc(ctx, c, &c->r, n));
+  return TP_OK;
+}
+
+static int to_4n(tp_ctx* ctx, tp_circuit* c, const Fr* coef, Fr* out4) {
+  TP_TRY(pad_copy_dev(ctx, coef, c->n, out4, 4 * c->n));
+  return ntt_dev(ctx, out4, out4, c->log_n + 2, false, nullptr);
+}
+
+// derived data once sel_coef, id, sig_eval, k are in place
+static int circuit_finish(tp_ctx* ctx, tp_circuit* c) {
+  for (int i = 0; i < 5; i++) {
+    TP_TRY(ntt_dev(ctx, c->sel_coef[i], c->sel_eval[i], c->log_n, false, nullptr));
+    TP_TRY(to_4n(ctx, c, c->sel_coef[i], c->sel4[i]));
+  }
+  for (int i = 0; i < 3; i++) {
+    TP_TRY(ntt_dev(ctx, c->sig_eval[i], c->sig_coef[i], c->log_n, true, nullptr));
+    TP_TRY(to_4n(ctx, c, c->sig_coef[i], c->sig4[i]));
+  }
+  const Fr* tw4;
+  TP_TRY(ntt_get_twiddles(ctx, c->log_n + 2, &tw4));
+  TP_TRY(l0_evals_4n_dev(ctx, tw4, c->n, c->l0_4));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TP_OK;
+}
+
+static int circuit_new(tp_ctx* ctx, const tp_srs* srs, size_t n, tp_circuit** out) {
+  if (!out || !srs) return fail(ctx, TP_ERR_INVALID_ARG, "circuit: null argument");
+  if (n < 2 || (n & (n - 1)) != 0 || n > ((size_t)1 << 26)) return fail(ctx, TP_ERR_INVALID_ARG, "circuit: n must be a power of two in [2, 2^26]");
+  if (srs->len < n) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "circuit: SRS shorter than the domain");
+  tp_circuit* c = new tp_circuit();
+  c->n = n;
+  c->log_n = log2_exact(n);
+  c->srs = srs;
+  int rc = circuit_alloc(ctx, c);
+  if (rc != TP_OK) {
+    for (void* p : c->allocs) cudaFree(p);
+    delete c;
+    return rc;
+  }
+  *out = c;
+  return TP_OK;
+}
+
+int tp_circuit_destroy(tp_ctx* ctx, tp_circuit* c) {
+  if (!c) return TP_OK;
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : c->allocs) cudaFree(p);
+  delete c;
+  return TP_OK;
+}
+
+int tp_circuit_load(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selectors[5], const uint64_t* const id[3],
+                    const uint64_t* const sigma[3], const uint64_t cosets[3][4], size_t n, tp_circuit** out) {
+  tp_circuit* c = nullptr;
+  TP_TRY(circuit_new(ctx, srs, n, &c));
+  int rc = TP_OK;
+  for (int i = 0; i < 5 && rc == TP_OK; i++) rc = h2d(ctx, c->sel_coef[i], selectors[i], n * sizeof(Fr));
+  for (int i = 0; i < 3 && rc == TP_OK; i++) {
+    rc = h2d(ctx, c->id[i], id[i], n * sizeof(Fr));
+    if (rc == TP_OK) rc = h2d(ctx, c->sig_eval[i], sigma[i], n * sizeof(Fr));
+    memcpy(c->k[i].v, cosets[i], 32);
+  }
+  if (rc == TP_OK) rc = circuit_finish(ctx, c);
+  if (rc != TP_OK) {
+    tp_circuit_destroy(ctx, c);
+    return rc;
+  }
+  *out = c;
+  return TP_OK;
+}
+
+int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selector_evals[5], const uint64_t* perm,
+                       size_t n, tp_circuit** out, uint8_t fixed_commitments[5 * TP_G1_BYTES]) {
+  tp_circuit* c = nullptr;
+  TP_TRY(circuit_new(ctx, srs, n, &c));
+  int rc = TP_OK;
+  // cosets (permutation/src/lib.rs:141-154): first three k >= 1 with k^n != 1
+  {
+    uint64_t kv = 1;
+    for (int i = 0; i < 3; i++) {
+      while (HFr::from_u64(kv).pow_u64((uint64_t)n) == HFr::one()) kv++;
+      c->k[i] = HFr::from_u64(kv);
+      kv++;
+    }
+  }
+  // selectors: evaluations -> coefficients (builder.rs:84-86), then commit
+  for (int i = 0; i < 5 && rc == TP_OK; i++) {
+    rc = h2d(ctx, c->sel_eval[i], selector_evals[i], n * sizeof(Fr));
+    if (rc == TP_OK) rc = ntt_dev(ctx, c->sel_eval[i], c->sel_coef[i], c->log_n, true, nullptr);
+    if (rc == TP_OK && fixed_commitments) rc = msm_dev(ctx, srs, c->sel_coef[i], n, fixed_commitments + i * TP_G1_BYTES);
+  }
+  // sigma / id tables (permutation/src/lib.rs:101-128)
+  if (rc == TP_OK) {
+    uint64_t* perm_dev = (uint64_t*)c->buf4[0];  // 3n u64 fits in a 4n Fr buffer
+    rc = h2d(ctx, perm_dev, perm, 3 * n * sizeof(uint64_t));
+    const Fr* tw;
+    if (rc == TP_OK) rc = ntt_get_twiddles(ctx, c->log_n, &tw);
+    Fr kd[3] = {to_dev(c->k[0]), to_dev(c->k[1]), to_dev(c->k[2])};
+    if (rc == TP_OK) rc = sigma_tables_dev(ctx, perm_dev, n, tw, kd, c->id, c->sig_eval);
+  }
+  if (rc == TP_OK) rc = circuit_finish(ctx, c);
+  if (rc != TP_OK) {
+    tp_circuit_destroy(ctx, c);
+    return rc;
+  }
+  *out = c;
+  return TP_OK;
+}
+
+int tp_circuit_sigma_commitments(tp_ctx* ctx, tp_circuit* c, uint8_t out[3 * TP_G1_BYTES]) {
+  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, c->srs, c->sig_coef[i], c->n, out + i * TP_G1_BYTES));
+  return TP_OK;
+}
+
+// ---- prover -----------------------------------------------------------------------------------
+static void put_g1(uint8_t*& w, const uint8_t pt[TP_G1_BYTES]) {
+  tph::serialize_g1_unchecked(pt, w);
+  w += 96;
+}
+static void put_fr(uint8_t*& w, const HFr& x) {
+  HFr c = x.from_mont();
+  memcpy(w, c.v, 32);
+  w += 32;
+}
+
+static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
+  const size_t n = c->n;
+  const tp_srs* srs = c->srs;
+  // witness + public-input polynomials (proof.rs:50, 105-106)
+  for (int i = 0; i < 3; i++) TP_TRY(ntt_dev(ctx, c->adv_eval[i], c->adv_coef[i], c->log_n, true, nullptr));
+  TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
+  // round 1 commitments (proof.rs:107-110)
+  uint8_t com[4][TP_G1_BYTES];
+  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, srs, c->adv_coef[i], n, com[i]));
+  HFr beta, gamma;
+  tph::challenges2({com[0], com[1], com[2]}, &beta, &gamma);
+  // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321)
+  {
+    bool ok = false;
+    const Fr* sel[5] = {c->sel_eval[0], c->sel_eval[1], c->sel_eval[2], c->sel_eval[3], c->sel_eval[4]};
+    const Fr* adv[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
+    TP_TRY(gate_check_dev(ctx, sel, adv, c->pi_eval, n, &ok));
+    if (!ok) return fail(ctx, TP_ERR_GATE_UNSATISFIED, "prove: gate constraints do not vanish on the domain");
+  }
+  // grand product z (proof.rs:117-131)
+  {
+    const Fr* v[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
+    const Fr* idp[3] = {c->id[0], c->id[1], c->id[2]};
+    const Fr* sg[3] = {c->sig_eval[0], c->sig_eval[1], c->sig_eval[2]};
+    TP_TRY(perm_grand_product_dev(ctx, v, idp, sg, n, to_dev(beta), to_dev(gamma), c->z_eval));
+  }
+  TP_TRY(ntt_dev(ctx, c->z_eval, c->z_coef, c->log_n, true, nullptr));
+  TP_TRY(msm_dev(ctx, srs, c->z_coef, n, com[3]));
+  HFr alpha, zeta;
+  tph::challenges2({com[0], com[1], com[2], com[3]}, &alpha, &zeta);
+
+  // quotient (proof.rs:292-375) on the 4n domain
+  {
+    const Fr* src[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->pi_coef};
+    for (int i = 0; i < 5; i++) TP_TRY(to_4n(ctx, c, src[i], c->buf4[i]));
+    QuotientArgs qa;
+    for (int i = 0; i < 5; i++) qa.sel4[i] = c->sel4[i];
+    for (int i = 0; i < 3; i++) {
+      qa.sig4[i] = c->sig4[i];
+      qa.adv4[i] = c->buf4[i];
+      qa.k[i] = to_dev(c->k[i]);
+    }
+    qa.z4 = c->buf4[3];
+    qa.pi4 = c->buf4[4];
+    qa.l0_4 = c->l0_4;
+    TP_TRY(ntt_get_twiddles(ctx, c->log_n + 2, &qa.tw4));
+    qa.alpha = to_dev(alpha);
+    qa.beta = to_dev(beta);
+    qa.gamma = to_dev(gamma);
+    qa.out = c->buf4[5];
+    qa.n = n;
+    TP_TRY(quotient_numerator_dev(ctx, qa));
+    TP_TRY(ntt_dev(ctx, c->buf4[5], c->buf4[5], c->log_n + 2, true, nullptr));
+    TP_TRY(divide_by_vanishing_dev(ctx, c->buf4[5], n, c->t));
+  }
+
+  // openings (proof.rs:147-163)
+  uint8_t wit[6][TP_G1_BYTES];
+  HFr ev[5];
+  HFr omega = omega_for_log(c->log_n);
+  const Fr* polys[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->z_coef};
+  HFr points[5] = {zeta, zeta, zeta, zeta, zeta * omega};
+  for (int i = 0; i < 5; i++) {
+    TP_TRY(poly_open_dev(ctx, polys[i], n, to_dev(points[i]), c->q, &ev[i]));
+    TP_TRY(msm_dev(ctx, srs, c->q, n - 1, wit[i]));
+  }
+  // linearisation (proof.rs:376-439)
+  HFr sig_bar[2], pi_bar;
+  for (int i = 0; i < 2; i++) TP_TRY(poly_open_dev(ctx, c->sig_coef[i], n, to_dev(zeta), nullptr, &sig_bar[i]));
+  TP_TRY(poly_open_dev(ctx, c->pi_coef, n, to_dev(zeta), nullptr, &pi_bar));
+  HFr a = ev[0], b = ev[1], cc = ev[2], zw = ev[4];
+  HFr l2 = HFr::one();
+  for (int i = 0; i < 3; i++) l2 = l2 * (ev[i] + c->k[i] * beta * zeta + gamma);
+  HFr perm_ab = (a + beta * sig_bar[0] + gamma) * (b + beta * sig_bar[1] + gamma);
+  HFr zn = zeta.pow_u64((uint64_t)n);
+  HFr zh = zn - HFr::one();
+  HFr l0;
+  if (zeta == HFr::one()) {
+    l0 = HFr::one();
+  } else {
+    l0 = zh * (HFr::from_u64((uint64_t)n) * (zeta - HFr::one())).inv();
+  }
+  HFr alpha2 = alpha.sqr();
+  HFr ab_zw = alpha * perm_ab * zw;
+  LinTerm terms[10];
+  terms[0] = {c->sel_coef[0], to_dev(a)};
+  terms[1] = {c->sel_coef[1], to_dev(b)};
+  terms[2] = {c->sel_coef[2], to_dev(cc.neg())};
+  terms[3] = {c->sel_coef[3], to_dev(a * b)};
+  terms[4] = {c->sel_coef[4], to_dev(HFr::one())};
+  terms[5] = {c->z_coef, to_dev(alpha * l2 + alpha2 * l0)};
+  terms[6] = {c->sig_coef[2], to_dev((ab_zw * beta).neg())};
+  terms[7] = {c->t, to_dev(zh.neg())};
+  terms[8] = {c->t + n, to_dev((zh * zn).neg())};
+  terms[9] = {c->t + 2 * n, to_dev((zh * zn * zn).neg())};
+  HFr constant = pi_bar - ab_zw * (gamma + cc) - alpha2 * l0;
+  TP_TRY(lincomb_dev(ctx, terms, 10, to_dev(constant), n, c->r));
+  HFr r_bar;
+  TP_TRY(poly_open_dev(ctx, c->r, n, to_dev(zeta), c->q, &r_bar));
+  TP_TRY(msm_dev(ctx, srs, c->q, n - 1, wit[5]));
+  // t commitments (proof.rs:181)
+  uint8_t tcom[3][TP_G1_BYTES];
+  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, srs, c->t + (size_t)i * n, n, tcom[i]));
+
+  uint8_t* w = proof_out;
+  for (int i = 0; i < 3; i++) {
+    put_g1(w, com[i]);
+    put_g1(w, wit[i]);
+    put_fr(w, ev[i]);
+  }
+  put_g1(w, com[3]);
+  put_g1(w, wit[3]);
+  put_fr(w, ev[3]);
+  put_g1(w, wit[4]);
+  put_fr(w, ev[4]);
+  put_fr(w, zeta);
+  for (int i = 0; i < 3; i++) put_g1(w, tcom[i]);
+  put_g1(w, wit[5]);
+  put_fr(w, r_bar);
+  return TP_OK;
+}
+
+int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
+                 uint8_t* proof_out, size_t proof_cap) {
+  if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
+  size_t bytes = c->n * sizeof(Fr);
+  for (int i = 0; i < 3; i++)
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(c->adv_eval[i], advice_dev[i], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(c->pi_eval, public_inputs_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return prove_resident(ctx, c, proof_out);
+}
+int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+             uint8_t* proof_out, size_t proof_cap) {
+  if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
+  size_t bytes = c->n * sizeof(Fr);
+  for (int i = 0; i < 3; i++) TP_TRY(h2d(ctx, c->adv_eval[i], advice[i], bytes));
+  TP_TRY(h2d(ctx, c->pi_eval, public_inputs, bytes));
+  return prove_resident(ctx, c, proof_out);
+}
+
+// ---- helpers -------------------------------------------------------------------------------------
+int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s) {
+  return measure_imad_dev(ctx, imad_per_s, imad_wide_per_s);
+}
+int tp_selftest(tp_ctx* ctx, int* failures) { return selftest_dev(ctx, failures); }
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+// Internal shared declarations of libtyplonk_b200: context, device buffers, error plumbing,
+// and the device-level entry points each .cu exports to the prover driver.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/typlonk_b200.h"
+#include "ec.cuh"
+#include "field.cuh"
+#include "host_field.h"
+
+namespace tp {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct NttTables {
+  Fr* tw = nullptr;  // omega_N^i, i in [0, N/2]
+};
+struct CosetTable {
+  unsigned log_n;
+  uint64_t g[4];
+  Fr* lo = nullptr;  // g^i, i < 2^LO
+  Fr* hi = nullptr;  // g^(i << LO)
+};
+
+}  // namespace tp
+
+struct tp_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  int sm_count = 148;
+  uint64_t launches = 0;
+  // sharding
+  int rank = 0, world = 1;
+  tp_allgather_fn allgather = nullptr;
+  void* allgather_user = nullptr;
+  // profiling
+  bool prof = false;
+  double prof_ms[TP_PHASE_COUNT] = {0};
+  uint64_t prof_launch[TP_PHASE_COUNT] = {0};
+  struct Pending {
+    int phase;
+    cudaEvent_t a, b;
+    uint64_t launches;
+  };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> event_pool;
+  // caches
+  std::map<unsigned, tp::NttTables> ntt_tables;
+  std::vector<tp::CosetTable> coset_tables;
+  // scratch
+  tp::DevBuf ntt_scratch;
+  tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_sorted, msm_sorted_keys, msm_hist, msm_offsets, msm_blocksums,
+      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums;
+  tp::DevBuf scan_tmp[8];
+  tp::DevBuf misc[16];
+  tp::DevBuf flag;
+  void* pinned = nullptr;  // small pinned staging area
+  size_t pinned_cap = 0;
+  void* fixed_base = nullptr;  // 32 x 255 affine multiples of G for SRS generation
+};
+
+struct tp_srs {
+  tp::G1Affine* g1 = nullptr;  // device, packed 96 B
+  size_t len = 0;
+};
+
+namespace tp {
+
+#define TP_CUDA_OK(ctx, call)                                                                   \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                         \
+      return TP_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+#define TP_TRY(expr)             \
+  do {                           \
+    int rc__ = (expr);           \
+    if (rc__ != TP_OK) return rc__; \
+  } while (0)
+
+inline int fail(tp_ctx* ctx, int code, const char* msg) {
+  ctx->err = msg;
+  return code;
+}
+
+// grow-only device buffer
+inline int ensure(tp_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return TP_OK;
+  if (b.p) {
+    TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    TP_CUDA_OK(ctx, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t want = bytes < 256 ? 256 : bytes;
+  TP_CUDA_OK(ctx, cudaMalloc(&b.p, want));
+  b.cap = want;
+  return TP_OK;
+}
+inline void release(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+inline int check_launch(tp_ctx* ctx, const char* what) {
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return TP_ERR_CUDA;
+  }
+  return TP_OK;
+}
+#define TP_LAUNCH(ctx, name) TP_TRY(tp::check_launch(ctx, name))
+
+// ---- profiling scopes (CUDA events on the ctx stream) ---------------------------------
+struct ProfScope {
+  tp_ctx* ctx;
+  int idx = -1;
+  ProfScope(tp_ctx* c, int phase) : ctx(c) {
+    if (!c->prof) return;
+    tp_ctx::Pending p;
+    p.phase = phase;
+    auto get = [&]() {
+      cudaEvent_t e;
+      if (!c->event_pool.empty()) {
+        e = c->event_pool.back();
+        c->event_pool.pop_back();
+      } else {
+        cudaEventCreate(&e);
+      }
+      return e;
+    };
+    p.a = get();
+    p.b = get();
+    p.launches = c->launches;
+    cudaEventRecord(p.a, c->stream);
+    c->pending.push_back(p);
+    idx = (int)c->pending.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx < 0) return;
+    auto& p = ctx->pending[idx];
+    cudaEventRecord(p.b, ctx->stream);
+    p.launches = ctx->launches - p.launches;
+  }
+};
+
+// ---- device-level entry points (each implemented in its own .cu) -----------------------
+// ntt.cu
+int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset);
+int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw);
+// msm.cu : result as host Jacobian (this rank's shard only when sharded = false, else combined)
+int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]);
+void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]);
+// poly.cu
+int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],
+                           size_t n, const Fr& beta, const Fr& gamma, Fr* out /* n+1 */);
+// q[k-1] = p[k] + z q[k]; writes q (len-1 coeffs, then a zero at [len-1]) and returns y = p(z)
+int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out /* len, may be null */, tph::HFr* y);
+int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
+                   bool* ok);
+struct QuotientArgs {
+  const Fr* sel4[5];   // 4n evaluations
+  const Fr* sig4[3];
+  const Fr* adv4[3];
+  const Fr* z4;
+  const Fr* pi4;
+  const Fr* l0_4;      // L0 on the 4n domain
+  const Fr* tw4;       // omega_4n^i, i in [0, 2n]
+  Fr alpha, beta, gamma;
+  Fr k[3];
+  Fr* out;             // 4n numerator evaluations
+  size_t n;
+};
+int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a);
+// t[k] = sum_{m>=1} c[k + m n] for k < 3n from the 4n numerator coefficients
+int divide_by_vanishing_dev(tp_ctx* ctx, const Fr* c4, size_t n, Fr* t /* 3n */);
+int l0_evals_4n_dev(tp_ctx* ctx, const Fr* tw4, size_t n, Fr* out /* 4n */);
+struct LinTerm {
+  const Fr* p;
+  Fr s;
+};
+int lincomb_dev(tp_ctx* ctx, const LinTerm* terms, int nterms, const Fr& constant, size_t n, Fr* out);
+int sigma_tables_dev(tp_ctx* ctx, const uint64_t* perm_dev, size_t n, const Fr* tw, const Fr k[3], Fr* id[3],
+                     Fr* sigma[3]);
+int pad_copy_dev(tp_ctx* ctx, const Fr* in, size_t len, Fr* out, size_t out_len);
+int rotate_copy_dev(tp_ctx* ctx, const Fr* in, size_t n, size_t shift, Fr* out);
+// srs.cu
+int srs_generate_dev(tp_ctx* ctx, const tph::HFr& tau, size_t len, G1Affine* out);
+// selftest.cu
+int selftest_dev(tp_ctx* ctx, int* failures);
+int measure_imad_dev(tp_ctx* ctx, double* imad, double* wide);
+
+inline Fr to_dev(const tph::HFr& h) {
+  Fr r;
+  memcpy(r.v, h.v, 32);
+  return r;
+}
+inline tph::HFr to_host(const Fr& d) {
+  tph::HFr r;
+  memcpy(r.v, d.v, 32);
+  return r;
+}
+
+}  // namespace tp

@@ -1,0 +1,414 @@
+// KZG commit as a Pippenger G1 multi-scalar multiplication for sm_100a.
+//
+// Replaces `KzgScheme::evaluate_in_s` (kzg/src/lib.rs:41-54), which the reference computes as
+// n independent double-and-add scalar multiplications folded with `Sum`.  The affine result of
+// a group sum is unique, so the bucket method is bit-exact with it.
+//
+// Pipeline (all on the ctx stream):
+//   1. k_msm_digits   : scalar Montgomery -> canonical, signed-digit windows of c bits; each
+//                       non-zero digit takes a rank in its bucket with one atomicAdd
+//                       (histogram and within-bucket rank in a single pass)
+//   2. k_scan_*       : exclusive scan of the bucket histogram -> bucket offsets
+//   3. k_msm_scatter  : counting-sort scatter of (point index | sign) and bucket key
+//   4. k_msm_accumulate: load-balanced segmented accumulation -- every thread owns a fixed-size
+//                       chunk of the sorted entries (not a bucket), adds SRS points in XYZZ mixed
+//                       coordinates, writes complete runs straight to their bucket and emits
+//                       head/tail partials for runs that cross chunk boundaries
+//   5. k_msm_merge    : stitches the boundary partials
+//   6. k_msm_bucket_reduce / k_msm_window_reduce: running-sum reduction of each window in
+//                       parallel segments, then a shared-memory tree
+//   7. host           : Horner over the <= 64 window sums + affine conversion (serial tail; one
+//                       CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic), and
+//                       the all-gather of partial points when the MSM is sharded over GPUs.
+#include "common.cuh"
+
+namespace tp {
+
+#define MSM_CHUNK 16          // sorted entries per accumulate thread
+#define MSM_SEG 32            // buckets per bucket-reduce thread
+#define MSM_NONE 0x7fffffffu
+
+struct MsmPlan {
+  unsigned c;        // window bits
+  unsigned nwin;     // number of windows
+  unsigned nbuck;    // buckets per window = 2^(c-1)
+};
+
+static MsmPlan msm_plan(size_t n) {
+  MsmPlan best = {0, 0, 0};
+  double best_cost = 1e300;
+  for (unsigned c = 2; c <= 21; c++) {
+    unsigned nwin = (255 + c - 1) / c;
+    unsigned top_bits = 255 - (nwin - 1) * c;
+    if (top_bits == c) nwin++;  // signed carry out of a full top window
+    double nb = (double)(1u << (c - 1));
+    double cost = (double)n * nwin * 10.0 + nwin * nb * 40.0 + nwin * 3000.0;
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = {c, nwin, 1u << (c - 1)};
+    }
+  }
+  return best;
+}
+
+// ---- 1. digits + histogram/rank ----------------------------------------------------------
+__global__ void k_msm_digits(const Fr* __restrict__ scalars, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
+                             unsigned* __restrict__ hist, unsigned* __restrict__ keys, unsigned* __restrict__ ranks) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fr_from_mont(fr_load(scalars + i));
+  unsigned carry = 0;
+  for (unsigned w = 0; w < nwin; w++) {
+    unsigned bit = w * c;
+    unsigned raw = 0;
+    if (bit < 256) {
+      unsigned limb = bit >> 5, off = bit & 31;
+      unsigned long long two = s.v[limb];
+      if (limb + 1 < 8) two |= (unsigned long long)s.v[limb + 1] << 32;
+      raw = (unsigned)(two >> off) & ((1u << c) - 1);
+    }
+    raw += carry;
+    unsigned key = MSM_NONE, rank = 0;
+    carry = 0;
+    if (raw != 0) {
+      unsigned mag = raw, neg = 0;
+      if (raw > (1u << (c - 1))) {
+        mag = (1u << c) - raw;
+        neg = 1;
+        carry = 1;
+      }
+      if (mag != 0) {
+        unsigned k = w * nbuck + (mag - 1);
+        rank = atomicAdd(&hist[k], 1u);
+        key = k | (neg << 31);
+      }
+    }
+    keys[(size_t)w * n + i] = key;
+    ranks[(size_t)w * n + i] = rank;
+  }
+}
+
+// ---- 2. exclusive scan of u32 (3 kernels) --------------------------------------------------
+#define SCAN_BLOCK 1024
+__global__ void k_scan_local(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned* __restrict__ sums,
+                             size_t n) {
+  __shared__ unsigned s[SCAN_BLOCK];
+  size_t g = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  unsigned v = g < n ? in[g] : 0;
+  s[threadIdx.x] = v;
+  __syncthreads();
+  for (unsigned d = 1; d < SCAN_BLOCK; d <<= 1) {
+    unsigned t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+    __syncthreads();
+    s[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (g < n) out[g] = s[threadIdx.x] - v;
+  if (threadIdx.x == SCAN_BLOCK - 1) sums[blockIdx.x] = s[threadIdx.x];
+}
+__global__ void k_scan_sums(unsigned* sums, size_t nblocks) {
+  // single block, serial over tiles of SCAN_BLOCK
+  __shared__ unsigned s[SCAN_BLOCK];
+  __shared__ unsigned carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (size_t base = 0; base < nblocks; base += SCAN_BLOCK) {
+    size_t g = base + threadIdx.x;
+    unsigned v = g < nblocks ? sums[g] : 0;
+    s[threadIdx.x] = v;
+    __syncthreads();
+    for (unsigned d = 1; d < SCAN_BLOCK; d <<= 1) {
+      unsigned t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+      __syncthreads();
+      s[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (g < nblocks) sums[g] = s[threadIdx.x] - v + carry;
+    __syncthreads();
+    if (threadIdx.x == SCAN_BLOCK - 1) carry += s[threadIdx.x];
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(unsigned* out, const unsigned* sums, size_t n) {
+  size_t g = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
+  if (g < n) out[g] += sums[blockIdx.x];
+}
+
+// ---- 3. scatter ----------------------------------------------------------------------------
+__global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
+                              const unsigned* __restrict__ offsets, size_t n, size_t total,
+                              unsigned* __restrict__ sorted_idx, unsigned* __restrict__ sorted_key) {
+  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  unsigned key = keys[e];
+  if ((key & MSM_NONE) == MSM_NONE) return;
+  unsigned k = key & MSM_NONE;
+  unsigned pos = offsets[k] + ranks[e];
+  unsigned i = (unsigned)(e % n);
+  sorted_idx[pos] = i | (key & 0x80000000u);
+  sorted_key[pos] = k;
+}
+
+// ---- 4. segmented accumulation ---------------------------------------------------------------
+// part_keys[2t], part_keys[2t+1]: keys of the head / tail partial of chunk t (MSM_NONE if absent)
+__global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* __restrict__ bases,
+                                                        const unsigned* __restrict__ sorted_idx,
+                                                        const unsigned* __restrict__ sorted_key, unsigned m_total,
+                                                        G1Xyzz* __restrict__ buckets, unsigned* __restrict__ part_keys,
+                                                        G1Xyzz* __restrict__ part_pts) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned start = t * MSM_CHUNK;
+  if (start >= m_total) return;
+  unsigned end = start + MSM_CHUNK < m_total ? start + MSM_CHUNK : m_total;
+  G1Xyzz acc = xyzz_identity();
+  unsigned cur = sorted_key[start];
+  bool is_first_run = true;
+  part_keys[2 * t + 1] = MSM_NONE;
+  for (unsigned e = start; e < end; e++) {
+    unsigned key = sorted_key[e];
+    if (key != cur) {
+      if (is_first_run) {
+        part_keys[2 * t] = cur;
+        xyzz_store(part_pts + 2 * t, acc);
+        is_first_run = false;
+      } else {
+        xyzz_store(buckets + cur, acc);  // complete interior run: exclusive owner of the bucket
+      }
+      acc = xyzz_identity();
+      cur = key;
+    }
+    unsigned idx = sorted_idx[e];
+    G1Affine p = affine_load(bases + (idx & 0x7fffffffu));
+    if (!affine_is_identity(p)) xyzz_madd(acc, p, (idx >> 31) != 0);
+  }
+  if (is_first_run) {
+    part_keys[2 * t] = cur;
+    xyzz_store(part_pts + 2 * t, acc);
+  } else {
+    part_keys[2 * t + 1] = cur;
+    xyzz_store(part_pts + 2 * t + 1, acc);
+  }
+}
+
+// ---- 5. boundary merge -----------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_msm_merge(const unsigned* __restrict__ part_keys,
+                                                   const G1Xyzz* __restrict__ part_pts, unsigned nslots,
+                                                   G1Xyzz* __restrict__ buckets) {
+  unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nslots) return;
+  unsigned key = part_keys[j];
+  if (key == MSM_NONE) return;
+  // owner <=> previous valid slot has a different key
+  if (j > 0) {
+    unsigned pk = part_keys[j - 1];
+    if (pk == MSM_NONE && j > 1) pk = part_keys[j - 2];
+    if (pk == key) return;
+  }
+  G1Xyzz acc = xyzz_load(part_pts + j);
+  for (unsigned q = j + 1; q < nslots; q++) {
+    unsigned k2 = part_keys[q];
+    if (k2 == MSM_NONE) continue;
+    if (k2 != key) break;
+    G1Xyzz o = xyzz_load(part_pts + q);
+    xyzz_add(acc, o);
+  }
+  xyzz_store(buckets + key, acc);
+}
+
+// ---- 6. bucket reduction ---------------------------------------------------------------------
+// Each thread reduces MSM_SEG consecutive buckets of one window: sum_v v * B_v over its segment.
+__global__ void __launch_bounds__(128) k_msm_bucket_reduce(const G1Xyzz* __restrict__ buckets,
+                                                           const unsigned* __restrict__ hist, unsigned nbuck,
+                                                           unsigned seg_len, unsigned segs_per_win, unsigned nwin,
+                                                           G1Xyzz* __restrict__ seg_out) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= segs_per_win * nwin) return;
+  unsigned w = t / segs_per_win, sidx = t % segs_per_win;
+  unsigned lo = sidx * seg_len;  // bucket index b holds value v = b + 1
+  G1Xyzz running = xyzz_identity(), total = xyzz_identity();
+  for (int b = (int)seg_len - 1; b >= 0; b--) {
+    unsigned k = w * nbuck + lo + b;
+    if (hist[k] != 0) {
+      G1Xyzz p = xyzz_load(buckets + k);
+      xyzz_add(running, p);
+    }
+    xyzz_add(total, running);
+  }
+  // total = sum (b+1) B ; add lo * running
+  if (lo != 0) {
+    xyzz_mul_small(running, lo);
+    xyzz_add(total, running);
+  }
+  xyzz_store(seg_out + t, total);
+}
+// One CTA per window: strided serial sum then shared-memory tree.
+__global__ void __launch_bounds__(128) k_msm_window_reduce(const G1Xyzz* __restrict__ seg, unsigned segs_per_win,
+                                                           G1Xyzz* __restrict__ win_out) {
+  __shared__ G1Xyzz sh[128];
+  unsigned w = blockIdx.x;
+  G1Xyzz acc = xyzz_identity();
+  for (unsigned s = threadIdx.x; s < segs_per_win; s += blockDim.x) {
+    G1Xyzz p = xyzz_load(seg + (size_t)w * segs_per_win + s);
+    xyzz_add(acc, p);
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (unsigned d = blockDim.x / 2; d > 0; d >>= 1) {
+    if (threadIdx.x < d) {
+      G1Xyzz a = sh[threadIdx.x];
+      G1Xyzz b = sh[threadIdx.x + d];
+      xyzz_add(a, b);
+      sh[threadIdx.x] = a;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) xyzz_store(win_out + w, sh[0]);
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]) {
+  tph::HFq x, y;
+  if (tph::g1_to_affine(p, &x, &y)) {
+    memcpy(out, x.v, 48);
+    memcpy(out + 48, y.v, 48);
+    out[96] = 0;
+  } else {
+    tph::HFq zero = tph::HFq::zero(), one = tph::HFq::one();
+    memcpy(out, zero.v, 48);
+    memcpy(out + 48, one.v, 48);
+    out[96] = 1;
+  }
+}
+
+static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, size_t n) {
+  size_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  TP_TRY(ensure(ctx, ctx->msm_blocksums, nblocks * sizeof(unsigned)));
+  unsigned* sums = (unsigned*)ctx->msm_blocksums.p;
+  k_scan_local<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n);
+  TP_LAUNCH(ctx, "k_scan_local");
+  k_scan_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nblocks);
+  TP_LAUNCH(ctx, "k_scan_sums");
+  k_scan_add<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(out, sums, n);
+  TP_LAUNCH(ctx, "k_scan_add");
+  return TP_OK;
+}
+
+// This rank's partial sum over SRS points [first, first+len) with the matching scalars.
+static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size_t len, tph::HG1* result) {
+  *result = tph::HG1::identity();
+  if (len == 0) return TP_OK;
+  if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
+  MsmPlan pl = msm_plan(len);
+  size_t nkeys = (size_t)pl.nwin * pl.nbuck;
+  size_t total = (size_t)pl.nwin * len;
+  if (total >= ((size_t)1 << 31)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
+  TP_TRY(ensure(ctx, ctx->msm_hist, (nkeys + 1) * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_offsets, (nkeys + 1) * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_keys, total * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_ranks, total * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_sorted_keys, total * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_buckets, nkeys * sizeof(G1Xyzz)));
+  unsigned* hist = (unsigned*)ctx->msm_hist.p;
+  unsigned* offsets = (unsigned*)ctx->msm_offsets.p;
+  unsigned* keys = (unsigned*)ctx->msm_keys.p;
+  unsigned* ranks = (unsigned*)ctx->msm_ranks.p;
+  unsigned* sorted = (unsigned*)ctx->msm_sorted.p;
+  unsigned* sorted_keys = (unsigned*)ctx->msm_sorted_keys.p;
+  G1Xyzz* buckets = (G1Xyzz*)ctx->msm_buckets.p;
+  unsigned m_total = 0;
+  {
+    ProfScope prof(ctx, TP_PHASE_MSM_SORT);
+    TP_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (nkeys + 1) * sizeof(unsigned), ctx->stream));
+    k_msm_digits<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(scalars, len, pl.c, pl.nwin, pl.nbuck, hist,
+                                                                         keys, ranks);
+    TP_LAUNCH(ctx, "k_msm_digits");
+    TP_TRY(exclusive_scan_u32(ctx, hist, offsets, nkeys + 1));
+    k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, sorted,
+                                                                           sorted_keys);
+    TP_LAUNCH(ctx, "k_msm_scatter");
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    m_total = *(unsigned*)ctx->pinned;
+  }
+  if (m_total == 0) return TP_OK;  // all scalars zero
+  unsigned nchunks = (m_total + MSM_CHUNK - 1) / MSM_CHUNK;
+  TP_TRY(ensure(ctx, ctx->msm_part_keys, (size_t)2 * nchunks * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_part_pts, (size_t)2 * nchunks * sizeof(G1Xyzz)));
+  {
+    ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
+    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, sorted, sorted_keys, m_total, buckets,
+                                                                     (unsigned*)ctx->msm_part_keys.p,
+                                                                     (G1Xyzz*)ctx->msm_part_pts.p);
+    TP_LAUNCH(ctx, "k_msm_accumulate");
+  }
+  unsigned seg_len = pl.nbuck < MSM_SEG ? pl.nbuck : MSM_SEG;
+  unsigned segs_per_win = pl.nbuck / seg_len;
+  TP_TRY(ensure(ctx, ctx->msm_seg, (size_t)segs_per_win * pl.nwin * sizeof(G1Xyzz)));
+  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)pl.nwin * sizeof(G1Xyzz)));
+  {
+    ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
+    k_msm_merge<<<(2 * nchunks + 127) / 128, 128, 0, ctx->stream>>>((unsigned*)ctx->msm_part_keys.p,
+                                                                    (G1Xyzz*)ctx->msm_part_pts.p, 2 * nchunks, buckets);
+    TP_LAUNCH(ctx, "k_msm_merge");
+    unsigned nthreads = segs_per_win * pl.nwin;
+    k_msm_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(buckets, hist, pl.nbuck, seg_len, segs_per_win,
+                                                                         pl.nwin, (G1Xyzz*)ctx->msm_seg.p);
+    TP_LAUNCH(ctx, "k_msm_bucket_reduce");
+    k_msm_window_reduce<<<pl.nwin, 128, 0, ctx->stream>>>((G1Xyzz*)ctx->msm_seg.p, segs_per_win,
+                                                          (G1Xyzz*)ctx->msm_winsums.p);
+    TP_LAUNCH(ctx, "k_msm_window_reduce");
+  }
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)pl.nwin * sizeof(G1Xyzz),
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  // serial tail on the host: result = sum_w 2^(c w) * W_w
+  const uint8_t* ws = (const uint8_t*)ctx->pinned;
+  tph::HG1 acc = tph::HG1::identity();
+  for (int w = (int)pl.nwin - 1; w >= 0; w--) {
+    for (unsigned d = 0; d < pl.c; d++) acc = tph::g1_dbl(acc);
+    tph::HFq x, y, zz, zzz;
+    memcpy(x.v, ws + (size_t)w * 192, 48);
+    memcpy(y.v, ws + (size_t)w * 192 + 48, 48);
+    memcpy(zz.v, ws + (size_t)w * 192 + 96, 48);
+    memcpy(zzz.v, ws + (size_t)w * 192 + 144, 48);
+    acc = tph::g1_add(acc, tph::g1_from_xyzz(x, y, zz, zzz));
+  }
+  *result = acc;
+  return TP_OK;
+}
+
+int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]) {
+  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
+  ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
+  tph::HG1 res;
+  if (ctx->world <= 1) {
+    TP_TRY(msm_local(ctx, srs->g1, scalars_dev, len, &res));
+  } else {
+    // contiguous point-range shard; every rank holds the full SRS and scalar vector
+    size_t per = (len + ctx->world - 1) / ctx->world;
+    size_t first = per * ctx->rank;
+    size_t cnt = first >= len ? 0 : (len - first < per ? len - first : per);
+    tph::HG1 part;
+    TP_TRY(msm_local(ctx, srs->g1 + first, scalars_dev + first, cnt, &part));
+    std::vector<uint8_t> recv((size_t)ctx->world * 144);
+    uint8_t send[144];
+    memcpy(send, part.x.v, 48);
+    memcpy(send + 48, part.y.v, 48);
+    memcpy(send + 96, part.z.v, 48);
+    if (!ctx->allgather || ctx->allgather(ctx->allgather_user, send, recv.data(), 144) != 0)
+      return fail(ctx, TP_ERR_COLLECTIVE, "msm: all-gather of partial points failed");
+    res = tph::HG1::identity();
+    for (int r = 0; r < ctx->world; r++) {
+      tph::HG1 p;
+      memcpy(p.x.v, recv.data() + (size_t)r * 144, 48);
+      memcpy(p.y.v, recv.data() + (size_t)r * 144 + 48, 48);
+      memcpy(p.z.v, recv.data() + (size_t)r * 144 + 96, 48);
+      res = tph::g1_add(res, p);
+    }
+  }
+  encode_g1(res, out);
+  return TP_OK;
+}
+
+}  // namespace tp

@@ -1,0 +1,538 @@
+// Elementwise and scan kernels of the prover (all HBM-streaming integer work over Fr):
+//   * permutation grand product   -- permutation/src/proving.rs:7-31 (one inversion per cell in
+//     the reference) as elementwise num/den, chunked Montgomery batch inversion, and a
+//     hierarchical prefix-product scan
+//   * opening polynomial          -- kzg/src/lib.rs:55-64: Horner evaluation and the division
+//     by (X - z) are one linear recurrence q[k-1] = p[k] + z q[k], solved as a hierarchical scan
+//   * gate check                  -- the `vanishes(line1)` assert, plonk/src/proof.rs:317-321
+//   * quotient numerator on the 4n domain and division by X^n - 1 -- plonk/src/proof.rs:292-375
+//     (the reference builds these with O(n^2) `naive_mul`)
+//   * linear combination for r(X) -- plonk/src/proof.rs:376-439
+//   * sigma / id tables           -- permutation/src/lib.rs:101-128
+#include "common.cuh"
+
+namespace tp {
+
+#define EW_THREADS 256
+static inline unsigned ew_grid(size_t n) { return (unsigned)((n + EW_THREADS - 1) / EW_THREADS); }
+
+// =====================================================================================
+// prefix-product scan (in place).  chunk per thread, recursive on chunk totals.
+// =====================================================================================
+#define SCAN_CH 32
+#define SCAN_BASE 64
+
+__global__ void k_mulscan_serial(Fr* a, size_t n, int exclusive) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr acc = fr_one();
+  for (size_t i = 0; i < n; i++) {
+    Fr x = fr_load(a + i);
+    if (exclusive) {
+      fr_store(a + i, acc);
+      acc = fr_mul(acc, x);
+    } else {
+      acc = fr_mul(acc, x);
+      fr_store(a + i, acc);
+    }
+  }
+}
+__global__ void k_mulscan_chunk(Fr* a, size_t n, Fr* tot, int exclusive) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * SCAN_CH;
+  if (lo >= n) return;
+  size_t hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
+  Fr acc = fr_one();
+  for (size_t i = lo; i < hi; i++) {
+    Fr x = fr_load(a + i);
+    if (exclusive) {
+      fr_store(a + i, acc);
+      acc = fr_mul(acc, x);
+    } else {
+      acc = fr_mul(acc, x);
+      fr_store(a + i, acc);
+    }
+  }
+  fr_store(tot + t, acc);
+}
+__global__ void k_mulscan_apply(Fr* a, size_t n, const Fr* carry) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t ch = i / SCAN_CH;
+  if (ch == 0) return;
+  fr_store(a + i, fr_mul(fr_load(a + i), fr_load(carry + ch)));
+}
+
+static int mulscan(tp_ctx* ctx, Fr* a, size_t n, bool exclusive, int level) {
+  if (n <= SCAN_BASE) {
+    k_mulscan_serial<<<1, 1, 0, ctx->stream>>>(a, n, exclusive ? 1 : 0);
+    TP_LAUNCH(ctx, "k_mulscan_serial");
+    return TP_OK;
+  }
+  size_t nch = (n + SCAN_CH - 1) / SCAN_CH;
+  TP_TRY(ensure(ctx, ctx->scan_tmp[level], nch * sizeof(Fr)));
+  Fr* tot = (Fr*)ctx->scan_tmp[level].p;
+  k_mulscan_chunk<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(a, n, tot, exclusive ? 1 : 0);
+  TP_LAUNCH(ctx, "k_mulscan_chunk");
+  TP_TRY(mulscan(ctx, tot, nch, true, level + 1));
+  k_mulscan_apply<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(a, n, tot);
+  TP_LAUNCH(ctx, "k_mulscan_apply");
+  return TP_OK;
+}
+
+// =====================================================================================
+// grand product
+// =====================================================================================
+struct PermArgs {
+  const Fr* v[3];
+  const Fr* id[3];
+  const Fr* sg[3];
+  Fr beta, gamma;
+  size_t n;
+  Fr* num;
+  Fr* den;
+  unsigned* flag;
+};
+__global__ void k_perm_numden(PermArgs a) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.n) return;
+  Fr num = fr_one(), den = fr_one();
+  bool zero = false;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    Fr v = fr_add(fr_load(a.v[i] + j), a.gamma);
+    Fr nu = fr_add(v, fr_mul(a.beta, fr_load(a.id[i] + j)));
+    Fr de = fr_add(v, fr_mul(a.beta, fr_load(a.sg[i] + j)));
+    zero |= fr_is_zero(de);
+    num = i == 0 ? nu : fr_mul(num, nu);
+    den = i == 0 ? de : fr_mul(den, de);
+  }
+  if (zero) atomicOr(a.flag, 1u);
+  fr_store(a.num + j, num);
+  fr_store(a.den + j, den);
+}
+// ratio[j] = num[j] / den[j] with one Fermat inversion per BINV_CH elements; written to out[j].
+#define BINV_CH 16
+__global__ void k_batch_ratio(const Fr* num, const Fr* den, size_t n, Fr* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * BINV_CH;
+  if (lo >= n) return;
+  int cnt = (int)(lo + BINV_CH < n ? BINV_CH : n - lo);
+  Fr pre[BINV_CH];
+  Fr acc = fr_one();
+  for (int i = 0; i < cnt; i++) {
+    pre[i] = acc;  // product of den[lo .. lo+i-1]
+    acc = fr_mul(acc, fr_load(den + lo + i));
+  }
+  Fr inv = fr_inv(acc);
+  for (int i = cnt - 1; i >= 0; i--) {
+    Fr d = fr_load(den + lo + i);
+    Fr di = fr_mul(inv, pre[i]);  // 1 / den[lo+i]
+    inv = fr_mul(inv, d);
+    fr_store(out + lo + i, fr_mul(fr_load(num + lo + i), di));
+  }
+}
+__global__ void k_set_one(Fr* p) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) fr_store(p, fr_one());
+}
+
+int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],
+                           size_t n, const Fr& beta, const Fr& gamma, Fr* out) {
+  ProfScope prof(ctx, TP_PHASE_PERM);
+  TP_TRY(ensure(ctx, ctx->misc[0], n * sizeof(Fr)));
+  TP_TRY(ensure(ctx, ctx->misc[1], n * sizeof(Fr)));
+  TP_TRY(ensure(ctx, ctx->flag, sizeof(unsigned)));
+  PermArgs a;
+  for (int i = 0; i < 3; i++) {
+    a.v[i] = values[i];
+    a.id[i] = id[i];
+    a.sg[i] = sigma[i];
+  }
+  a.beta = beta;
+  a.gamma = gamma;
+  a.n = n;
+  a.num = (Fr*)ctx->misc[0].p;
+  a.den = (Fr*)ctx->misc[1].p;
+  a.flag = (unsigned*)ctx->flag.p;
+  TP_CUDA_OK(ctx, cudaMemsetAsync(a.flag, 0, sizeof(unsigned), ctx->stream));
+  k_perm_numden<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(a);
+  TP_LAUNCH(ctx, "k_perm_numden");
+  size_t nth = (n + BINV_CH - 1) / BINV_CH;
+  k_batch_ratio<<<(unsigned)((nth + 127) / 128), 128, 0, ctx->stream>>>(a.num, a.den, n, out + 1);
+  TP_LAUNCH(ctx, "k_batch_ratio");
+  TP_TRY(mulscan(ctx, out + 1, n, false, 0));
+  k_set_one<<<1, 1, 0, ctx->stream>>>(out);
+  TP_LAUNCH(ctx, "k_set_one");
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, a.flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (*(unsigned*)ctx->pinned) return fail(ctx, TP_ERR_ZERO_DENOMINATOR, "permutation prove: zero denominator");
+  return TP_OK;
+}
+
+// =====================================================================================
+// linear recurrence  q[k-1] = p[k] + z q[k]   (Horner + division by X - z)
+// =====================================================================================
+#define LIN_CH 32
+#define LIN_BASE 64
+
+// h[t] = sum_{k in chunk t} p[k] z^(k - lo)
+__global__ void k_linrec_reduce(const Fr* p, size_t n, Fr z, Fr* h) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * LIN_CH;
+  if (lo >= n) return;
+  size_t hi = lo + LIN_CH < n ? lo + LIN_CH : n;
+  Fr acc = fr_zero();
+  for (size_t k = hi; k-- > lo;) acc = fr_add(fr_load(p + k), fr_mul(z, acc));
+  fr_store(h + t, acc);
+}
+// q[k-1] = p[k] + z q[k] inside chunk t, starting from carry = qprime[t] (q at index hi-1)
+__global__ void k_linrec_apply(const Fr* p, size_t n, Fr z, const Fr* qprime, Fr* q) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * LIN_CH;
+  if (lo >= n) return;
+  size_t hi = lo + LIN_CH < n ? lo + LIN_CH : n;
+  Fr acc = fr_load(qprime + t);
+  if (hi == n) fr_store(q + n - 1, fr_zero());
+  for (size_t k = hi; k-- > lo;) {
+    acc = fr_add(fr_load(p + k), fr_mul(z, acc));
+    if (k >= 1) fr_store(q + k - 1, acc);
+  }
+}
+// serial base case: q (may alias nothing) and y = p(z) -> yout
+__global__ void k_linrec_serial(const Fr* p, size_t n, Fr z, Fr* q, Fr* yout) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Fr acc = fr_zero();
+  if (q) fr_store(q + n - 1, fr_zero());
+  for (size_t k = n; k-- > 0;) {
+    acc = fr_add(fr_load(p + k), fr_mul(z, acc));
+    if (q && k >= 1) fr_store(q + k - 1, acc);
+  }
+  fr_store(yout, acc);
+}
+
+// q may be null (evaluation only).  y is written to the device word yout.
+static int linrec(tp_ctx* ctx, const Fr* p, size_t n, const tph::HFr& z, Fr* q, Fr* yout, int level) {
+  if (n <= LIN_BASE) {
+    k_linrec_serial<<<1, 1, 0, ctx->stream>>>(p, n, to_dev(z), q, yout);
+    TP_LAUNCH(ctx, "k_linrec_serial");
+    return TP_OK;
+  }
+  size_t nch = (n + LIN_CH - 1) / LIN_CH;
+  // level buffers: h (nch) and qprime (nch)
+  TP_TRY(ensure(ctx, ctx->scan_tmp[level], 2 * nch * sizeof(Fr)));
+  Fr* h = (Fr*)ctx->scan_tmp[level].p;
+  Fr* qp = h + nch;
+  k_linrec_reduce<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(p, n, to_dev(z), h);
+  TP_LAUNCH(ctx, "k_linrec_reduce");
+  tph::HFr zc = z.pow_u64(LIN_CH);
+  TP_TRY(linrec(ctx, h, nch, zc, q ? qp : nullptr, yout, level + 1));
+  if (q) {
+    k_linrec_apply<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(p, n, to_dev(z), qp, q);
+    TP_LAUNCH(ctx, "k_linrec_apply");
+  }
+  return TP_OK;
+}
+
+int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out, tph::HFr* y) {
+  if (len == 0) return fail(ctx, TP_ERR_EMPTY_POLY, "open: empty polynomial");
+  ProfScope prof(ctx, TP_PHASE_SCAN);
+  TP_TRY(ensure(ctx, ctx->misc[2], sizeof(Fr)));
+  Fr* yd = (Fr*)ctx->misc[2].p;
+  TP_TRY(linrec(ctx, p, len, to_host(z), q_out, yd, 0));
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, yd, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(y->v, ctx->pinned, 32);
+  return TP_OK;
+}
+
+// =====================================================================================
+// gate check on the n rows
+// =====================================================================================
+struct GateArgs {
+  const Fr* sel[5];
+  const Fr* adv[3];
+  const Fr* pi;
+  size_t n;
+  unsigned* flag;
+};
+__global__ void k_gate_check(GateArgs g) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= g.n) return;
+  Fr a = fr_load(g.adv[0] + j), b = fr_load(g.adv[1] + j), c = fr_load(g.adv[2] + j);
+  Fr acc = fr_mul(fr_load(g.sel[0] + j), a);
+  acc = fr_add(acc, fr_mul(fr_load(g.sel[1] + j), b));
+  acc = fr_sub(acc, fr_mul(fr_load(g.sel[2] + j), c));
+  acc = fr_add(acc, fr_mul(fr_mul(fr_load(g.sel[3] + j), a), b));
+  acc = fr_add(acc, fr_load(g.sel[4] + j));
+  acc = fr_add(acc, fr_load(g.pi + j));
+  if (!fr_is_zero(acc)) atomicOr(g.flag, 1u);
+}
+int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
+                   bool* ok) {
+  TP_TRY(ensure(ctx, ctx->flag, sizeof(unsigned)));
+  GateArgs g;
+  for (int i = 0; i < 5; i++) g.sel[i] = sel_evals[i];
+  for (int i = 0; i < 3; i++) g.adv[i] = adv[i];
+  g.pi = pi;
+  g.n = n;
+  g.flag = (unsigned*)ctx->flag.p;
+  TP_CUDA_OK(ctx, cudaMemsetAsync(g.flag, 0, sizeof(unsigned), ctx->stream));
+  k_gate_check<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(g);
+  TP_LAUNCH(ctx, "k_gate_check");
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, g.flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  *ok = (*(unsigned*)ctx->pinned == 0);
+  return TP_OK;
+}
+
+// =====================================================================================
+// quotient numerator on the 4n domain
+// =====================================================================================
+struct QuotKernelArgs {
+  const Fr* sel4[5];
+  const Fr* sig4[3];
+  const Fr* adv4[3];
+  const Fr* z4;
+  const Fr* pi4;
+  const Fr* l0_4;
+  const Fr* tw4;
+  Fr alpha, alpha2, beta, gamma;
+  Fr bk[3];  // beta * k_i
+  Fr* out;
+  size_t n;
+};
+__global__ void __launch_bounds__(EW_THREADS) k_quotient_numerator(QuotKernelArgs q) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n4 = q.n * 4;
+  if (i >= n4) return;
+  size_t half = q.n * 2;
+  Fr x = i < half ? fr_load(q.tw4 + i) : fr_neg(fr_load(q.tw4 + (i - half)));
+  Fr a = fr_load(q.adv4[0] + i), b = fr_load(q.adv4[1] + i), c = fr_load(q.adv4[2] + i);
+  Fr z = fr_load(q.z4 + i);
+  size_t iw = i + 4 < n4 ? i + 4 : i + 4 - n4;
+  Fr zw = fr_load(q.z4 + iw);
+  // gate line (proof.rs:317-320)
+  Fr acc = fr_mul(fr_load(q.sel4[0] + i), a);
+  acc = fr_add(acc, fr_mul(fr_load(q.sel4[1] + i), b));
+  acc = fr_sub(acc, fr_mul(fr_load(q.sel4[2] + i), c));
+  acc = fr_add(acc, fr_mul(fr_mul(fr_load(q.sel4[3] + i), a), b));
+  acc = fr_add(acc, fr_load(q.sel4[4] + i));
+  acc = fr_add(acc, fr_load(q.pi4 + i));
+  // permutation lines (proof.rs:323-354)
+  Fr ag = fr_add(a, q.gamma), bg = fr_add(b, q.gamma), cg = fr_add(c, q.gamma);
+  Fr l2 = fr_mul(fr_add(ag, fr_mul(q.bk[0], x)), fr_add(bg, fr_mul(q.bk[1], x)));
+  l2 = fr_mul(l2, fr_add(cg, fr_mul(q.bk[2], x)));
+  l2 = fr_mul(l2, z);
+  Fr l3 = fr_mul(fr_add(ag, fr_mul(q.beta, fr_load(q.sig4[0] + i))), fr_add(bg, fr_mul(q.beta, fr_load(q.sig4[1] + i))));
+  l3 = fr_mul(l3, fr_add(cg, fr_mul(q.beta, fr_load(q.sig4[2] + i))));
+  l3 = fr_mul(l3, zw);
+  acc = fr_add(acc, fr_mul(q.alpha, fr_sub(l2, l3)));
+  // L0 line (proof.rs:355-360)
+  Fr l4 = fr_mul(fr_sub(z, fr_one()), fr_load(q.l0_4 + i));
+  acc = fr_add(acc, fr_mul(q.alpha2, l4));
+  fr_store(q.out + i, acc);
+}
+int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a) {
+  ProfScope prof(ctx, TP_PHASE_QUOTIENT);
+  QuotKernelArgs q;
+  for (int i = 0; i < 5; i++) q.sel4[i] = a.sel4[i];
+  for (int i = 0; i < 3; i++) {
+    q.sig4[i] = a.sig4[i];
+    q.adv4[i] = a.adv4[i];
+  }
+  q.z4 = a.z4;
+  q.pi4 = a.pi4;
+  q.l0_4 = a.l0_4;
+  q.tw4 = a.tw4;
+  tph::HFr al = to_host(a.alpha), be = to_host(a.beta);
+  q.alpha = a.alpha;
+  q.alpha2 = to_dev(al.sqr());
+  q.beta = a.beta;
+  q.gamma = a.gamma;
+  for (int i = 0; i < 3; i++) q.bk[i] = to_dev(be * to_host(a.k[i]));
+  q.out = a.out;
+  q.n = a.n;
+  k_quotient_numerator<<<ew_grid(a.n * 4), EW_THREADS, 0, ctx->stream>>>(q);
+  TP_LAUNCH(ctx, "k_quotient_numerator");
+  return TP_OK;
+}
+
+__global__ void k_divide_vanishing(const Fr* c4, size_t n, Fr* t) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  Fr t2 = fr_load(c4 + k + 3 * n);
+  Fr t1 = fr_add(fr_load(c4 + k + 2 * n), t2);
+  Fr t0 = fr_add(fr_load(c4 + k + n), t1);
+  fr_store(t + k + 2 * n, t2);
+  fr_store(t + k + n, t1);
+  fr_store(t + k, t0);
+}
+int divide_by_vanishing_dev(tp_ctx* ctx, const Fr* c4, size_t n, Fr* t) {
+  ProfScope prof(ctx, TP_PHASE_QUOTIENT);
+  k_divide_vanishing<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(c4, n, t);
+  TP_LAUNCH(ctx, "k_divide_vanishing");
+  return TP_OK;
+}
+
+// L0(x) = (x^n - 1) / (n (x - 1)) on the 4n domain; chunked batch inversion (8 per thread).
+#define L0_CH 8
+__global__ void k_l0_evals(const Fr* tw4, size_t n, Fr ninv, Fr* out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n4 = 4 * n, half = 2 * n;
+  size_t lo = t * L0_CH;
+  if (lo >= n4) return;
+  Fr xs[L0_CH], pre[L0_CH];
+  Fr acc = fr_one();
+  Fr one = fr_one();
+  for (int i = 0; i < L0_CH; i++) {
+    size_t idx = lo + i;
+    Fr x = idx < half ? fr_load(tw4 + idx) : fr_neg(fr_load(tw4 + (idx - half)));
+    Fr d = fr_sub(x, one);
+    if ((idx & 3) == 0) d = one;  // x in H: handled separately (avoid the zero at x = 1)
+    xs[i] = d;
+    pre[i] = acc;
+    acc = fr_mul(acc, d);
+  }
+  Fr inv = fr_inv(acc);
+  // x^n = iota^(idx mod 4), iota = omega_4n^n
+  Fr iota = fr_load(tw4 + n);
+  for (int i = L0_CH - 1; i >= 0; i--) {
+    size_t idx = lo + i;
+    Fr di = fr_mul(inv, pre[i]);
+    inv = fr_mul(inv, xs[i]);
+    Fr r;
+    unsigned m = (unsigned)(idx & 3);
+    if (m == 0) {
+      r = idx == 0 ? one : fr_zero();
+    } else {
+      Fr xn = m == 1 ? iota : (m == 2 ? fr_neg(one) : fr_neg(iota));
+      r = fr_mul(fr_mul(fr_sub(xn, one), ninv), di);
+    }
+    fr_store(out + idx, r);
+  }
+}
+int l0_evals_4n_dev(tp_ctx* ctx, const Fr* tw4, size_t n, Fr* out) {
+  tph::HFr ninv = tph::HFr::from_u64((uint64_t)n).inv();
+  size_t nth = (4 * n + L0_CH - 1) / L0_CH;
+  if ((4 * n) % L0_CH != 0) return fail(ctx, TP_ERR_INVALID_ARG, "l0: 4n must be a multiple of 8");
+  k_l0_evals<<<(unsigned)((nth + 127) / 128), 128, 0, ctx->stream>>>(tw4, n, to_dev(ninv), out);
+  TP_LAUNCH(ctx, "k_l0_evals");
+  return TP_OK;
+}
+
+// =====================================================================================
+// linear combination out = constant (at coeff 0) + sum_t s_t * p_t
+// =====================================================================================
+#define LIN_MAX_TERMS 12
+struct LinArgs {
+  const Fr* p[LIN_MAX_TERMS];
+  Fr s[LIN_MAX_TERMS];
+  int nterms;
+  Fr constant;
+  size_t n;
+  Fr* out;
+};
+__global__ void k_lincomb(LinArgs a) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  Fr acc = i == 0 ? a.constant : fr_zero();
+  for (int t = 0; t < a.nterms; t++) acc = fr_add(acc, fr_mul(a.s[t], fr_load(a.p[t] + i)));
+  fr_store(a.out + i, acc);
+}
+int lincomb_dev(tp_ctx* ctx, const LinTerm* terms, int nterms, const Fr& constant, size_t n, Fr* out) {
+  if (nterms > LIN_MAX_TERMS) return fail(ctx, TP_ERR_INVALID_ARG, "lincomb: too many terms");
+  LinArgs a;
+  for (int t = 0; t < nterms; t++) {
+    a.p[t] = terms[t].p;
+    a.s[t] = terms[t].s;
+  }
+  a.nterms = nterms;
+  a.constant = constant;
+  a.n = n;
+  a.out = out;
+  k_lincomb<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(a);
+  TP_LAUNCH(ctx, "k_lincomb");
+  return TP_OK;
+}
+
+// =====================================================================================
+// sigma / id tables
+// =====================================================================================
+struct SigmaArgs {
+  const uint64_t* perm;
+  size_t n;
+  const Fr* tw;  // omega_n^i, i in [0, n/2]
+  Fr k[3];
+  Fr* id[3];
+  Fr* sg[3];
+};
+__device__ __forceinline__ Fr root_pow(const Fr* tw, size_t n, size_t j) {
+  size_t half = n >> 1;
+  if (n == 1) return fr_one();
+  return j < half ? fr_load(tw + j) : fr_neg(fr_load(tw + (j - half)));
+}
+__global__ void k_sigma_tables(SigmaArgs a) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * a.n) return;
+  size_t i = idx / a.n, j = idx % a.n;
+  uint64_t p = a.perm[idx];
+  size_t ti = (size_t)(p / a.n), tj = (size_t)(p % a.n);
+  Fr ki = i == 0 ? a.k[0] : (i == 1 ? a.k[1] : a.k[2]);
+  Fr kt = ti == 0 ? a.k[0] : (ti == 1 ? a.k[1] : a.k[2]);
+  Fr idv = fr_mul(ki, root_pow(a.tw, a.n, j));
+  Fr sgv = fr_mul(kt, root_pow(a.tw, a.n, tj));
+  Fr* idp = i == 0 ? a.id[0] : (i == 1 ? a.id[1] : a.id[2]);
+  Fr* sgp = i == 0 ? a.sg[0] : (i == 1 ? a.sg[1] : a.sg[2]);
+  fr_store(idp + j, idv);
+  fr_store(sgp + j, sgv);
+}
+int sigma_tables_dev(tp_ctx* ctx, const uint64_t* perm_dev, size_t n, const Fr* tw, const Fr k[3], Fr* id[3],
+                     Fr* sigma[3]) {
+  SigmaArgs a;
+  a.perm = perm_dev;
+  a.n = n;
+  a.tw = tw;
+  for (int i = 0; i < 3; i++) {
+    a.k[i] = k[i];
+    a.id[i] = id[i];
+    a.sg[i] = sigma[i];
+  }
+  k_sigma_tables<<<ew_grid(3 * n), EW_THREADS, 0, ctx->stream>>>(a);
+  TP_LAUNCH(ctx, "k_sigma_tables");
+  return TP_OK;
+}
+
+__global__ void k_pad_copy(const Fr* in, size_t len, Fr* out, size_t out_len) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_len) return;
+  uint4* o = reinterpret_cast<uint4*>(out + i);
+  if (i < len) {
+    const uint4* s = reinterpret_cast<const uint4*>(in + i);
+    o[0] = s[0];
+    o[1] = s[1];
+  } else {
+    o[0] = make_uint4(0, 0, 0, 0);
+    o[1] = make_uint4(0, 0, 0, 0);
+  }
+}
+int pad_copy_dev(tp_ctx* ctx, const Fr* in, size_t len, Fr* out, size_t out_len) {
+  k_pad_copy<<<ew_grid(out_len), EW_THREADS, 0, ctx->stream>>>(in, len, out, out_len);
+  TP_LAUNCH(ctx, "k_pad_copy");
+  return TP_OK;
+}
+__global__ void k_rotate_copy(const Fr* in, size_t n, size_t shift, Fr* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  size_t s = i + shift;
+  if (s >= n) s -= n;
+  const uint4* src = reinterpret_cast<const uint4*>(in + s);
+  uint4* o = reinterpret_cast<uint4*>(out + i);
+  o[0] = src[0];
+  o[1] = src[1];
+}
+int rotate_copy_dev(tp_ctx* ctx, const Fr* in, size_t n, size_t shift, Fr* out) {
+  k_rotate_copy<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(in, n, shift % n, out);
+  TP_LAUNCH(ctx, "k_rotate_copy");
+  return TP_OK;
+}
+
+}  // namespace tp

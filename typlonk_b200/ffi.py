@@ -1,0 +1,271 @@
+"""ctypes binding of libtyplonk_b200.so (include/typlonk_b200.h).
+
+No CPU fallback: if the shared library is missing this module raises at import of the
+symbols, and every call needs a CUDA device (tp_ctx_create -> TP_ERR_NO_DEVICE otherwise).
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtyplonk_b200.so"
+
+G1_BYTES = 97
+PROOF_FIXED_BYTES = 1472
+PHASES = ["msm_total", "msm_sort", "msm_accum", "msm_reduce", "ntt", "quotient", "perm", "scan"]
+
+ERRORS = {
+    1: "TP_ERR_INVALID_ARG", 2: "TP_ERR_CUDA", 3: "TP_ERR_SRS_TOO_SHORT", 4: "TP_ERR_EMPTY_POLY",
+    5: "TP_ERR_ZERO_DENOMINATOR", 6: "TP_ERR_GATE_UNSATISFIED", 7: "TP_ERR_NO_DEVICE",
+    8: "TP_ERR_COLLECTIVE", 9: "TP_ERR_BUFFER_TOO_SMALL",
+}
+
+# every symbol include/typlonk_b200.h declares
+SYMBOLS = [
+    "tp_ctx_create", "tp_ctx_destroy", "tp_last_error", "tp_sync", "tp_ctx_set_shard",
+    "tp_prof_enable", "tp_prof_reset", "tp_prof_get", "tp_launch_count",
+    "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
+    "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
+    "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
+    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest",
+]
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class TyplonkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "TP_ERR"), code, msg))
+        self.code = code
+
+
+class GateUnsatisfied(TyplonkError):
+    """The reference panics here (`vanishes`, plonk/src/proof.rs:321)."""
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library (built by `python -m typlonk_b200.build`); loud failure if absent."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise ImportError(
+                "typlonk_b200: %s is missing -- build it with `python -m typlonk_b200.build` "
+                "(there is no CPU fallback)" % _LIB_PATH)
+        _lib = C.CDLL(str(_LIB_PATH))
+        _lib.tp_last_error.restype = C.c_char_p
+        _lib.tp_last_error.argtypes = [C.c_void_p]
+        for name in SYMBOLS:
+            getattr(_lib, name)  # AttributeError if the header and the library diverge
+    return _lib
+
+
+def _buf(b):
+    """bytes-like -> ctypes pointer (zero copy for bytearray / numpy, copy for bytes)."""
+    if isinstance(b, (bytes, bytearray)):
+        return (C.c_char * len(b)).from_buffer_copy(b) if isinstance(b, bytes) else (C.c_char * len(b)).from_buffer(b)
+    if isinstance(b, int):  # raw host address (e.g. a pinned torch tensor's data_ptr())
+        return C.c_void_p(b)
+    if hasattr(b, "ctypes"):  # numpy array
+        return b.ctypes.data_as(C.c_void_p)
+    return b
+
+
+class Context:
+    def __init__(self, device=0, stream=None):
+        L = lib()
+        self._h = C.c_void_p()
+        rc = L.tp_ctx_create(C.c_int(device), C.c_void_p(stream or 0), C.byref(self._h))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_ctx_create failed (no CUDA device? there is no CPU fallback)")
+        self._cb = None
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib().tp_last_error(self._h).decode()
+            if rc == 6:
+                raise GateUnsatisfied(rc, msg)
+            raise TyplonkError(rc, msg)
+
+    def close(self):
+        if self._h:
+            lib().tp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def sync(self):
+        self._check(lib().tp_sync(self._h))
+
+    def selftest(self):
+        f = C.c_int(-1)
+        self._check(lib().tp_selftest(self._h, C.byref(f)))
+        return f.value
+
+    def measure_imad_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(lib().tp_measure_imad_peak(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def prof_enable(self, on=True):
+        self._check(lib().tp_prof_enable(self._h, C.c_int(1 if on else 0)))
+
+    def prof_reset(self):
+        self._check(lib().tp_prof_reset(self._h))
+
+    def prof_get(self):
+        ms = (C.c_double * len(PHASES))()
+        ln = (C.c_uint64 * len(PHASES))()
+        self._check(lib().tp_prof_get(self._h, ms, ln))
+        return {p: (ms[i], ln[i]) for i, p in enumerate(PHASES)}
+
+    def launch_count(self):
+        v = C.c_uint64()
+        self._check(lib().tp_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    def set_shard(self, rank, world, allgather=None):
+        """allgather(send: bytes) -> bytes of world * len(send) (e.g. via torch.distributed)."""
+        if world > 1:
+            def cb(_user, send, recv, nbytes):
+                try:
+                    data = C.string_at(send, nbytes)
+                    out = allgather(data)
+                    assert len(out) == nbytes * world
+                    C.memmove(recv, out, len(out))
+                    return 0
+                except Exception:  # noqa: BLE001 -- must not unwind through C
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            self._cb = ALLGATHER_FN(cb)
+            self._check(lib().tp_ctx_set_shard(self._h, rank, world, self._cb, None))
+        else:
+            self._cb = None
+            self._check(lib().tp_ctx_set_shard(self._h, 0, 1, C.cast(None, ALLGATHER_FN), None))
+
+    # ---- SRS ---------------------------------------------------------------------------
+    def srs_from_secret(self, tau_mont: bytes, gates: int):
+        h = C.c_void_p()
+        self._check(lib().tp_srs_from_secret(self._h, _buf(tau_mont), C.c_size_t(gates), C.byref(h)))
+        return SrsHandle(self, h)
+
+    def srs_upload(self, g1_xy: bytes):
+        assert len(g1_xy) % 96 == 0
+        h = C.c_void_p()
+        self._check(lib().tp_srs_upload(self._h, _buf(g1_xy), C.c_size_t(len(g1_xy) // 96), C.byref(h)))
+        return SrsHandle(self, h)
+
+    # ---- KZG / NTT / permutation ---------------------------------------------------------
+    def commit(self, srs, coeffs_mont: bytes) -> bytes:
+        out = (C.c_char * G1_BYTES)()
+        self._check(lib().tp_commit(self._h, srs._h, _buf(coeffs_mont), C.c_size_t(len(coeffs_mont) // 32), out))
+        return bytes(out)
+
+    def commit_dev(self, srs, dptr: int, length: int) -> bytes:
+        out = (C.c_char * G1_BYTES)()
+        self._check(lib().tp_commit_dev(self._h, srs._h, C.c_void_p(dptr), C.c_size_t(length), out))
+        return bytes(out)
+
+    def open(self, srs, coeffs_mont: bytes, z_mont: bytes):
+        w = (C.c_char * G1_BYTES)()
+        y = (C.c_char * 32)()
+        self._check(lib().tp_open(self._h, srs._h, _buf(coeffs_mont), C.c_size_t(len(coeffs_mont) // 32),
+                                  _buf(z_mont), w, y))
+        return bytes(w), bytes(y)
+
+    def ntt(self, data_mont, log_n: int, inverse=False, coset_mont: bytes = None) -> bytes:
+        buf = bytearray(data_mont)
+        assert len(buf) == 32 << log_n
+        cos = _buf(coset_mont) if coset_mont is not None else None
+        self._check(lib().tp_ntt(self._h, _buf(buf), C.c_uint(log_n), C.c_int(1 if inverse else 0), cos))
+        return bytes(buf)
+
+    def ntt_dev(self, dptr: int, log_n: int, inverse=False, coset_mont: bytes = None):
+        cos = _buf(coset_mont) if coset_mont is not None else None
+        self._check(lib().tp_ntt_dev(self._h, C.c_void_p(dptr), C.c_uint(log_n), C.c_int(1 if inverse else 0), cos))
+
+    def perm_prove(self, values, ids, sigmas, beta_mont: bytes, gamma_mont: bytes) -> bytes:
+        n = len(values[0]) // 32
+        keep = [_buf(b) for b in list(values) + list(ids) + list(sigmas)]
+        arr = lambda xs: (C.c_void_p * 3)(*[C.cast(x, C.c_void_p) for x in xs])  # noqa: E731
+        out = (C.c_char * (32 * (n + 1)))()
+        self._check(lib().tp_perm_prove(self._h, arr(keep[0:3]), arr(keep[3:6]), arr(keep[6:9]), C.c_size_t(n),
+                                        _buf(beta_mont), _buf(gamma_mont), out))
+        return bytes(out)
+
+    # ---- circuits ----------------------------------------------------------------------------
+    def circuit_load(self, srs, selector_coeffs, ids, sigmas, cosets_mont, n):
+        keep = [_buf(b) for b in list(selector_coeffs) + list(ids) + list(sigmas)]
+        sel = (C.c_void_p * 5)(*[C.cast(x, C.c_void_p) for x in keep[0:5]])
+        idp = (C.c_void_p * 3)(*[C.cast(x, C.c_void_p) for x in keep[5:8]])
+        sgp = (C.c_void_p * 3)(*[C.cast(x, C.c_void_p) for x in keep[8:11]])
+        cos = _buf(b"".join(cosets_mont))
+        h = C.c_void_p()
+        self._check(lib().tp_circuit_load(self._h, srs._h, sel, idp, sgp, cos, C.c_size_t(n), C.byref(h)))
+        return CircuitHandle(self, h, n, srs)
+
+    def circuit_compile(self, srs, selector_evals, perm_u64: bytes, n):
+        keep = [_buf(b) for b in selector_evals]
+        sel = (C.c_void_p * 5)(*[C.cast(x, C.c_void_p) for x in keep])
+        fixed = (C.c_char * (5 * G1_BYTES))()
+        h = C.c_void_p()
+        self._check(lib().tp_circuit_compile(self._h, srs._h, sel, _buf(perm_u64), C.c_size_t(n), C.byref(h), fixed))
+        raw = bytes(fixed)
+        return CircuitHandle(self, h, n, srs), [raw[i * G1_BYTES:(i + 1) * G1_BYTES] for i in range(5)]
+
+
+class SrsHandle:
+    def __init__(self, ctx, h):
+        self.ctx = ctx
+        self._h = h
+
+    def __len__(self):
+        v = C.c_size_t()
+        lib().tp_srs_len(self._h, C.byref(v))
+        return v.value
+
+    def download(self, offset=0, count=None) -> bytes:
+        count = len(self) - offset if count is None else count
+        out = (C.c_char * (96 * count))()
+        self.ctx._check(lib().tp_srs_g1_download(self.ctx._h, self._h, C.c_size_t(offset), C.c_size_t(count), out))
+        return bytes(out)
+
+    def destroy(self):
+        if self._h:
+            lib().tp_srs_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()
+
+
+class CircuitHandle:
+    def __init__(self, ctx, h, n, srs):
+        self.ctx = ctx
+        self._h = h
+        self.n = n
+        self.srs = srs
+
+    def prove(self, advice_mont, public_inputs_mont) -> bytes:
+        keep = [_buf(b) for b in advice_mont]
+        adv = (C.c_void_p * 3)(*[C.cast(x, C.c_void_p) for x in keep])
+        out = (C.c_char * PROOF_FIXED_BYTES)()
+        self.ctx._check(lib().tp_prove(self.ctx._h, self._h, adv, _buf(public_inputs_mont), out,
+                                       C.c_size_t(PROOF_FIXED_BYTES)))
+        return bytes(out)
+
+    def prove_dev(self, advice_dptrs, pi_dptr) -> bytes:
+        adv = (C.c_void_p * 3)(*[C.c_void_p(p) for p in advice_dptrs])
+        out = (C.c_char * PROOF_FIXED_BYTES)()
+        self.ctx._check(lib().tp_prove_dev(self.ctx._h, self._h, adv, C.c_void_p(pi_dptr), out,
+                                           C.c_size_t(PROOF_FIXED_BYTES)))
+        return bytes(out)
+
+    def sigma_commitments(self):
+        out = (C.c_char * (3 * G1_BYTES))()
+        self.ctx._check(lib().tp_circuit_sigma_commitments(self.ctx._h, self._h, out))
+        raw = bytes(out)
+        return [raw[i * G1_BYTES:(i + 1) * G1_BYTES] for i in range(3)]
+
+    def destroy(self):
+        if self._h:
+            lib().tp_circuit_destroy(self.ctx._h, self._h)
+            self._h = C.c_void_p()

@@ -1,0 +1,210 @@
+"""Host-side mirror of the reference's `plonk` crate API over the CUDA library:
+CircuitDescription / Var (plonk/src/description.rs:4-16), CircuitBuilder::compile
+(plonk/src/builder.rs:60-113), CompiledCircuit::prove (plonk/src/proof.rs:26-57).
+
+    class Circuit(CircuitDescription):
+        INPUTS = 3
+        @staticmethod
+        def run(inputs):
+            a, b, c = inputs
+            a = a.clone() * a; b = b.clone() * b; c = c.clone() * c
+            d = a + b
+            d.assert_eq(c)
+
+    circuit = Circuit.build(ctx, tau)                 # description.rs:6-8
+    proof = circuit.prove([3, 4, 5], [0], blinders)   # proof.rs:26
+
+The tracing DSL and cycle building are host bookkeeping (out of the GPU scope, SURVEY.md 2
+#13/#15); everything numeric -- SRS, selector interpolation and commitments, sigma tables, the
+whole prover -- runs in libtyplonk_b200.  tau and the nine blinders are explicit inputs where the
+reference draws them from thread_rng (builder.rs:71, proof.rs:42-48).  `verify` (pairings) is
+out of scope for the GPU path; tests verify proofs with the CPU oracle.
+"""
+import struct
+from dataclasses import dataclass
+from typing import List
+
+from . import field as F
+from .ffi import Context, GateUnsatisfied, PROOF_FIXED_BYTES  # noqa: F401
+from .kzg import Srs
+from .permutation import PermutationBuilder
+
+GATE_ROWS = {"Mul": (0, 0, 1, 1, 0), "Add": (1, 1, 1, 0, 0), "Dummy": (0, 0, 0, 0, 0)}  # builder.rs:318-324
+
+
+class _Context:
+    """builder.rs:119-188."""
+
+    def __init__(self):
+        self.gates = []
+        self.permutation = PermutationBuilder()
+        self.next_var_id = 0
+        self.pending_eq = []
+        self.var_map = {}
+
+    def new_id(self):
+        self.next_var_id += 1
+        return self.next_var_id - 1
+
+    def add_gate(self, gate):
+        self.gates.append(gate)
+        self.permutation.add_row()
+        return len(self.gates) - 1
+
+    def add_eq(self, left, right):
+        a, b = self.var_map.get(left), self.var_map.get(right)
+        if a is not None and b is not None:
+            if not self.permutation.add_constrain(a, b):
+                raise ValueError("invalid tag")
+        else:
+            self.pending_eq.append((left, right))
+
+    def finish(self):
+        pending, self.pending_eq = self.pending_eq, []
+        for left, right in pending:
+            self.add_eq(left, right)
+        assert not self.pending_eq
+        size = 2
+        while size < len(self.gates) + 3:  # fill(), builder.rs:47-58
+            size *= 2
+        self.gates += ["Dummy"] * (size - len(self.gates))
+        return self.gates, self.permutation
+
+
+class Var:
+    """description.rs:10-16: `+`, `*`, `clone`, `assert_eq`."""
+
+    def clone(self):
+        raise NotImplementedError
+
+    def assert_eq(self, other):
+        raise NotImplementedError
+
+
+class BuildVar(Var):
+    """builder.rs:327-378."""
+
+    def __init__(self, context, vid):
+        self.context, self.id = context, vid
+
+    def clone(self):
+        return BuildVar(self.context, self.id)
+
+    def _binary(self, rhs, gate):
+        ctx = self.context
+        j = ctx.add_gate(gate)
+        out = ctx.new_id()
+        ctx.var_map[out] = (2, j)
+        for vid, i in ((self.id, 0), (rhs.id, 1)):
+            if vid in ctx.var_map:
+                new_id = ctx.new_id()
+                ctx.var_map[new_id] = (i, j)
+                ctx.add_eq(vid, new_id)
+            else:
+                ctx.var_map[vid] = (i, j)
+        return BuildVar(ctx, out)
+
+    def __add__(self, rhs):
+        return self._binary(rhs, "Add")
+
+    def __mul__(self, rhs):
+        return self._binary(rhs, "Mul")
+
+    def assert_eq(self, other):
+        self.context.add_eq(self.id, other.id)
+
+
+class ComputeVar(Var):
+    """builder.rs:332-336, 380-397; assert_eq is a no-op as in the reference (:435-441)."""
+
+    def __init__(self, value, advice):
+        self.value, self.advice = value % F.R_MOD, advice
+
+    def clone(self):
+        return ComputeVar(self.value, self.advice)
+
+    def _binary(self, rhs, mul):
+        l, r = self.value, rhs.value
+        v = (l * r if mul else l + r) % F.R_MOD
+        self.advice[0].append(l)
+        self.advice[1].append(r)
+        self.advice[2].append(v)
+        return ComputeVar(v, self.advice)
+
+    def __add__(self, rhs):
+        return self._binary(rhs, False)
+
+    def __mul__(self, rhs):
+        return self._binary(rhs, True)
+
+    def assert_eq(self, other):
+        pass
+
+
+@dataclass
+class Proof:
+    """proof.rs:85-95 as bytes: `fixed` is the 1472-byte block tp_prove writes, followed by the
+    n-padded public inputs (u64 LE length + n x 32 B), SURVEY.md App. A.6."""
+    fixed: bytes
+    public_inputs: List[int]
+
+    def to_bytes(self) -> bytes:
+        return (self.fixed + struct.pack("<Q", len(self.public_inputs)) +
+                b"".join(v.to_bytes(32, "little") for v in self.public_inputs))
+
+
+class CompiledCircuit:
+    """plonk/src/lib.rs:18-26."""
+
+    def __init__(self, desc, ctx, srs, handle, rows, fixed_commitments, gates, perm):
+        self.desc, self.ctx, self.srs, self.handle = desc, ctx, srs, handle
+        self.rows = rows
+        self.fixed_commitments = fixed_commitments
+        self.gates = gates
+        self.perm = perm
+
+    def witness(self, inputs, blinders):
+        """proof.rs:33-49."""
+        advice = [[], [], []]
+        self.desc.run([ComputeVar(v, advice) for v in inputs])
+        assert len(blinders) == 9
+        cols = []
+        for k, col in enumerate(advice):
+            col = col[: self.rows - 3] + [0] * max(0, self.rows - 3 - len(col))
+            cols.append(col + [b % F.R_MOD for b in blinders[3 * k: 3 * k + 3]])
+        return cols
+
+    def prove(self, inputs, public_inputs, blinders) -> Proof:
+        """CompiledCircuit::prove (proof.rs:26-57).  Raises GateUnsatisfied where the reference
+        panics in `vanishes`."""
+        cols = self.witness(inputs, blinders)
+        pis = ([v % F.R_MOD for v in public_inputs] + [0] * self.rows)[: self.rows]
+        fixed = self.handle.prove([F.fr_vec_to_bytes(c) for c in cols], F.fr_vec_to_bytes(pis))
+        return Proof(fixed, pis)
+
+
+class CircuitDescription:
+    """description.rs:4-9."""
+    INPUTS = 0
+
+    @staticmethod
+    def run(inputs):
+        raise NotImplementedError
+
+    @classmethod
+    def trace(cls):
+        ctx = _Context()
+        cls.run([BuildVar(ctx, ctx.new_id()) for _ in range(cls.INPUTS)])
+        gates, permutation = ctx.finish()
+        return gates, permutation.build(len(gates))
+
+    @classmethod
+    def build(cls, ctx: Context, tau: int) -> CompiledCircuit:
+        """CircuitBuilder::compile (builder.rs:60-113) with the SRS secret as an input."""
+        gates, perm = cls.trace()
+        rows = len(gates)
+        srs = Srs.from_secret(ctx, tau, rows)
+        sel = [F.fr_vec_to_bytes([GATE_ROWS[g][k] for g in gates]) for k in range(5)]
+        perm_bytes = struct.pack("<%dQ" % len(perm.perm), *perm.perm)
+        handle, fixed = ctx.circuit_compile(srs.handle, sel, perm_bytes, rows)
+        return CompiledCircuit(cls, ctx, srs, handle, rows, [F.g1_from_abi(c) for c in fixed], gates, perm)
