@@ -159,6 +159,10 @@ int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], co
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* Measured dependent-free IMAD throughput of this device (instructions/s), for rooflines. */
 int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s);
+/* Synthetic-input helper: `count` x ark-ff 0.3 `Fr::rand` drawn from rand 0.8
+ * `StdRng::seed_from_u64(seed)` (ChaCha12), written as Montgomery limbs -- the same stream the
+ * reference's Fiat-Shamir uses (plonk/src/proof/challenges.rs:38-45).  Host only. */
+int tp_fr_rand_stream(uint64_t seed, size_t count, uint64_t* out);
 /* Self-test of the device field/curve arithmetic against host arithmetic; 0 failures expected. */
 int tp_selftest(tp_ctx* ctx, int* failures);
 

@@ -588,5 +588,14 @@ int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_
   return measure_imad_dev(ctx, imad_per_s, imad_wide_per_s);
 }
 int tp_selftest(tp_ctx* ctx, int* failures) { return selftest_dev(ctx, failures); }
+int tp_fr_rand_stream(uint64_t seed, size_t count, uint64_t* out) {
+  if (!out && count) return TP_ERR_INVALID_ARG;
+  tph::StdRng rng = tph::StdRng::seed_from_u64(seed);
+  for (size_t i = 0; i < count; i++) {
+    HFr x = tph::fr_rand(rng);
+    memcpy(out + 4 * i, x.v, 32);
+  }
+  return TP_OK;
+}
 
 }  // extern "C"

@@ -26,7 +26,7 @@ SYMBOLS = [
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
-    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest",
+    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -70,6 +70,15 @@ def _buf(b):
     if hasattr(b, "ctypes"):  # numpy array
         return b.ctypes.data_as(C.c_void_p)
     return b
+
+
+def fr_rand_stream(seed: int, count: int) -> bytes:
+    """count x Fr::rand from StdRng::seed_from_u64(seed), Montgomery bytes (host only)."""
+    out = (C.c_char * (32 * count))()
+    rc = lib().tp_fr_rand_stream(C.c_uint64(seed), C.c_size_t(count), out)
+    if rc != 0:
+        raise TyplonkError(rc, "tp_fr_rand_stream")
+    return bytes(out)
 
 
 class Context:

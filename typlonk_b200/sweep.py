@@ -1,0 +1,63 @@
+"""BASELINE.json configs[3]: standalone KZG G1 MSM sweep and Fr NTT / coset NTT sweep, device
+resident, timed with CUDA events on the ctx stream.  Emits one JSON line per point."""
+import json
+
+from . import field as F, synthetic
+from .ffi import fr_rand_stream
+from .kzg import Srs
+
+
+def _events(torch):
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+def run(ctx, torch, out, msm_logs=(16, 18, 20, 22, 24), ntt_logs=(16, 18, 20, 22, 24), reps=3):
+    dev = torch.device("cuda", ctx.device)
+    imad, imad_wide = ctx.measure_imad_peak()
+    max_log = max(msm_logs)
+    srs = Srs.from_secret(ctx, synthetic.tau(), (1 << max_log) - 3)
+    for lg in msm_logs:
+        n = 1 << lg
+        # uniform scalars: Fr::rand stream (seed 3) for the first 2^16, then a device-side mix
+        base = torch.frombuffer(bytearray(fr_rand_stream(synthetic.SEED_MSM, 1 << 16)), dtype=torch.uint8).to(dev)
+        sc = base.repeat(n >> 16).view(n, 32).clone()
+        if n > (1 << 16):
+            # make repeats distinct while staying < r: xor a counter into limb bytes 8..11
+            idx = torch.arange(n, device=dev, dtype=torch.int64)
+            mix = ((idx >> 16) * 2654435761) & 0xFFFFFFFF
+            for b in range(4):
+                sc[:, 8 + b] ^= ((mix >> (8 * b)) & 0xFF).to(torch.uint8)
+        torch.cuda.synchronize()
+        ctx.commit_dev(srs.handle, sc.data_ptr(), n)
+        ctx.prof_reset(); ctx.prof_enable(True)
+        e0, e1 = _events(torch)
+        e0.record()
+        for _ in range(reps):
+            ctx.commit_dev(srs.handle, sc.data_ptr(), n)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        prof = ctx.prof_get(); ctx.prof_enable(False)
+        out.write(json.dumps({"sweep": "msm", "log_n": lg, "ms": ms, "mpts_per_s": n / ms / 1e3,
+                              "hbm_gbs_algorithmic": 128.0 * n / ms / 1e6,
+                              "phases_ms": {k: v[0] / reps for k, v in prof.items() if k.startswith("msm")}}) + "\n")
+        del sc
+    srs.handle.destroy()
+    for lg in ntt_logs:
+        n = 1 << lg
+        x = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev)
+        x[:, 31] &= 0x3F
+        torch.cuda.synchronize()
+        for name, kw in (("ntt", {}), ("intt", {"inverse": True}), ("coset_ntt", {"coset_mont": F.fr_to_bytes(7)})):
+            ctx.ntt_dev(x.data_ptr(), lg, **kw)
+            e0, e1 = _events(torch)
+            e0.record()
+            for _ in range(reps):
+                ctx.ntt_dev(x.data_ptr(), lg, **kw)
+            e1.record(); torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            butterflies = (n // 2) * lg
+            out.write(json.dumps({"sweep": name, "log_n": lg, "ms": ms, "gbs_algorithmic": 64.0 * n / ms / 1e6,
+                                  "gbutterflies_per_s": butterflies / ms / 1e6,
+                                  "imad_frac_est": butterflies * 176 / (ms * 1e-3) / imad_wide}) + "\n")
+        del x
+    out.flush()
