@@ -140,8 +140,11 @@ def main():
     from typlonk_b200 import field as F, synthetic
     from typlonk_b200.ffi import Context, PHASES
 
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = Context(local_rank, stream)
+    # a non-default torch stream: its handle is what the library launches on, so torch.cuda.Event
+    # timings bracket the library's kernels (the legacy default stream has handle 0 = "make your own")
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    ctx = Context(local_rank, tstream.cuda_stream)
 
     if world > 1:
         def allgather(data: bytes) -> bytes:

@@ -213,3 +213,50 @@ def test_perm_prove_zero_denominator(ctx):
     assert e.value.code == 5
     with pytest.raises(ZeroDivisionError):
         compiled.prove(values, beta, gamma)
+
+
+# ---- BASELINE-scale MSM checks through the SRS trapdoor: commit(p) == p(tau) * G ----------------
+
+@pytest.fixture(scope="module")
+def srs_big(ctx):
+    tau = rng.fr_rand_stream(1, 1)[0]
+    return tau, Srs.from_secret(ctx, tau, (1 << 18) - 3)
+
+
+def _expect_from_trapdoor(tau, scalars):
+    acc = 0
+    for s in reversed(scalars):
+        acc = (acc * tau + s) % R
+    return curve.g1_mul(curve.G1_GEN, acc)
+
+
+def test_commit_large_random_vs_trapdoor(ctx, srs_big):
+    tau, srs = srs_big
+    n = 1 << 18
+    seed = rng.fr_rand_stream(3, 64)
+    scalars = [(seed[i % 64] * (i + 1) + i * i) % R for i in range(n)]
+    assert KzgScheme(srs).commit(scalars) == _expect_from_trapdoor(tau, scalars)
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "two_values", "tiny_range", "top_bits_only", "sparse"])
+def test_commit_skewed_buckets_vs_trapdoor(ctx, srs_big, kind):
+    """Degenerate digit distributions: every window funnels its points into one or a few buckets
+    (bucket sizes up to 2^17), which the merge must still reduce in parallel."""
+    tau, srs = srs_big
+    n = 1 << 17
+    if kind == "all_equal":
+        scalars = [rng.fr_rand_stream(9, 1)[0]] * n
+    elif kind == "two_values":
+        a, b = rng.fr_rand_stream(9, 2)
+        scalars = [a if (i * 7) % 3 else b for i in range(n)]
+    elif kind == "tiny_range":
+        scalars = [(i * 2654435761) % 5 for i in range(n)]
+        scalars[-1] = 1
+    elif kind == "top_bits_only":
+        scalars = [((i % 3) + 1) << 252 for i in range(n)]
+    else:
+        scalars = [0] * n
+        for i in range(0, n, 1000):
+            scalars[i] = R - 1 - i
+        scalars[-1] = 7
+    assert KzgScheme(srs).commit(scalars) == _expect_from_trapdoor(tau, scalars)

@@ -41,19 +41,22 @@ def _stamp():
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
+def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "") -> Path:
+    """`defines` / `tag` build an experimental variant libtyplonk_b200_<tag>.so (selected at run
+    time with TYPLONK_B200_LIB); the default build takes neither."""
     LIBDIR.mkdir(exist_ok=True)
-    stamp_file = LIBDIR / "build.stamp"
-    stamp = _stamp()
-    if not force and LIB.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
-        return LIB
+    lib = LIBDIR / ("libtyplonk_b200_%s.so" % tag) if tag else LIB
+    stamp_file = LIBDIR / ("build%s.stamp" % ("_" + tag if tag else ""))
+    stamp = _stamp() + "|" + " ".join(defines)
+    if not force and lib.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+        return lib
     nvcc = _nvcc()
-    objdir = LIBDIR / "obj"
+    objdir = LIBDIR / ("obj" + ("_" + tag if tag else ""))
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src):
         obj = objdir / (src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -65,14 +68,16 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
     stamp_file.write_text(stamp)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    tags = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--tag=")]
+    path = build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs, tag=tags[0] if tags else "")
     print(path)

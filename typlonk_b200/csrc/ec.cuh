@@ -40,7 +40,7 @@ __device__ __forceinline__ G1Xyzz xyzz_load(const G1Xyzz* p) {
 }
 
 // 2 * (affine P), P != identity.
-static __device__ __noinline__ void xyzz_mdbl(G1Xyzz& r, const G1Affine& p) {
+static __device__ __noinline__ void xyzz_mdbl(G1Xyzz& r, const G1Affine p) {
   Fq u = fq_dbl(p.y);
   Fq v = fq_sqr(u);
   Fq w = fq_mul(u, v);
@@ -84,7 +84,9 @@ __device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const G1Affine& p_in, boo
   Fq rr = fq_sub(s2, acc.y);
   if (fq_is_zero(pp_)) {
     if (fq_is_zero(rr)) {
-      xyzz_mdbl(acc, p);
+      G1Xyzz d;  // separate object so `acc` itself never has its address taken
+      xyzz_mdbl(d, p);
+      acc = d;
     } else {
       acc = xyzz_identity();
     }

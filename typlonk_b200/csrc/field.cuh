@@ -123,11 +123,20 @@ __device__ __forceinline__ Fq fq_one() {
   for (int i = 0; i < 12; i++) r.v[i] = c[i];
   return r;
 }
+#ifdef TP_FQ_MUL_CALL
+// One shared copy of the 381-bit product (keeps hot loops inside the instruction cache).
+static __device__ __noinline__ Fq fq_mul(Fq a, Fq b) {
+  Fq r;
+  fq_mul_ptx(r.v, a.v, b.v);
+  return r;
+}
+#else
 __device__ __forceinline__ Fq fq_mul(const Fq& a, const Fq& b) {
   Fq r;
   fq_mul_ptx(r.v, a.v, b.v);
   return r;
 }
+#endif
 __device__ __forceinline__ Fq fq_sqr(const Fq& a) { return fq_mul(a, a); }
 __device__ __forceinline__ Fq fq_add(const Fq& a, const Fq& b) {
   Fq r;

@@ -20,13 +20,26 @@
 //   7. host           : Horner over the <= 64 window sums + affine conversion (serial tail; one
 //                       CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic), and
 //                       the all-gather of partial points when the MSM is sharded over GPUs.
+#include <stdlib.h>
+
+#include <utility>
+
 #include "common.cuh"
 
 namespace tp {
 
-#define MSM_CHUNK 16          // sorted entries per accumulate thread
-#define MSM_SEG 32            // buckets per bucket-reduce thread
 #define MSM_NONE 0x7fffffffu
+#define MSM_IDENT 0x80000000u   // partial slot holds the identity (point not stored)
+
+// Tunables (defaults chosen on B200; TP_MSM_CHUNK / TP_MSM_SEG / TP_MSM_C override for sweeps).
+static unsigned env_uint(const char* name, unsigned dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  long x = strtol(v, nullptr, 10);
+  return x > 0 ? (unsigned)x : dflt;
+}
+static unsigned msm_chunk() { static unsigned v = env_uint("TP_MSM_CHUNK", 64); return v; }   // sorted entries per accumulate thread
+static unsigned msm_seg() { static unsigned v = env_uint("TP_MSM_SEG", 8); return v; }        // buckets per bucket-reduce thread
 
 struct MsmPlan {
   unsigned c;        // window bits
@@ -37,12 +50,15 @@ struct MsmPlan {
 static MsmPlan msm_plan(size_t n) {
   MsmPlan best = {0, 0, 0};
   double best_cost = 1e300;
+  static unsigned force_c = env_uint("TP_MSM_C", 0);
   for (unsigned c = 2; c <= 21; c++) {
+    if (force_c && c != force_c) continue;
     unsigned nwin = (255 + c - 1) / c;
     unsigned top_bits = 255 - (nwin - 1) * c;
     if (top_bits == c) nwin++;  // signed carry out of a full top window
     double nb = (double)(1u << (c - 1));
     double cost = (double)n * nwin * 10.0 + nwin * nb * 40.0 + nwin * 3000.0;
+    if (top_bits + 6 < c && n > 4096) cost += 25e6;  // top window funnels ~n points into < nb/32 buckets
     if (cost < best_cost) {
       best_cost = cost;
       best = {c, nwin, 1u << (c - 1)};
@@ -151,19 +167,21 @@ __global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned*
 
 // ---- 4. segmented accumulation ---------------------------------------------------------------
 // part_keys[2t], part_keys[2t+1]: keys of the head / tail partial of chunk t (MSM_NONE if absent)
-__global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* __restrict__ bases,
+#ifndef TP_ACC_MIN_BLOCKS
+#define TP_ACC_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
                                                         const unsigned* __restrict__ sorted_idx,
                                                         const unsigned* __restrict__ sorted_key, unsigned m_total,
                                                         G1Xyzz* __restrict__ buckets, unsigned* __restrict__ part_keys,
-                                                        G1Xyzz* __restrict__ part_pts) {
+                                                        G1Xyzz* __restrict__ part_pts, unsigned chunk) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned start = t * MSM_CHUNK;
+  unsigned start = t * chunk;
   if (start >= m_total) return;
-  unsigned end = start + MSM_CHUNK < m_total ? start + MSM_CHUNK : m_total;
+  unsigned end = start + chunk < m_total ? start + chunk : m_total;
   G1Xyzz acc = xyzz_identity();
   unsigned cur = sorted_key[start];
   bool is_first_run = true;
-  part_keys[2 * t + 1] = MSM_NONE;
   for (unsigned e = start; e < end; e++) {
     unsigned key = sorted_key[e];
     if (key != cur) {
@@ -184,6 +202,7 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* __restri
   if (is_first_run) {
     part_keys[2 * t] = cur;
     xyzz_store(part_pts + 2 * t, acc);
+    part_keys[2 * t + 1] = cur | MSM_IDENT;  // single-run chunk: empty tail partial
   } else {
     part_keys[2 * t + 1] = cur;
     xyzz_store(part_pts + 2 * t + 1, acc);
@@ -191,28 +210,53 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const G1Affine* __restri
 }
 
 // ---- 5. boundary merge -----------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_msm_merge(const unsigned* __restrict__ part_keys,
-                                                   const G1Xyzz* __restrict__ part_pts, unsigned nslots,
-                                                   G1Xyzz* __restrict__ buckets) {
-  unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= nslots) return;
-  unsigned key = part_keys[j];
-  if (key == MSM_NONE) return;
-  // owner <=> previous valid slot has a different key
-  if (j > 0) {
-    unsigned pk = part_keys[j - 1];
-    if (pk == MSM_NONE && j > 1) pk = part_keys[j - 2];
-    if (pk == key) return;
+// The partial list (2 slots per chunk, keys non-decreasing) is reduced level by level: every
+// thread takes MERGE_B consecutive slots, sums runs of equal key with general XYZZ additions,
+// writes runs that lie strictly inside its block to their bucket (it is their only owner) and
+// emits a head / tail partial for the next level.  Run length -- i.e. bucket size -- only costs
+// extra levels of ~MERGE_B additions, so a bucket holding millions of points (small top window,
+// repeated scalars) is as parallel as a uniform one.  The last level is one thread.
+#define MERGE_B 16
+__global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restrict__ keys_in,
+                                                         const G1Xyzz* __restrict__ pts_in, unsigned nslots,
+                                                         G1Xyzz* __restrict__ buckets, unsigned* __restrict__ keys_out,
+                                                         G1Xyzz* __restrict__ pts_out, int final_level) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned start = final_level ? 0 : t * MERGE_B;
+  if (start >= nslots || (final_level && t != 0)) return;
+  unsigned end = final_level ? nslots : (start + MERGE_B < nslots ? start + MERGE_B : nslots);
+  unsigned k0 = keys_in[start];
+  unsigned cur = k0 & MSM_NONE;
+  G1Xyzz acc = (k0 & MSM_IDENT) ? xyzz_identity() : xyzz_load(pts_in + start);
+  bool is_first_run = true;
+  for (unsigned e = start + 1; e < end; e++) {
+    unsigned kraw = keys_in[e];
+    unsigned key = kraw & MSM_NONE;
+    if (key != cur) {
+      if (is_first_run && !final_level) {
+        keys_out[2 * t] = cur;
+        xyzz_store(pts_out + 2 * t, acc);
+        is_first_run = false;
+      } else {
+        xyzz_store(buckets + cur, acc);
+      }
+      cur = key;
+      acc = (kraw & MSM_IDENT) ? xyzz_identity() : xyzz_load(pts_in + e);
+    } else if (!(kraw & MSM_IDENT)) {
+      G1Xyzz o = xyzz_load(pts_in + e);
+      xyzz_add(acc, o);
+    }
   }
-  G1Xyzz acc = xyzz_load(part_pts + j);
-  for (unsigned q = j + 1; q < nslots; q++) {
-    unsigned k2 = part_keys[q];
-    if (k2 == MSM_NONE) continue;
-    if (k2 != key) break;
-    G1Xyzz o = xyzz_load(part_pts + q);
-    xyzz_add(acc, o);
+  if (final_level) {
+    xyzz_store(buckets + cur, acc);
+  } else if (is_first_run) {
+    keys_out[2 * t] = cur;
+    xyzz_store(pts_out + 2 * t, acc);
+    keys_out[2 * t + 1] = cur | MSM_IDENT;
+  } else {
+    keys_out[2 * t + 1] = cur;
+    xyzz_store(pts_out + 2 * t + 1, acc);
   }
-  xyzz_store(buckets + key, acc);
 }
 
 // ---- 6. bucket reduction ---------------------------------------------------------------------
@@ -332,25 +376,41 @@ static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size
     m_total = *(unsigned*)ctx->pinned;
   }
   if (m_total == 0) return TP_OK;  // all scalars zero
-  unsigned nchunks = (m_total + MSM_CHUNK - 1) / MSM_CHUNK;
-  TP_TRY(ensure(ctx, ctx->msm_part_keys, (size_t)2 * nchunks * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_part_pts, (size_t)2 * nchunks * sizeof(G1Xyzz)));
+  const unsigned chunk = msm_chunk();
+  unsigned nchunks = (m_total + chunk - 1) / chunk;
+  // first half: accumulate's partials; second half: ping-pong space for the merge levels
+  TP_TRY(ensure(ctx, ctx->msm_part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
     k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, sorted, sorted_keys, m_total, buckets,
                                                                      (unsigned*)ctx->msm_part_keys.p,
-                                                                     (G1Xyzz*)ctx->msm_part_pts.p);
+                                                                     (G1Xyzz*)ctx->msm_part_pts.p, chunk);
     TP_LAUNCH(ctx, "k_msm_accumulate");
   }
-  unsigned seg_len = pl.nbuck < MSM_SEG ? pl.nbuck : MSM_SEG;
+  unsigned seg_len = pl.nbuck < msm_seg() ? pl.nbuck : msm_seg();
   unsigned segs_per_win = pl.nbuck / seg_len;
   TP_TRY(ensure(ctx, ctx->msm_seg, (size_t)segs_per_win * pl.nwin * sizeof(G1Xyzz)));
   TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)pl.nwin * sizeof(G1Xyzz)));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
-    k_msm_merge<<<(2 * nchunks + 127) / 128, 128, 0, ctx->stream>>>((unsigned*)ctx->msm_part_keys.p,
-                                                                    (G1Xyzz*)ctx->msm_part_pts.p, 2 * nchunks, buckets);
-    TP_LAUNCH(ctx, "k_msm_merge");
+    {
+      unsigned* ka = (unsigned*)ctx->msm_part_keys.p;
+      G1Xyzz* pa = (G1Xyzz*)ctx->msm_part_pts.p;
+      unsigned* kb = ka + 2 * (size_t)nchunks;
+      G1Xyzz* pb = pa + 2 * (size_t)nchunks;
+      unsigned nslots = 2 * nchunks;
+      while (nslots > 2 * MERGE_B) {
+        unsigned nth = (nslots + MERGE_B - 1) / MERGE_B;
+        k_msm_merge_level<<<(nth + 127) / 128, 128, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 0);
+        TP_LAUNCH(ctx, "k_msm_merge_level");
+        std::swap(ka, kb);
+        std::swap(pa, pb);
+        nslots = 2 * nth;
+      }
+      k_msm_merge_level<<<1, 32, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 1);
+      TP_LAUNCH(ctx, "k_msm_merge_level");
+    }
     unsigned nthreads = segs_per_win * pl.nwin;
     k_msm_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(buckets, hist, pl.nbuck, seg_len, segs_per_win,
                                                                          pl.nwin, (G1Xyzz*)ctx->msm_seg.p);

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libtyplonk_b200.so"
+_LIB_PATH = Path(os.environ.get("TYPLONK_B200_LIB") or
+                 (Path(__file__).resolve().parent / "lib" / "libtyplonk_b200.so"))
 
 G1_BYTES = 97
 PROOF_FIXED_BYTES = 1472
