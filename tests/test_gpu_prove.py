@@ -106,3 +106,43 @@ def test_mul_chain_bytes(ctx, gates):
     oproof = oplonk.prove(oc, [3, 5], [0], BLINDERS)
     assert proof.to_bytes() == oproof.to_bytes()
     assert oplonk.verify(oc, oproof, use_trapdoor=True)
+
+
+# ---- BASELINE.json configs[1] / configs[2]: 2^16 byte parity with the C++ oracle, 2^20 verify ------
+
+def test_mul_chain_2_16_bytes_vs_c_oracle(ctx):
+    from oracle import coracle
+    from typlonk_b200 import field as F, synthetic
+    log_n = 16
+    n = 1 << log_n
+    circuit = synthetic.mul_chain_direct(ctx, log_n)
+    cols = synthetic.mul_chain_witness(n - 3, n)
+    proof = circuit.handle.prove([F.fr_vec_to_bytes(c) for c in cols], bytes(32 * n))
+    tau_b, sel, perm, ocols, pi = coracle.mul_chain_inputs(log_n)
+    assert perm == circuit.perm.perm
+    oc = coracle.Circuit(tau_b, sel, perm, n)
+    assert oc.fixed_commitments() == [F.g1_to_packed(c) + b"\x00" for c in circuit.fixed_commitments]
+    assert oc.prove(ocols, pi) == proof
+    oc.close()
+
+
+@pytest.mark.parametrize("log_n", [10, 20])
+def test_large_proof_verifies_with_trapdoor_verifier(ctx, log_n):
+    """verify() at BASELINE scale: the O(n) trapdoor verifier of the oracle accepts the GPU proof
+    (and rejects it after a one-byte corruption)."""
+    from oracle.pyoracle import fastverify
+    from typlonk_b200 import field as F, synthetic
+    n = 1 << log_n
+    circuit = synthetic.mul_chain_direct(ctx, log_n)
+    cols = synthetic.mul_chain_witness(n - 3, n)
+    proof = circuit.handle.prove([F.fr_vec_to_bytes(c) for c in cols], bytes(32 * n))
+    sig = [F.g1_from_abi(s) for s in circuit.handle.sigma_commitments()]
+    ok = fastverify.verify_trapdoor(proof, n, synthetic.tau(), circuit.perm.perm, circuit.fixed_commitments, sig)
+    assert ok
+    if log_n == 10:
+        bad = bytearray(proof)
+        bad[96 * 2 + 5] ^= 1  # a.y
+        assert not fastverify.verify_trapdoor(bytes(bad), n, synthetic.tau(), circuit.perm.perm,
+                                              circuit.fixed_commitments, sig)
+    circuit.handle.destroy()
+    circuit.srs.handle.destroy()

@@ -1,0 +1,115 @@
+"""CPU: host-side logic of the product package (tracing DSL mirror, permutation builder, synthetic
+circuit generator, proof framing) against the oracle, and the C-ABI library's exported surface.
+No compute calls -- there is no GPU here and the library has no CPU fallback."""
+import os
+import re
+
+import pytest
+
+from oracle.pyoracle import builder as obuilder, fields, permutation as operm, rng
+from typlonk_b200 import field as F, ffi, synthetic
+from typlonk_b200.permutation import PermutationBuilder
+from typlonk_b200.plonk import CircuitDescription, Proof
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class Pythagoras(CircuitDescription):
+    INPUTS = 3
+
+    @staticmethod
+    def run(inputs):
+        a, b, c = inputs
+        a = a.clone() * a
+        b = b.clone() * b
+        c = c.clone() * c
+        d = a + b
+        d.assert_eq(c)
+
+
+def test_tracer_matches_oracle_tracer():
+    gates, perm = Pythagoras.trace()
+    ogates, operm_ = obuilder.trace(obuilder.circuit_pythagoras, 3)
+    assert gates == ogates and perm.perm == operm_.perm
+    for g in (1, 2, 5, 13, 29):
+        gates, perm = synthetic.mul_chain_description(g).trace()
+        ogates, operm_ = obuilder.trace(obuilder.make_mul_chain(g), 2)
+        assert gates == ogates and perm.perm == operm_.perm
+
+
+def test_direct_mul_chain_structure_equals_traced():
+    for g in (1, 5, 13, 61, 125):
+        gates, perm = synthetic.mul_chain_structure(g)
+        tgates, tperm = synthetic.mul_chain_description(g).trace()
+        assert gates == tgates and perm.perm == tperm.perm
+    n = 64
+    cols = synthetic.mul_chain_witness(61, n, blind=list(range(1, 10)))
+    ocols = obuilder.witness_columns(obuilder.make_mul_chain(61), [3, 5], n, list(range(1, 10)))
+    assert cols == ocols
+
+
+def test_permutation_builder_invalid_tag():
+    pb = PermutationBuilder.with_rows(4)
+    assert pb.add_constrain((0, 0), (1, 3))
+    assert not pb.add_constrain((0, 0), (1, 4))      # j out of range -> Err(()) in the reference
+    assert pb.add_constrain((3, 0), (0, 0))          # sic: `i <= C` (permutation/src/lib.rs:46)
+    with pytest.raises(ValueError):
+        pb.add_constrains([((0, 0), (9, 9))])
+    opb = operm.PermutationBuilder.with_rows(4)
+    assert not opb.add_constrain((0, 0), (1, 4))
+
+
+def test_field_helpers_round_trip():
+    xs = rng.fr_rand_stream(8, 20) + [0, 1, fields.R_MOD - 1]
+    assert F.fr_vec_from_bytes(F.fr_vec_to_bytes(xs)) == xs
+    assert F.fr_vec_to_bytes(xs) == fields.fr_vec_to_mont_bytes(xs)
+    assert F.g1_from_packed(F.g1_to_packed(None)) is None
+    assert F.g1_serialize_unchecked(None)[-1] == 0x40
+
+
+def test_proof_framing():
+    p = Proof(bytes(range(256)) * 5 + bytes(192), [0, 1, 2])
+    raw = p.to_bytes()
+    assert len(raw) == 1472 + 8 + 3 * 32 and raw[1472:1480] == (3).to_bytes(8, "little")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = ffi.lib()
+    header = open(os.path.join(ROOT, "include", "typlonk_b200.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|const char\*)\s+(tp_[a-z0-9_]+)\(", header, flags=re.M)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert sorted(ffi.SYMBOLS) == declared
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product refuses to run instead of falling back to a CPU path."""
+    import ctypes
+    h = ctypes.c_void_p()
+    rc = ffi.lib().tp_ctx_create(0, None, ctypes.byref(h))
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        assert rc == 7  # TP_ERR_NO_DEVICE
+        with pytest.raises(ffi.TyplonkError):
+            ffi.Context(0)
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "typlonk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "oracle/" not in text.replace(
+                    "independent of oracle/", "").replace("Product code -- independent of oracle/.", ""), f
+
+
+def test_host_fr_rand_stream_matches_oracle():
+    assert ffi.fr_rand_stream(5, 12) == fields.fr_vec_to_mont_bytes(rng.fr_rand_stream(5, 12))
+    assert synthetic.tau() == rng.fr_rand_stream(1, 1)[0]
+    assert synthetic.blinders() == rng.fr_rand_stream(2, 9)

@@ -39,7 +39,7 @@ static unsigned env_uint(const char* name, unsigned dflt) {
   return x > 0 ? (unsigned)x : dflt;
 }
 static unsigned msm_chunk() { static unsigned v = env_uint("TP_MSM_CHUNK", 64); return v; }   // sorted entries per accumulate thread
-static unsigned msm_seg() { static unsigned v = env_uint("TP_MSM_SEG", 8); return v; }        // buckets per bucket-reduce thread
+static unsigned msm_seg() { static unsigned v = env_uint("TP_MSM_SEG", 16); return v; }        // buckets per bucket-reduce thread
 
 struct MsmPlan {
   unsigned c;        // window bits
