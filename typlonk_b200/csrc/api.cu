@@ -35,7 +35,7 @@ struct tp_circuit {
   Fr* z_coef = nullptr;
   Fr* buf4[6] = {0};     // a4 b4 c4 z4 pi4 num4
   Fr* t = nullptr;       // 3n
-  Fr* q = nullptr;       // n
+  Fr* q[6] = {0};        // opening quotients (a, b, c, z, z-omega, r), n each
   Fr* r = nullptr;       // n
   std::vector<void*> allocs;
 };
@@ -84,7 +84,7 @@ int tp_ctx_create(int device, void* stream, tp_ctx** out) {
     }
     ctx->own_stream = true;
   }
-  ctx->pinned_cap = 1 << 16;
+  ctx->pinned_cap = 1 << 20;
   if (cudaMallocHost(&ctx->pinned, ctx->pinned_cap) != cudaSuccess) {
     delete ctx;
     return TP_ERR_CUDA;
@@ -316,7 +316,7 @@ static int circuit_alloc(tp_ctx* ctx, tp_circuit* c) {
   TP_TRY(dmalloc(ctx, c, &c->z_coef, n));
   for (int i = 0; i < 6; i++) TP_TRY(dmalloc(ctx, c, &c->buf4[i], 4 * n));
   TP_TRY(dmalloc(ctx, c, &c->t, 3 * n));
-  TP_TRY(dmalloc(ctx, c, &c->q, n));
+  for (int i = 0; i < 6; i++) TP_TRY(dmalloc(ctx, c, &c->q[i], n));
   TP_TRY(dmalloc(ctx, c, &c->r, n));
   return TP_OK;
 }
@@ -451,7 +451,10 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
   // round 1 commitments (proof.rs:107-110)
   uint8_t com[4][TP_G1_BYTES];
-  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, srs, c->adv_coef[i], n, com[i]));
+  {
+    const Fr* sets[3] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2]};
+    TP_TRY(msm_batch_dev(ctx, srs, sets, 3, n, com));
+  }
   HFr beta, gamma;
   tph::challenges2({com[0], com[1], com[2]}, &beta, &gamma);
   // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321)
@@ -505,10 +508,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   HFr omega = omega_for_log(c->log_n);
   const Fr* polys[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->z_coef};
   HFr points[5] = {zeta, zeta, zeta, zeta, zeta * omega};
-  for (int i = 0; i < 5; i++) {
-    TP_TRY(poly_open_dev(ctx, polys[i], n, to_dev(points[i]), c->q, &ev[i]));
-    TP_TRY(msm_dev(ctx, srs, c->q, n - 1, wit[i]));
-  }
+  for (int i = 0; i < 5; i++) TP_TRY(poly_open_dev(ctx, polys[i], n, to_dev(points[i]), c->q[i], &ev[i]));
   // linearisation (proof.rs:376-439)
   HFr sig_bar[2], pi_bar;
   for (int i = 0; i < 2; i++) TP_TRY(poly_open_dev(ctx, c->sig_coef[i], n, to_dev(zeta), nullptr, &sig_bar[i]));
@@ -541,11 +541,17 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   HFr constant = pi_bar - ab_zw * (gamma + cc) - alpha2 * l0;
   TP_TRY(lincomb_dev(ctx, terms, 10, to_dev(constant), n, c->r));
   HFr r_bar;
-  TP_TRY(poly_open_dev(ctx, c->r, n, to_dev(zeta), c->q, &r_bar));
-  TP_TRY(msm_dev(ctx, srs, c->q, n - 1, wit[5]));
-  // t commitments (proof.rs:181)
+  TP_TRY(poly_open_dev(ctx, c->r, n, to_dev(zeta), c->q[5], &r_bar));
+  // the six opening witnesses and the three t commitments (proof.rs:149,162,163,175,181) are
+  // independent of one another: one batched MSM.  (q[i][n-1] == 0, so length n is exact.)
   uint8_t tcom[3][TP_G1_BYTES];
-  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, srs, c->t + (size_t)i * n, n, tcom[i]));
+  {
+    const Fr* sets[9] = {c->q[0], c->q[1], c->q[2], c->q[3], c->q[4], c->q[5], c->t, c->t + n, c->t + 2 * n};
+    uint8_t outs[9][TP_G1_BYTES];
+    TP_TRY(msm_batch_dev(ctx, srs, sets, 9, n, outs));
+    for (int i = 0; i < 6; i++) memcpy(wit[i], outs[i], TP_G1_BYTES);
+    for (int i = 0; i < 3; i++) memcpy(tcom[i], outs[6 + i], TP_G1_BYTES);
+  }
 
   uint8_t* w = proof_out;
   for (int i = 0; i < 3; i++) {

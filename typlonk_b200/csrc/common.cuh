@@ -166,6 +166,9 @@ int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, co
 int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw);
 // msm.cu : result as host Jacobian (this rank's shard only when sharded = false, else combined)
 int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]);
+// `batch` MSMs over the same bases in one pipeline (out[b] = sum_i scalars[b][i] * srs[i])
+int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len,
+                  uint8_t (*out)[TP_G1_BYTES]);
 void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]);
 // poly.cu
 int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],

@@ -68,11 +68,17 @@ static MsmPlan msm_plan(size_t n) {
 }
 
 // ---- 1. digits + histogram/rank ----------------------------------------------------------
-__global__ void k_msm_digits(const Fr* __restrict__ scalars, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
+#define MSM_MAX_BATCH 16
+struct MsmScalarSets {
+  const Fr* p[MSM_MAX_BATCH];
+};
+// blockIdx.y = batch element; its windows are numbered b * nwin + w in every later stage.
+__global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
                              unsigned* __restrict__ hist, unsigned* __restrict__ keys, unsigned* __restrict__ ranks) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fr s = fr_from_mont(fr_load(scalars + i));
+  const unsigned wbase = blockIdx.y * nwin;
+  Fr s = fr_from_mont(fr_load(sets.p[blockIdx.y] + i));
   unsigned carry = 0;
   for (unsigned w = 0; w < nwin; w++) {
     unsigned bit = w * c;
@@ -94,13 +100,13 @@ __global__ void k_msm_digits(const Fr* __restrict__ scalars, size_t n, unsigned 
         carry = 1;
       }
       if (mag != 0) {
-        unsigned k = w * nbuck + (mag - 1);
+        unsigned k = (wbase + w) * nbuck + (mag - 1);
         rank = atomicAdd(&hist[k], 1u);
         key = k | (neg << 31);
       }
     }
-    keys[(size_t)w * n + i] = key;
-    ranks[(size_t)w * n + i] = rank;
+    keys[(size_t)(wbase + w) * n + i] = key;
+    ranks[(size_t)(wbase + w) * n + i] = rank;
   }
 }
 
@@ -337,15 +343,25 @@ static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, si
   return TP_OK;
 }
 
-// This rank's partial sum over SRS points [first, first+len) with the matching scalars.
-static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size_t len, tph::HG1* result) {
-  *result = tph::HG1::identity();
-  if (len == 0) return TP_OK;
+// This rank's partial sums over `len` bases for `batch` scalar vectors at once: all vectors share
+// one sort / accumulate / merge / reduce pipeline (window index = b * nwin + w), which amortises the
+// latency-bound reduction tail and the launch overhead over the batch.
+static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* const* scalars, int batch, size_t len,
+                     tph::HG1* results) {
+  for (int b = 0; b < batch; b++) results[b] = tph::HG1::identity();
+  if (len == 0 || batch == 0) return TP_OK;
+  if (batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: batch too large");
   if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
   MsmPlan pl = msm_plan(len);
-  size_t nkeys = (size_t)pl.nwin * pl.nbuck;
-  size_t total = (size_t)pl.nwin * len;
-  if (total >= ((size_t)1 << 31)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
+  if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nwin * pl.nbuck * batch >= ((size_t)1 << 30)) {
+    if (batch == 1) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
+    int half = batch / 2;  // split the batch until the entry count fits 31 bits
+    TP_TRY(msm_local(ctx, bases, scalars, half, len, results));
+    return msm_local(ctx, bases, scalars + half, batch - half, len, results + half);
+  }
+  const unsigned nwin_total = pl.nwin * batch;
+  size_t nkeys = (size_t)nwin_total * pl.nbuck;
+  size_t total = (size_t)nwin_total * len;
   TP_TRY(ensure(ctx, ctx->msm_hist, (nkeys + 1) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_offsets, (nkeys + 1) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_keys, total * sizeof(unsigned)));
@@ -364,8 +380,10 @@ static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size
   {
     ProfScope prof(ctx, TP_PHASE_MSM_SORT);
     TP_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (nkeys + 1) * sizeof(unsigned), ctx->stream));
-    k_msm_digits<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(scalars, len, pl.c, pl.nwin, pl.nbuck, hist,
-                                                                         keys, ranks);
+    MsmScalarSets sets;
+    for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < batch ? b : 0];
+    dim3 grid((unsigned)((len + 255) / 256), (unsigned)batch);
+    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, hist, keys, ranks);
     TP_LAUNCH(ctx, "k_msm_digits");
     TP_TRY(exclusive_scan_u32(ctx, hist, offsets, nkeys + 1));
     k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, sorted,
@@ -390,8 +408,8 @@ static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size
   }
   unsigned seg_len = pl.nbuck < msm_seg() ? pl.nbuck : msm_seg();
   unsigned segs_per_win = pl.nbuck / seg_len;
-  TP_TRY(ensure(ctx, ctx->msm_seg, (size_t)segs_per_win * pl.nwin * sizeof(G1Xyzz)));
-  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)pl.nwin * sizeof(G1Xyzz)));
+  TP_TRY(ensure(ctx, ctx->msm_seg, (size_t)segs_per_win * nwin_total * sizeof(G1Xyzz)));
+  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)nwin_total * sizeof(G1Xyzz)));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
     {
@@ -411,64 +429,82 @@ static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* scalars, size
       k_msm_merge_level<<<1, 32, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 1);
       TP_LAUNCH(ctx, "k_msm_merge_level");
     }
-    unsigned nthreads = segs_per_win * pl.nwin;
+    unsigned nthreads = segs_per_win * nwin_total;
     k_msm_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(buckets, hist, pl.nbuck, seg_len, segs_per_win,
-                                                                         pl.nwin, (G1Xyzz*)ctx->msm_seg.p);
+                                                                         nwin_total, (G1Xyzz*)ctx->msm_seg.p);
     TP_LAUNCH(ctx, "k_msm_bucket_reduce");
-    k_msm_window_reduce<<<pl.nwin, 128, 0, ctx->stream>>>((G1Xyzz*)ctx->msm_seg.p, segs_per_win,
-                                                          (G1Xyzz*)ctx->msm_winsums.p);
+    k_msm_window_reduce<<<nwin_total, 128, 0, ctx->stream>>>((G1Xyzz*)ctx->msm_seg.p, segs_per_win,
+                                                             (G1Xyzz*)ctx->msm_winsums.p);
     TP_LAUNCH(ctx, "k_msm_window_reduce");
   }
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)pl.nwin * sizeof(G1Xyzz),
+  if ((size_t)nwin_total * sizeof(G1Xyzz) > ctx->pinned_cap) return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)nwin_total * sizeof(G1Xyzz),
                                   cudaMemcpyDeviceToHost, ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  // serial tail on the host: result = sum_w 2^(c w) * W_w
+  // serial tail on the host: result_b = sum_w 2^(c w) * W_{b,w}
   const uint8_t* ws = (const uint8_t*)ctx->pinned;
-  tph::HG1 acc = tph::HG1::identity();
-  for (int w = (int)pl.nwin - 1; w >= 0; w--) {
-    for (unsigned d = 0; d < pl.c; d++) acc = tph::g1_dbl(acc);
-    tph::HFq x, y, zz, zzz;
-    memcpy(x.v, ws + (size_t)w * 192, 48);
-    memcpy(y.v, ws + (size_t)w * 192 + 48, 48);
-    memcpy(zz.v, ws + (size_t)w * 192 + 96, 48);
-    memcpy(zzz.v, ws + (size_t)w * 192 + 144, 48);
-    acc = tph::g1_add(acc, tph::g1_from_xyzz(x, y, zz, zzz));
+  for (int b = 0; b < batch; b++) {
+    tph::HG1 acc = tph::HG1::identity();
+    for (int w = (int)pl.nwin - 1; w >= 0; w--) {
+      for (unsigned d = 0; d < pl.c; d++) acc = tph::g1_dbl(acc);
+      const uint8_t* q = ws + ((size_t)b * pl.nwin + w) * 192;
+      tph::HFq x, y, zz, zzz;
+      memcpy(x.v, q, 48);
+      memcpy(y.v, q + 48, 48);
+      memcpy(zz.v, q + 96, 48);
+      memcpy(zzz.v, q + 144, 48);
+      acc = tph::g1_add(acc, tph::g1_from_xyzz(x, y, zz, zzz));
+    }
+    results[b] = acc;
   }
-  *result = acc;
+  return TP_OK;
+}
+
+int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len,
+                  uint8_t (*out)[TP_G1_BYTES]) {
+  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
+  if (batch <= 0 || batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: bad batch size");
+  ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
+  tph::HG1 res[MSM_MAX_BATCH];
+  if (ctx->world <= 1) {
+    TP_TRY(msm_local(ctx, srs->g1, scalars_dev, batch, len, res));
+  } else {
+    // contiguous point-range shard; every rank holds the full SRS and scalar vectors
+    size_t per = (len + ctx->world - 1) / ctx->world;
+    size_t first = per * ctx->rank;
+    size_t cnt = first >= len ? 0 : (len - first < per ? len - first : per);
+    const Fr* shifted[MSM_MAX_BATCH];
+    for (int b = 0; b < batch; b++) shifted[b] = scalars_dev[b] + first;
+    tph::HG1 part[MSM_MAX_BATCH];
+    TP_TRY(msm_local(ctx, srs->g1 + first, shifted, batch, cnt, part));
+    const size_t per_rank = (size_t)144 * batch;
+    std::vector<uint8_t> send(per_rank), recv(per_rank * ctx->world);
+    for (int b = 0; b < batch; b++) {
+      memcpy(&send[(size_t)b * 144], part[b].x.v, 48);
+      memcpy(&send[(size_t)b * 144 + 48], part[b].y.v, 48);
+      memcpy(&send[(size_t)b * 144 + 96], part[b].z.v, 48);
+    }
+    if (!ctx->allgather || ctx->allgather(ctx->allgather_user, send.data(), recv.data(), per_rank) != 0)
+      return fail(ctx, TP_ERR_COLLECTIVE, "msm: all-gather of partial points failed");
+    for (int b = 0; b < batch; b++) {
+      res[b] = tph::HG1::identity();
+      for (int r = 0; r < ctx->world; r++) {
+        const uint8_t* q = recv.data() + (size_t)r * per_rank + (size_t)b * 144;
+        tph::HG1 p;
+        memcpy(p.x.v, q, 48);
+        memcpy(p.y.v, q + 48, 48);
+        memcpy(p.z.v, q + 96, 48);
+        res[b] = tph::g1_add(res[b], p);
+      }
+    }
+  }
+  for (int b = 0; b < batch; b++) encode_g1(res[b], out[b]);
   return TP_OK;
 }
 
 int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]) {
-  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
-  ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
-  tph::HG1 res;
-  if (ctx->world <= 1) {
-    TP_TRY(msm_local(ctx, srs->g1, scalars_dev, len, &res));
-  } else {
-    // contiguous point-range shard; every rank holds the full SRS and scalar vector
-    size_t per = (len + ctx->world - 1) / ctx->world;
-    size_t first = per * ctx->rank;
-    size_t cnt = first >= len ? 0 : (len - first < per ? len - first : per);
-    tph::HG1 part;
-    TP_TRY(msm_local(ctx, srs->g1 + first, scalars_dev + first, cnt, &part));
-    std::vector<uint8_t> recv((size_t)ctx->world * 144);
-    uint8_t send[144];
-    memcpy(send, part.x.v, 48);
-    memcpy(send + 48, part.y.v, 48);
-    memcpy(send + 96, part.z.v, 48);
-    if (!ctx->allgather || ctx->allgather(ctx->allgather_user, send, recv.data(), 144) != 0)
-      return fail(ctx, TP_ERR_COLLECTIVE, "msm: all-gather of partial points failed");
-    res = tph::HG1::identity();
-    for (int r = 0; r < ctx->world; r++) {
-      tph::HG1 p;
-      memcpy(p.x.v, recv.data() + (size_t)r * 144, 48);
-      memcpy(p.y.v, recv.data() + (size_t)r * 144 + 48, 48);
-      memcpy(p.z.v, recv.data() + (size_t)r * 144 + 96, 48);
-      res = tph::g1_add(res, p);
-    }
-  }
-  encode_g1(res, out);
-  return TP_OK;
+  const Fr* one[1] = {scalars_dev};
+  return msm_batch_dev(ctx, srs, one, 1, len, (uint8_t(*)[TP_G1_BYTES])out);
 }
 
 }  // namespace tp
