@@ -93,6 +93,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import coracle  # the only product-side place allowed to execute oracle/
     log_n = min(args.log_n, args.ref_log_n)
     res = coracle.bench_prove(log_n, steps=args.steps, warmup=min(args.warmup, 1))
@@ -245,10 +247,12 @@ def main():
         "roofline": roofline,
         "phases_ms_per_step": {p: round(prof[p][0] / args.steps, 3) for p in PHASES},
         "imad_peak_per_s": imad_wide,
+        "proof_sha256": __import__("hashlib").sha256(proof).hexdigest()[:16],
         "cpu_baseline": None,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
+            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
             from oracle import coracle
             res = coracle.bench_prove(min(log_n, args.ref_log_n), steps=1, warmup=0)
             rl = min(log_n, args.ref_log_n)
