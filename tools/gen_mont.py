@@ -120,9 +120,13 @@ def cond_sub_p(pr, t, d, out, mod, n):
         pr.emit("selp.u32", out[i], t[i], d[i], "%pb")
 
 
-def build_mul(mod, n, reduce_final=True, mod_regs=False):
+def build_mul(mod, n, reduce_final=True, mod_regs=False, m0_reg=False, special=False):
+    """special=True replaces products by modulus limbs equal to 1 / 0xffffffff (Fr's two lowest
+    limbs) with additions: 16 of the 128 products of an Fr multiplication."""
     pl = ["p%d" % i for i in range(n)] if mod_regs else limbs(mod, n)
     m0 = (-pow(mod, -1, 1 << 32)) & MASK
+    if m0_reg:
+        m0 = "m0"  # register operand, see main()
     pr = Prog()
     a = ["a%d" % i for i in range(n)]
     b = ["b%d" % i for i in range(n)]
@@ -132,8 +136,19 @@ def build_mul(mod, n, reduce_final=True, mod_regs=False):
     def cmad(acc, src, off, m):
         """acc[j],acc[j+1] += src[j+off]*m for j = 0,2,..; leaves carry in CC."""
         for j in range(0, n, 2):
-            pr.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", acc[j], src[j + off], m, acc[j])
-            pr.emit("madc.hi.cc.u32", acc[j + 1], src[j + off], m, acc[j + 1], drop_carry=(off == 1 and j == n - 2))
+            lim = src[j + off]
+            if special and lim == 1 and j == 0:
+                # m * 1: no multiplier needed
+                pr.emit("add.cc.u32", acc[j], acc[j], m)
+                pr.emit("addc.cc.u32", acc[j + 1], acc[j + 1], 0)
+                continue
+            if special and lim == MASK and j == 0:
+                # m * (2^32 - 1) = (hm : nm) with nm = -m, hm = m - (m != 0), prepared by the caller
+                pr.emit("add.cc.u32", acc[j], acc[j], "nm")
+                pr.emit("addc.cc.u32", acc[j + 1], acc[j + 1], "hm")
+                continue
+            pr.emit("mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32", acc[j], lim, m, acc[j])
+            pr.emit("madc.hi.cc.u32", acc[j + 1], lim, m, acc[j + 1], drop_carry=(off == 1 and j == n - 2))
 
     def mad_n_redc(even, odd, bi, first):
         if first:
@@ -153,6 +168,9 @@ def build_mul(mod, n, reduce_final=True, mod_regs=False):
             cmad(even, a, 0, bi)
             pr.emit("addc.u32", odd[n - 1], odd[n - 1], 0, drop_carry=True)
         pr.emit("mul.lo.u32", "mi", even[0], m0)
+        if special and pl[1] == MASK:
+            pr.emit("sub.cc.u32", "nm", 0, "mi")   # borrow <=> mi != 0
+            pr.emit("subc.u32", "hm", "mi", 0)
         cmad(odd, pl, 1, "mi")
         cmad(even, pl, 0, "mi")
         pr.emit("addc.u32", odd[n - 1], odd[n - 1], 0, drop_carry=True)
@@ -204,10 +222,10 @@ def build_sub(mod, n):
     return pr
 
 
-def check(name, mod, n, trials=300, mod_regs=False):
+def check(name, mod, n, trials=300, mod_regs=False, m0_reg=False, special=False):
     R = 1 << (32 * n)
     rinv = pow(R, -1, mod)
-    mul = build_mul(mod, n, mod_regs=mod_regs)
+    mul = build_mul(mod, n, mod_regs=mod_regs, m0_reg=m0_reg, special=special)
     add = build_add(mod, n)
     sub = build_sub(mod, n)
     rnd = random.Random(1234 + n)
@@ -222,6 +240,7 @@ def check(name, mod, n, trials=300, mod_regs=False):
             env["b%d" % i] = v
         for i, v in enumerate(limbs(mod, n)):
             env["p%d" % i] = v
+        env["m0"] = (-pow(mod, -1, 1 << 32)) & MASK
         out = mul.run(dict(env))
         got = sum(out["r%d" % i] << (32 * i) for i in range(n))
         assert got == x * y * rinv % mod, (name, "mul", hex(x), hex(y))
@@ -235,8 +254,10 @@ def check(name, mod, n, trials=300, mod_regs=False):
     print("%s: %d cases ok; mul = %d PTX instrs (%d mul/mad)" % (name, len(cases), len(mul.ins), nmad))
 
 
-def emit_fn(fname, pr, n, mod_sym=None):
+def emit_fn(fname, pr, n, mod_sym=None, m0_sym=None):
     regmap = {}
+    if m0_sym:
+        regmap["m0"] = "%%%d" % (3 * n)
     if mod_sym:
         for i in range(n):
             regmap["p%d" % i] = "%%%d" % (3 * n + i)
@@ -248,7 +269,7 @@ def emit_fn(fname, pr, n, mod_sym=None):
     lines = []
     lines.append("__device__ __forceinline__ void %s(uint32_t* __restrict__ r, const uint32_t* a, const uint32_t* b) {" % fname)
     lines.append("  asm(\"{\\n\\t\"")
-    lines.append("      \".reg .u32 e<%d>, o<%d>, mi, brw;\\n\\t\"" % (n, n))
+    lines.append("      \".reg .u32 e<%d>, o<%d>, mi, nm, hm, brw;\\n\\t\"" % (n, n))
     lines.append("      \".reg .pred %%pb;\\n\\t\"")
     for ln in body:
         lines.append("      \"%s\\n\\t\"" % ln.replace("%pb", "%%pb"))
@@ -257,6 +278,8 @@ def emit_fn(fname, pr, n, mod_sym=None):
     ins = ", ".join("\"r\"(a[%d])" % i for i in range(n)) + ", " + ", ".join("\"r\"(b[%d])" % i for i in range(n))
     if mod_sym:
         ins += ", " + ", ".join("\"r\"(%s[%d])" % (mod_sym, i) for i in range(n))
+    if m0_sym:
+        ins += ", \"r\"(%s)" % m0_sym
     lines.append("      : %s" % outs)
     lines.append("      : %s);" % ins)
     lines.append("}")
@@ -266,6 +289,8 @@ def emit_fn(fname, pr, n, mod_sym=None):
 def main():
     check("Fr", R_MOD, 8)
     check("Fr(mod in regs)", R_MOD, 8, mod_regs=True)
+    check("Fr(m0 in a register)", R_MOD, 8, m0_reg=True)
+    check("Fr(m0 in a register, low limbs by addition)", R_MOD, 8, m0_reg=True, special=True, trials=3000)
     check("Fq", Q_MOD, 12)
     if "--check-only" in sys.argv:
         return
@@ -281,11 +306,17 @@ def main():
         out.append("#define TP_%s_ONE %s   // R mod p" % (nm, carr(R, n)))
         out.append("#define TP_%s_R2 %s   // R^2 mod p" % (nm, carr(R * R % mod, n)))
         out.append("#define TP_%s_MODM2 %s   // p - 2 (Fermat inversion exponent)" % (nm, carr(mod - 2, n)))
+    # Fr has -r^-1 mod 2^32 = 0xffffffff.  When ptxas sees that immediate it rewrites mi = -t0 and
+    # then splits every reduction product mi * r_j into IMAD.X + IMAD.HI.U32.X (6.6 clk on the
+    # FMA-heavy pipe instead of 4 for the fused IMAD.WIDE.U32.X) -- about half of all products of
+    # the multiplication.  Feeding the constant through a __constant__ word keeps it opaque: 8 extra
+    # 32-bit IMADs, all 128 products fused.  Fq's 0xfffcfffd does not trigger the rewrite.
+    out.append("static __constant__ uint32_t TP_FR_M0 = 0xffffffffu;   // -r^-1 mod 2^32, deliberately not an immediate")
     for name, mod, n in (("fr", R_MOD, 8), ("fq", Q_MOD, 12)):
-        # NB: for Fr ptxas splits the modulus products into IMAD + IMAD.HI.U32 (64-bit addend)
-        # instead of IMAD.WIDE.U32.X whether the limbs are immediates or constant-bank operands
-        # (mod_regs=True); immediates cost 10 fewer registers, so both fields use them.
-        out.append(emit_fn("%s_mul_ptx" % name, build_mul(mod, n), n))
+        if name == "fr":
+            out.append(emit_fn("fr_mul_ptx", build_mul(mod, n, m0_reg=True, special=True), n, m0_sym="TP_FR_M0"))
+        else:
+            out.append(emit_fn("%s_mul_ptx" % name, build_mul(mod, n), n))
         out.append(emit_fn("%s_add_ptx" % name, build_add(mod, n), n))
         out.append(emit_fn("%s_sub_ptx" % name, build_sub(mod, n), n))
     dst = Path(__file__).resolve().parent.parent / "typlonk_b200" / "csrc" / "mont_gen.cuh"

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Standalone MSM timing (device-resident scalars): python tools/msm_bench.py --log-n 20 [--reps 3]
-Prints one JSON line with per-phase ms.  Env TP_MSM_CHUNK / TP_MSM_SEG / TP_MSM_C tune the kernels."""
+Prints one JSON line with per-phase ms.  Env TP_MSM_CHUNK / TP_MSM_C / TP_MSM_LEVELS tune the kernels."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -35,6 +35,6 @@ e1.record(); torch.cuda.synchronize()
 assert out == first
 prof = ctx.prof_get()
 print(json.dumps({"log_n": a.log_n, "ms": e0.elapsed_time(e1) / a.reps,
-                  "env": {k: os.environ.get(k) for k in ("TP_MSM_CHUNK", "TP_MSM_SEG", "TP_MSM_C")},
+                  "env": {k: os.environ.get(k) for k in ("TP_MSM_CHUNK", "TP_MSM_C", "TP_MSM_LEVELS")},
                   "phases": {k: round(v[0] / a.reps, 3) for k, v in prof.items() if k.startswith("msm")},
                   "digest": out[:8].hex()}))

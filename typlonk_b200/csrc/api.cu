@@ -178,39 +178,61 @@ int tp_launch_count(tp_ctx* ctx, uint64_t* out) {
 }
 
 // ---- SRS ------------------------------------------------------------------------------------
+// Allocates the SRS with as many fixed-base table levels as the MSM plan wants and the device can
+// spare (at most ~45 % of what is free; level 0 alone when nothing more fits).
+static int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
+  tp_srs* s = new tp_srs();
+  s->len = len;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+  size_t budget = (size_t)(0.45 * (double)free_b);
+  // the window size is planned for the point range ONE rank accumulates (set the shard before
+  // creating the SRS): a shard of n / world points wants a smaller window than n points
+  size_t per_rank = (len + (size_t)ctx->world - 1) / (size_t)ctx->world;
+  for (int attempt = 0; attempt < 2; attempt++) {
+    msm_choose_tables(per_rank, len, attempt == 0 ? budget : 0, &s->c, &s->levels);
+    cudaError_t e = cudaMalloc(&s->g1, (len ? len : 1) * (size_t)s->levels * sizeof(G1Affine));
+    if (e == cudaSuccess) {
+      *out = s;
+      return TP_OK;
+    }
+    cudaGetLastError();
+    s->g1 = nullptr;
+  }
+  delete s;
+  return fail(ctx, TP_ERR_CUDA, "srs: out of device memory");
+}
+
 int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out) {
   if (!out || !tau) return fail(ctx, TP_ERR_INVALID_ARG, "srs_from_secret: null argument");
   size_t len = gates + 3;
-  tp_srs* s = new tp_srs();
-  cudaError_t e = cudaMalloc(&s->g1, len * sizeof(G1Affine));
-  if (e != cudaSuccess) {
-    delete s;
-    return fail(ctx, TP_ERR_CUDA, cudaGetErrorString(e));
-  }
-  s->len = len;
+  tp_srs* s = nullptr;
+  TP_TRY(srs_alloc(ctx, len, &s));
   HFr t;
   memcpy(t.v, tau, 32);
   int rc = srs_generate_dev(ctx, t, len, s->g1);
+  if (rc == TP_OK) rc = srs_build_levels_dev(ctx, s);
+  if (rc == TP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TP_ERR_CUDA, "srs: generation failed");
   if (rc != TP_OK) {
     cudaFree(s->g1);
     delete s;
     return rc;
   }
-  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *out = s;
   return TP_OK;
 }
 int tp_srs_upload(tp_ctx* ctx, const uint8_t* g1_xy, size_t len, tp_srs** out) {
   if (!out || (!g1_xy && len)) return fail(ctx, TP_ERR_INVALID_ARG, "srs_upload: null argument");
-  tp_srs* s = new tp_srs();
-  cudaError_t e = cudaMalloc(&s->g1, (len ? len : 1) * sizeof(G1Affine));
-  if (e != cudaSuccess) {
+  tp_srs* s = nullptr;
+  TP_TRY(srs_alloc(ctx, len, &s));
+  int rc = h2d(ctx, s->g1, g1_xy, len * 96);
+  if (rc == TP_OK) rc = srs_build_levels_dev(ctx, s);
+  if (rc == TP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TP_ERR_CUDA, "srs: upload failed");
+  if (rc != TP_OK) {
+    cudaFree(s->g1);
     delete s;
-    return fail(ctx, TP_ERR_CUDA, cudaGetErrorString(e));
+    return rc;
   }
-  s->len = len;
-  TP_TRY(h2d(ctx, s->g1, g1_xy, len * 96));
-  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   *out = s;
   return TP_OK;
 }

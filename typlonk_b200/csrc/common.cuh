@@ -70,8 +70,13 @@ struct tp_ctx {
 };
 
 struct tp_srs {
-  tp::G1Affine* g1 = nullptr;  // device, packed 96 B
+  // device, packed 96 B per point: `levels` copies of the SRS, g1[k * len + i] = 2^(c k) * [tau^i]G.
+  // Level 0 is the SRS itself (what the ABI uploads / downloads); levels >= 1 are the fixed-base
+  // window tables of the MSM (msm.cu), built once by srs_build_levels_dev.
+  tp::G1Affine* g1 = nullptr;
   size_t len = 0;
+  unsigned c = 0;       // MSM window bits the tables were built for
+  unsigned levels = 1;
 };
 
 namespace tp {
@@ -203,8 +208,10 @@ int sigma_tables_dev(tp_ctx* ctx, const uint64_t* perm_dev, size_t n, const Fr* 
                      Fr* sigma[3]);
 int pad_copy_dev(tp_ctx* ctx, const Fr* in, size_t len, Fr* out, size_t out_len);
 int rotate_copy_dev(tp_ctx* ctx, const Fr* in, size_t n, size_t shift, Fr* out);
+void msm_choose_tables(size_t len, size_t table_len, size_t budget_bytes, unsigned* c_out, unsigned* levels_out);
 // srs.cu
 int srs_generate_dev(tp_ctx* ctx, const tph::HFr& tau, size_t len, G1Affine* out);
+int srs_build_levels_dev(tp_ctx* ctx, tp_srs* srs);
 // selftest.cu
 int selftest_dev(tp_ctx* ctx, int* failures);
 int measure_imad_dev(tp_ctx* ctx, double* imad, double* wide);

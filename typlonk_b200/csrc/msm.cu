@@ -15,11 +15,17 @@
 //                       coordinates, writes complete runs straight to their bucket and emits
 //                       head/tail partials for runs that cross chunk boundaries
 //   5. k_msm_merge    : stitches the boundary partials
-//   6. k_msm_bucket_reduce / k_msm_window_reduce: running-sum reduction of each window in
-//                       parallel segments, then a shared-memory tree
-//   7. host           : Horner over the <= 64 window sums + affine conversion (serial tail; one
-//                       CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic), and
-//                       the all-gather of partial points when the MSM is sharded over GPUs.
+//   6. k_msm_wsum_level / k_msm_masked_sum: sum_v v * B_v of each bucket set without a single
+//                       scalar multiplication: two levels of 8-bucket running sums, then the
+//                       remaining index bits as masked tree sums (see "bucket reduction" below)
+//   7. host           : <= 40 additions/doublings per bucket set + affine conversion (serial tail;
+//                       one CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic),
+//                       and the all-gather of partial points when the MSM is sharded over GPUs.
+//
+// Fixed-base tables: the SRS never changes, so tp_srs holds `levels` copies of it, level k =
+// 2^(c k) * P_i (srs.cu).  Window w of scalar i then adds table[w % levels][i] into bucket set
+// w / levels, i.e. with levels == nwin ALL windows of an MSM share ONE set of 2^(c-1) buckets: the
+// bucket reduction shrinks nwin-fold, which in turn lets c grow (fewer windows = fewer additions).
 #include <stdlib.h>
 
 #include <utility>
@@ -31,40 +37,75 @@ namespace tp {
 #define MSM_NONE 0x7fffffffu
 #define MSM_IDENT 0x80000000u   // partial slot holds the identity (point not stored)
 
-// Tunables (defaults chosen on B200; TP_MSM_CHUNK / TP_MSM_SEG / TP_MSM_C override for sweeps).
+// Tunables (defaults chosen on B200; TP_MSM_CHUNK / TP_MSM_C / TP_MSM_LEVELS override for sweeps).
 static unsigned env_uint(const char* name, unsigned dflt) {
   const char* v = getenv(name);
   if (!v || !*v) return dflt;
   long x = strtol(v, nullptr, 10);
   return x > 0 ? (unsigned)x : dflt;
 }
+static bool msm_force_levels() { static unsigned v = env_uint("TP_MSM_FORCE_LEVEL_MERGE", 0); return v != 0; }
 static unsigned msm_chunk() { static unsigned v = env_uint("TP_MSM_CHUNK", 64); return v; }   // sorted entries per accumulate thread
-static unsigned msm_seg() { static unsigned v = env_uint("TP_MSM_SEG", 16); return v; }        // buckets per bucket-reduce thread
 
 struct MsmPlan {
   unsigned c;        // window bits
   unsigned nwin;     // number of windows
-  unsigned nbuck;    // buckets per window = 2^(c-1)
+  unsigned nbuck;    // buckets per set = 2^(c-1)
+  unsigned levels;   // fixed-base table levels held by the SRS
+  unsigned nsets;    // bucket sets per MSM = ceil(nwin / levels)
 };
 
-static MsmPlan msm_plan(size_t n) {
-  MsmPlan best = {0, 0, 0};
-  double best_cost = 1e300;
+static unsigned windows_for(unsigned c) {
+  unsigned nwin = (255 + c - 1) / c;
+  unsigned top_bits = 255 - (nwin - 1) * c;
+  if (top_bits == c) nwin++;  // signed carry out of a full top window
+  return nwin;
+}
+
+// Window size and table depth for an SRS of `table_len` points of which one MSM call on this rank
+// touches `len` (the shard when the MSM is split over GPUs), when `budget` bytes may go to tables.
+// Cost in Fq multiplications: 10 per bucket addition (XYZZ mixed), ~30 per bucket in the reduction.
+void msm_choose_tables(size_t len, size_t table_len, size_t budget, unsigned* c_out, unsigned* levels_out) {
   static unsigned force_c = env_uint("TP_MSM_C", 0);
-  for (unsigned c = 2; c <= 21; c++) {
+  static unsigned max_levels = env_uint("TP_MSM_LEVELS", 1u << 30);
+  double best_cost = 1e300;
+  unsigned best_c = 2, best_l = 1;
+  size_t n = len ? len : 1;
+  size_t tn = table_len ? table_len : 1;
+  size_t afford = budget / (tn * sizeof(G1Affine));
+  if (afford < 1) afford = 1;
+  for (unsigned c = 2; c <= 26; c++) {
     if (force_c && c != force_c) continue;
-    unsigned nwin = (255 + c - 1) / c;
-    unsigned top_bits = 255 - (nwin - 1) * c;
-    if (top_bits == c) nwin++;  // signed carry out of a full top window
+    unsigned nwin = windows_for(c);
+    unsigned levels = nwin;
+    if (levels > afford) levels = (unsigned)afford;
+    if (levels > max_levels) levels = max_levels;
+    if ((size_t)levels * tn >= ((size_t)1 << 31)) levels = (unsigned)((((size_t)1 << 31) - 1) / tn);
+    if (levels < 1) levels = 1;
+    unsigned nsets = (nwin + levels - 1) / levels;
+    levels = (nwin + nsets - 1) / nsets;  // no deeper than the set count needs
     double nb = (double)(1u << (c - 1));
-    double cost = (double)n * nwin * 10.0 + nwin * nb * 40.0 + nwin * 3000.0;
-    if (top_bits + 6 < c && n > 4096) cost += 25e6;  // top window funnels ~n points into < nb/32 buckets
+    double cost = (double)n * nwin * 10.0 + nsets * nb * 30.0 + nsets * 3000.0;
+    unsigned top_bits = 255 - (nwin - 1) * c;
+    if (levels == 1 && top_bits + 6 < c && n > 4096) cost += 25e6;  // a lone top window funnels ~n points into few buckets
     if (cost < best_cost) {
       best_cost = cost;
-      best = {c, nwin, 1u << (c - 1)};
+      best_c = c;
+      best_l = levels;
     }
   }
-  return best;
+  *c_out = best_c;
+  *levels_out = best_l;
+}
+
+static MsmPlan msm_plan(const tp_srs* srs) {
+  MsmPlan pl;
+  pl.c = srs->c;
+  pl.nwin = windows_for(pl.c);
+  pl.nbuck = 1u << (pl.c - 1);
+  pl.levels = srs->levels;
+  pl.nsets = (pl.nwin + pl.levels - 1) / pl.levels;
+  return pl;
 }
 
 // ---- 1. digits + histogram/rank ----------------------------------------------------------
@@ -72,12 +113,15 @@ static MsmPlan msm_plan(size_t n) {
 struct MsmScalarSets {
   const Fr* p[MSM_MAX_BATCH];
 };
-// blockIdx.y = batch element; its windows are numbered b * nwin + w in every later stage.
-__global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
-                             unsigned* __restrict__ hist, unsigned* __restrict__ keys, unsigned* __restrict__ ranks) {
+// blockIdx.y = batch element b.  Window w goes to bucket set b * nsets + w / levels; the entry
+// arrays stay window-major ((b * nwin + w) * n + i) so the scatter can recover (w, i).
+__global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck, unsigned levels,
+                             unsigned nsets, unsigned* __restrict__ hist, unsigned* __restrict__ keys,
+                             unsigned* __restrict__ ranks) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned wbase = blockIdx.y * nwin;
+  const unsigned sbase = blockIdx.y * nsets;
   Fr s = fr_from_mont(fr_load(sets.p[blockIdx.y] + i));
   unsigned carry = 0;
   for (unsigned w = 0; w < nwin; w++) {
@@ -100,7 +144,7 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
         carry = 1;
       }
       if (mag != 0) {
-        unsigned k = (wbase + w) * nbuck + (mag - 1);
+        unsigned k = (sbase + w / levels) * nbuck + (mag - 1);
         rank = atomicAdd(&hist[k], 1u);
         key = k | (neg << 31);
       }
@@ -113,10 +157,14 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
 // ---- 2. exclusive scan of u32 (3 kernels) --------------------------------------------------
 #define SCAN_BLOCK 1024
 __global__ void k_scan_local(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned* __restrict__ sums,
-                             size_t n) {
+                             size_t n, unsigned* __restrict__ max_out) {
   __shared__ unsigned s[SCAN_BLOCK];
   size_t g = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
   unsigned v = g < n ? in[g] : 0;
+  if (max_out) {  // largest bucket (decides whether chunks can consist of a single run)
+    unsigned wmax = __reduce_max_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(max_out, wmax);
+  }
   s[threadIdx.x] = v;
   __syncthreads();
   for (unsigned d = 1; d < SCAN_BLOCK; d <<= 1) {
@@ -158,8 +206,8 @@ __global__ void k_scan_add(unsigned* out, const unsigned* sums, size_t n) {
 
 // ---- 3. scatter ----------------------------------------------------------------------------
 __global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
-                              const unsigned* __restrict__ offsets, size_t n, size_t total,
-                              unsigned* __restrict__ sorted_idx, unsigned* __restrict__ sorted_key) {
+                              const unsigned* __restrict__ offsets, size_t n, size_t total, unsigned nwin,
+                              unsigned levels, unsigned stride, uint2* __restrict__ sorted) {
   size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   unsigned key = keys[e];
@@ -167,8 +215,9 @@ __global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned*
   unsigned k = key & MSM_NONE;
   unsigned pos = offsets[k] + ranks[e];
   unsigned i = (unsigned)(e % n);
-  sorted_idx[pos] = i | (key & 0x80000000u);
-  sorted_key[pos] = k;
+  unsigned w = (unsigned)(e / n) % nwin;
+  // index into the fixed-base table: level (w % levels) holds 2^(c (w % levels)) * P_i
+  sorted[pos] = make_uint2(((w % levels) * stride + i) | (key & 0x80000000u), k);  // one 8-byte store
 }
 
 // ---- 4. segmented accumulation ---------------------------------------------------------------
@@ -177,8 +226,8 @@ __global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned*
 #define TP_ACC_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
-                                                        const unsigned* __restrict__ sorted_idx,
-                                                        const unsigned* __restrict__ sorted_key, unsigned m_total,
+                                                        const uint2* __restrict__ sorted /* (index | sign, key) */,
+                                                        unsigned m_total,
                                                         G1Xyzz* __restrict__ buckets, unsigned* __restrict__ part_keys,
                                                         G1Xyzz* __restrict__ part_pts, unsigned chunk) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,10 +235,11 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
   if (start >= m_total) return;
   unsigned end = start + chunk < m_total ? start + chunk : m_total;
   G1Xyzz acc = xyzz_identity();
-  unsigned cur = sorted_key[start];
+  unsigned cur = sorted[start].y;
   bool is_first_run = true;
   for (unsigned e = start; e < end; e++) {
-    unsigned key = sorted_key[e];
+    const uint2 ent = sorted[e];
+    const unsigned key = ent.y;
     if (key != cur) {
       if (is_first_run) {
         part_keys[2 * t] = cur;
@@ -201,7 +251,7 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
       acc = xyzz_identity();
       cur = key;
     }
-    unsigned idx = sorted_idx[e];
+    const unsigned idx = ent.x;
     G1Affine p = affine_load(bases + (idx & 0x7fffffffu));
     if (!affine_is_identity(p)) xyzz_madd(acc, p, (idx >> 31) != 0);
   }
@@ -215,7 +265,39 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
   }
 }
 
-// ---- 5. boundary merge -----------------------------------------------------------------------
+// ---- 5a. boundary fix-up, common case ---------------------------------------------------------
+// A chunk's head run is complete if it starts in that chunk and the chunk has further runs.  The
+// run that is still open at the end of chunk t (its tail, or its head when the whole chunk is one
+// run that starts there) is owned by thread t, which walks forward over the heads of the following
+// chunks until the run ends.  The host takes this path when the largest bucket is shorter than
+// PAIR_MAX_SPAN chunks, so the walk is at most PAIR_MAX_SPAN + 1 additions and almost always one;
+// heavier skew goes through the logarithmic merge below.
+#define PAIR_MAX_SPAN 8
+__global__ void __launch_bounds__(128) k_msm_pair_fixup(const unsigned* __restrict__ part_keys,
+                                                        const G1Xyzz* __restrict__ part_pts, unsigned nchunks,
+                                                        G1Xyzz* __restrict__ buckets) {
+  unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const unsigned hk = part_keys[2 * t];
+  const unsigned lraw = part_keys[2 * t + 1];
+  const bool multi = !(lraw & MSM_IDENT);
+  const bool head_starts = t == 0 || (part_keys[2 * t - 1] & MSM_NONE) != hk;
+  if (head_starts && multi) {  // complete run: copy
+    G1Xyzz h = xyzz_load(part_pts + 2 * t);
+    xyzz_store(buckets + hk, h);
+  }
+  if (!multi && !head_starts) return;  // interior piece of a run owned by an earlier chunk
+  const unsigned key = multi ? lraw : hk;
+  G1Xyzz acc = xyzz_load(part_pts + 2 * t + (multi ? 1 : 0));
+  for (unsigned j = t + 1; j < nchunks && part_keys[2 * j] == key; j++) {
+    G1Xyzz h = xyzz_load(part_pts + 2 * j);
+    xyzz_add(acc, h);
+    if (!(part_keys[2 * j + 1] & MSM_IDENT)) break;  // chunk j has further runs: this one ended there
+  }
+  xyzz_store(buckets + key, acc);
+}
+
+// ---- 5b. boundary merge -----------------------------------------------------------------------
 // The partial list (2 slots per chunk, keys non-decreasing) is reduced level by level: every
 // thread takes MERGE_B consecutive slots, sums runs of equal key with general XYZZ additions,
 // writes runs that lie strictly inside its block to their bucket (it is their only owner) and
@@ -266,39 +348,73 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
 }
 
 // ---- 6. bucket reduction ---------------------------------------------------------------------
-// Each thread reduces MSM_SEG consecutive buckets of one window: sum_v v * B_v over its segment.
-__global__ void __launch_bounds__(128) k_msm_bucket_reduce(const G1Xyzz* __restrict__ buckets,
-                                                           const unsigned* __restrict__ hist, unsigned nbuck,
-                                                           unsigned seg_len, unsigned segs_per_win, unsigned nwin,
-                                                           G1Xyzz* __restrict__ seg_out) {
+// Wanted per bucket set: V = sum_b (b + 1) * B_b = P + F(B), with P = sum_b B_b and
+// F(A) = sum_m m * A_m.  Writing m = S * seg + j:
+//     F(A) = sum_seg t_seg + S * F(R),   t_seg = sum_j j * A[S seg + j],  R_seg = sum_j A[S seg + j]
+// k_msm_wsum_level computes (t_seg, R_seg) with running sums (2 additions per element) and shrinks
+// the array S-fold.  After the levels the short array R is finished bit by bit,
+//     F(R) = sum_k 2^k * (sum of R_m over the m with bit k set),     P = sum_m R_m,
+// all of them masked tree sums (k_msm_masked_sum) that run side by side in one launch together with
+// the plain sums T_l = sum_seg t_seg of every level.  The host then needs ~40 group operations per
+// set (S = 8 is a power of two) instead of a Horner walk over all windows.  No thread ever does a
+// scalar multiplication and the longest dependent chain is 2 S additions per level.
+#define WSUM_S_FIRST 8       // segment length of the first level (where the work is: 2 additions per bucket)
+#define WSUM_S_NEXT 4        // later levels are latency-bound: shorter chains
+#define WSUM_MIN 32768       // keep levelling while a set still has at least this many entries
+#define WSUM_MAX_LEVELS 6
+__global__ void __launch_bounds__(128) k_msm_wsum_level(const G1Xyzz* __restrict__ in, const unsigned* __restrict__ hist,
+                                                        unsigned m_in, unsigned seg, unsigned total_out,
+                                                        G1Xyzz* __restrict__ r_out, G1Xyzz* __restrict__ t_out) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= segs_per_win * nwin) return;
-  unsigned w = t / segs_per_win, sidx = t % segs_per_win;
-  unsigned lo = sidx * seg_len;  // bucket index b holds value v = b + 1
-  G1Xyzz running = xyzz_identity(), total = xyzz_identity();
-  for (int b = (int)seg_len - 1; b >= 0; b--) {
-    unsigned k = w * nbuck + lo + b;
-    if (hist[k] != 0) {
-      G1Xyzz p = xyzz_load(buckets + k);
+  if (t >= total_out) return;
+  const unsigned m_out = m_in / seg;
+  const size_t base = (size_t)(t / m_out) * m_in + (size_t)(t % m_out) * seg;
+  G1Xyzz running = xyzz_identity(), tot = xyzz_identity();
+  for (int j = (int)seg - 1; j >= 0; j--) {
+    if (!hist || hist[base + j] != 0) {  // first level: empty buckets were never written
+      G1Xyzz p = xyzz_load(in + base + j);
       xyzz_add(running, p);
     }
-    xyzz_add(total, running);
+    if (j > 0) xyzz_add(tot, running);
   }
-  // total = sum (b+1) B ; add lo * running
-  if (lo != 0) {
-    xyzz_mul_small(running, lo);
-    xyzz_add(total, running);
-  }
-  xyzz_store(seg_out + t, total);
+  xyzz_store(r_out + t, running);
+  xyzz_store(t_out + t, tot);
 }
-// One CTA per window: strided serial sum then shared-memory tree.
-__global__ void __launch_bounds__(128) k_msm_window_reduce(const G1Xyzz* __restrict__ seg, unsigned segs_per_win,
-                                                           G1Xyzz* __restrict__ win_out) {
+
+// Masked sums.  Task k covers `nmask[k]` consecutive mask slots starting at mask_base[k]: slot 0 of
+// a task is the plain sum of in[k][set * m[k] + i], slot 1 + b sums the i with bit b set.
+// grid = (slices, total mask slots, sets); every block tree-sums its slice.
+#define SUM_MAX_TASKS (WSUM_MAX_LEVELS + 1)
+struct MsmSumTasks {
+  const G1Xyzz* in[SUM_MAX_TASKS];
+  const unsigned* hist[SUM_MAX_TASKS];  // non-null: element present iff hist != 0 (raw buckets)
+  unsigned m[SUM_MAX_TASKS];
+  unsigned slices[SUM_MAX_TASKS];       // blocks per mask slot of this task (<= gridDim.x)
+  unsigned mask_base[SUM_MAX_TASKS + 1];
+  int ntasks;
+};
+__global__ void __launch_bounds__(128) k_msm_masked_sum(MsmSumTasks tasks, G1Xyzz* __restrict__ out) {
   __shared__ G1Xyzz sh[128];
-  unsigned w = blockIdx.x;
+  int k = 0;
+  while (k + 1 < tasks.ntasks && blockIdx.y >= tasks.mask_base[k + 1]) k++;
+  G1Xyzz* dst = out + ((size_t)blockIdx.z * tasks.mask_base[tasks.ntasks] + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned slices = tasks.slices[k];
+  if (blockIdx.x >= slices) {  // this task needs fewer blocks than the widest one
+    if (threadIdx.x == 0) xyzz_store(dst, xyzz_identity());
+    return;
+  }
+  const unsigned mask = blockIdx.y - tasks.mask_base[k];
+  const unsigned m = tasks.m[k];
+  const unsigned per = (m + slices - 1) / slices;
+  const unsigned lo = blockIdx.x * per;
+  const unsigned hi = lo + per < m ? lo + per : m;
+  const G1Xyzz* in = tasks.in[k] + (size_t)blockIdx.z * m;
+  const unsigned* hist = tasks.hist[k] ? tasks.hist[k] + (size_t)blockIdx.z * m : nullptr;
   G1Xyzz acc = xyzz_identity();
-  for (unsigned s = threadIdx.x; s < segs_per_win; s += blockDim.x) {
-    G1Xyzz p = xyzz_load(seg + (size_t)w * segs_per_win + s);
+  for (unsigned i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    if (mask != 0 && !((i >> (mask - 1)) & 1)) continue;
+    if (hist && hist[i] == 0) continue;
+    G1Xyzz p = xyzz_load(in + i);
     xyzz_add(acc, p);
   }
   sh[threadIdx.x] = acc;
@@ -312,7 +428,7 @@ __global__ void __launch_bounds__(128) k_msm_window_reduce(const G1Xyzz* __restr
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) xyzz_store(win_out + w, sh[0]);
+  if (threadIdx.x == 0) xyzz_store(dst, sh[0]);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -330,11 +446,11 @@ void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]) {
   }
 }
 
-static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, size_t n) {
+static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, size_t n, unsigned* max_out) {
   size_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   TP_TRY(ensure(ctx, ctx->msm_blocksums, nblocks * sizeof(unsigned)));
   unsigned* sums = (unsigned*)ctx->msm_blocksums.p;
-  k_scan_local<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n);
+  k_scan_local<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n, max_out);
   TP_LAUNCH(ctx, "k_scan_local");
   k_scan_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nblocks);
   TP_LAUNCH(ctx, "k_scan_sums");
@@ -343,76 +459,110 @@ static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, si
   return TP_OK;
 }
 
-// This rank's partial sums over `len` bases for `batch` scalar vectors at once: all vectors share
-// one sort / accumulate / merge / reduce pipeline (window index = b * nwin + w), which amortises the
-// latency-bound reduction tail and the launch overhead over the batch.
-static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* const* scalars, int batch, size_t len,
+// This rank's partial sums over the `len` bases starting at SRS index `first`, for `batch` scalar
+// vectors at once: all vectors share one sort / accumulate / merge / reduce pipeline (bucket set
+// index = b * nsets + q), which amortises the latency-bound reduction tail and the launch overhead.
+static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* const* scalars, int batch, size_t len,
                      tph::HG1* results) {
   for (int b = 0; b < batch; b++) results[b] = tph::HG1::identity();
   if (len == 0 || batch == 0) return TP_OK;
   if (batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: batch too large");
   if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
-  MsmPlan pl = msm_plan(len);
-  if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nwin * pl.nbuck * batch >= ((size_t)1 << 30)) {
+  const MsmPlan pl = msm_plan(srs);
+  if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nsets * pl.nbuck * batch >= ((size_t)1 << 30)) {
     if (batch == 1) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
     int half = batch / 2;  // split the batch until the entry count fits 31 bits
-    TP_TRY(msm_local(ctx, bases, scalars, half, len, results));
-    return msm_local(ctx, bases, scalars + half, batch - half, len, results + half);
+    TP_TRY(msm_local(ctx, srs, first, scalars, half, len, results));
+    return msm_local(ctx, srs, first, scalars + half, batch - half, len, results + half);
   }
-  const unsigned nwin_total = pl.nwin * batch;
-  size_t nkeys = (size_t)nwin_total * pl.nbuck;
-  size_t total = (size_t)nwin_total * len;
-  TP_TRY(ensure(ctx, ctx->msm_hist, (nkeys + 1) * sizeof(unsigned)));
+  const G1Affine* bases = srs->g1 + first;      // level k of point i lives at bases[k * srs->len + i]
+  const unsigned nsets_total = pl.nsets * batch;
+  size_t nkeys = (size_t)nsets_total * pl.nbuck;
+  size_t total = (size_t)pl.nwin * batch * len;
+  TP_TRY(ensure(ctx, ctx->msm_hist, (nkeys + 2) * sizeof(unsigned)));  // + scan sentinel + largest bucket
   TP_TRY(ensure(ctx, ctx->msm_offsets, (nkeys + 1) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_keys, total * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_ranks, total * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_sorted_keys, total * sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(uint2)));
   TP_TRY(ensure(ctx, ctx->msm_buckets, nkeys * sizeof(G1Xyzz)));
   unsigned* hist = (unsigned*)ctx->msm_hist.p;
   unsigned* offsets = (unsigned*)ctx->msm_offsets.p;
   unsigned* keys = (unsigned*)ctx->msm_keys.p;
   unsigned* ranks = (unsigned*)ctx->msm_ranks.p;
-  unsigned* sorted = (unsigned*)ctx->msm_sorted.p;
-  unsigned* sorted_keys = (unsigned*)ctx->msm_sorted_keys.p;
+  uint2* sorted = (uint2*)ctx->msm_sorted.p;
   G1Xyzz* buckets = (G1Xyzz*)ctx->msm_buckets.p;
-  unsigned m_total = 0;
+  unsigned m_total = 0, max_bucket = 0;
   {
     ProfScope prof(ctx, TP_PHASE_MSM_SORT);
-    TP_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (nkeys + 1) * sizeof(unsigned), ctx->stream));
+    TP_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (nkeys + 2) * sizeof(unsigned), ctx->stream));
     MsmScalarSets sets;
     for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < batch ? b : 0];
     dim3 grid((unsigned)((len + 255) / 256), (unsigned)batch);
-    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, hist, keys, ranks);
+    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, hist, keys,
+                                                ranks);
     TP_LAUNCH(ctx, "k_msm_digits");
-    TP_TRY(exclusive_scan_u32(ctx, hist, offsets, nkeys + 1));
-    k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, sorted,
-                                                                           sorted_keys);
+    TP_TRY(exclusive_scan_u32(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
+    k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
+                                                                           pl.levels, (unsigned)srs->len, sorted);
     TP_LAUNCH(ctx, "k_msm_scatter");
     TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA_OK(ctx, cudaMemcpyAsync((unsigned*)ctx->pinned + 1, hist + nkeys + 1, sizeof(unsigned), cudaMemcpyDeviceToHost,
+                                    ctx->stream));
     TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    m_total = *(unsigned*)ctx->pinned;
+    m_total = ((unsigned*)ctx->pinned)[0];
+    max_bucket = ((unsigned*)ctx->pinned)[1];
   }
   if (m_total == 0) return TP_OK;  // all scalars zero
-  const unsigned chunk = msm_chunk();
+  // Entries per accumulate thread: longer chunks when buckets are long (fewer boundary partials),
+  // as long as the grid still fills the GPU several times over.
+  unsigned chunk = msm_chunk();
+  while (chunk <= max_bucket && chunk < 1024 && (size_t)m_total / (2 * chunk) >= (size_t)ctx->sm_count * 384 * 4) chunk *= 2;
+  const bool pair_path = max_bucket < PAIR_MAX_SPAN * chunk && !msm_force_levels();
   unsigned nchunks = (m_total + chunk - 1) / chunk;
   // first half: accumulate's partials; second half: ping-pong space for the merge levels
   TP_TRY(ensure(ctx, ctx->msm_part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
-    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, sorted, sorted_keys, m_total, buckets,
+    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, sorted, m_total, buckets,
                                                                      (unsigned*)ctx->msm_part_keys.p,
                                                                      (G1Xyzz*)ctx->msm_part_pts.p, chunk);
     TP_LAUNCH(ctx, "k_msm_accumulate");
   }
-  unsigned seg_len = pl.nbuck < msm_seg() ? pl.nbuck : msm_seg();
-  unsigned segs_per_win = pl.nbuck / seg_len;
-  TP_TRY(ensure(ctx, ctx->msm_seg, (size_t)segs_per_win * nwin_total * sizeof(G1Xyzz)));
-  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)nwin_total * sizeof(G1Xyzz)));
+  // reduction plan: levels of running sums (segment 8, then 4), then masked sums over what is left
+  unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1];
+  int nl = 0;
+  m_level[0] = pl.nbuck;
+  seg_level[0] = 1;
+  while (nl < WSUM_MAX_LEVELS && m_level[nl] >= WSUM_MIN) {
+    seg_level[nl + 1] = nl == 0 ? WSUM_S_FIRST : WSUM_S_NEXT;
+    m_level[nl + 1] = m_level[nl] / seg_level[nl + 1];
+    nl++;
+  }
+  const unsigned m_last = m_level[nl];
+  unsigned nbits = 0;
+  while ((1u << nbits) < m_last) nbits++;
+  const unsigned total_masks = 1 + nbits + nl;  // [P, bit_0 .. bit_{nbits-1}, T_1 .. T_nl]
+  auto slices_for = [](unsigned m) {
+    unsigned sl = (m + 511) / 512;
+    return sl > 128 ? 128u : (sl < 1 ? 1u : sl);
+  };
+  unsigned slices = slices_for(m_last);
+  for (int l = 1; l <= nl; l++) slices = slices_for(m_level[l]) > slices ? slices_for(m_level[l]) : slices;
+  size_t slab = 0;  // R_l and t_l arrays, l = 1..nl
+  for (int l = 1; l <= nl; l++) slab += 2 * (size_t)nsets_total * m_level[l];
+  slab += (size_t)nsets_total * total_masks * slices;  // stage A partial sums
+  TP_TRY(ensure(ctx, ctx->msm_seg, (slab ? slab : 1) * sizeof(G1Xyzz)));
+  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)nsets_total * total_masks * sizeof(G1Xyzz)));
+  if ((size_t)nsets_total * total_masks * sizeof(G1Xyzz) > ctx->pinned_cap)
+    return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
   {
     ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
-    {
+    if (pair_path) {
+      k_msm_pair_fixup<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>((const unsigned*)ctx->msm_part_keys.p,
+                                                                       (const G1Xyzz*)ctx->msm_part_pts.p, nchunks, buckets);
+      TP_LAUNCH(ctx, "k_msm_pair_fixup");
+    } else {
       unsigned* ka = (unsigned*)ctx->msm_part_keys.p;
       G1Xyzz* pa = (G1Xyzz*)ctx->msm_part_pts.p;
       unsigned* kb = ka + 2 * (size_t)nchunks;
@@ -429,31 +579,85 @@ static int msm_local(tp_ctx* ctx, const G1Affine* bases, const Fr* const* scalar
       k_msm_merge_level<<<1, 32, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 1);
       TP_LAUNCH(ctx, "k_msm_merge_level");
     }
-    unsigned nthreads = segs_per_win * nwin_total;
-    k_msm_bucket_reduce<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(buckets, hist, pl.nbuck, seg_len, segs_per_win,
-                                                                         nwin_total, (G1Xyzz*)ctx->msm_seg.p);
-    TP_LAUNCH(ctx, "k_msm_bucket_reduce");
-    k_msm_window_reduce<<<nwin_total, 128, 0, ctx->stream>>>((G1Xyzz*)ctx->msm_seg.p, segs_per_win,
-                                                             (G1Xyzz*)ctx->msm_winsums.p);
-    TP_LAUNCH(ctx, "k_msm_window_reduce");
+    G1Xyzz* cursor = (G1Xyzz*)ctx->msm_seg.p;
+    const G1Xyzz* cur_in = buckets;
+    const unsigned* cur_hist = hist;
+    MsmSumTasks tasks;
+    memset(&tasks, 0, sizeof(tasks));
+    const G1Xyzz* t_arr[WSUM_MAX_LEVELS + 1] = {nullptr};
+    for (int l = 1; l <= nl; l++) {
+      unsigned total_out = nsets_total * m_level[l];
+      G1Xyzz* r_out = cursor;
+      G1Xyzz* t_out = cursor + total_out;
+      cursor += 2 * (size_t)total_out;
+      k_msm_wsum_level<<<(total_out + 127) / 128, 128, 0, ctx->stream>>>(cur_in, cur_hist, m_level[l - 1], seg_level[l],
+                                                                         total_out, r_out, t_out);
+      TP_LAUNCH(ctx, "k_msm_wsum_level");
+      cur_in = r_out;
+      cur_hist = nullptr;
+      t_arr[l] = t_out;
+    }
+    tasks.ntasks = 1 + nl;
+    tasks.in[0] = cur_in;
+    tasks.hist[0] = cur_hist;
+    tasks.m[0] = m_last;
+    tasks.slices[0] = slices_for(m_last);
+    tasks.mask_base[0] = 0;
+    tasks.mask_base[1] = 1 + nbits;
+    for (int l = 1; l <= nl; l++) {
+      tasks.in[l] = t_arr[l];
+      tasks.hist[l] = nullptr;
+      tasks.m[l] = m_level[l];
+      tasks.slices[l] = slices_for(m_level[l]);
+      tasks.mask_base[l + 1] = tasks.mask_base[l] + 1;
+    }
+    G1Xyzz* part = cursor;
+    G1Xyzz* fin = (G1Xyzz*)ctx->msm_winsums.p;
+    k_msm_masked_sum<<<dim3(slices, total_masks, nsets_total), 128, 0, ctx->stream>>>(tasks, slices > 1 ? part : fin);
+    TP_LAUNCH(ctx, "k_msm_masked_sum");
+    if (slices > 1) {
+      MsmSumTasks fold;
+      memset(&fold, 0, sizeof(fold));
+      fold.ntasks = 1;
+      fold.in[0] = part;
+      fold.m[0] = slices;
+      fold.slices[0] = 1;
+      fold.mask_base[1] = 1;
+      k_msm_masked_sum<<<dim3(1, 1, nsets_total * total_masks), 128, 0, ctx->stream>>>(fold, fin);
+      TP_LAUNCH(ctx, "k_msm_masked_sum");
+    }
   }
-  if ((size_t)nwin_total * sizeof(G1Xyzz) > ctx->pinned_cap) return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)nwin_total * sizeof(G1Xyzz),
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)nsets_total * total_masks * sizeof(G1Xyzz),
                                   cudaMemcpyDeviceToHost, ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  // serial tail on the host: result_b = sum_w 2^(c w) * W_{b,w}
+  // serial tail on the host
   const uint8_t* ws = (const uint8_t*)ctx->pinned;
+  auto point = [&](unsigned set, unsigned slot) {
+    const uint8_t* q = ws + ((size_t)set * total_masks + slot) * 192;
+    tph::HFq x, y, zz, zzz;
+    memcpy(x.v, q, 48);
+    memcpy(y.v, q + 48, 48);
+    memcpy(zz.v, q + 96, 48);
+    memcpy(zzz.v, q + 144, 48);
+    return tph::g1_from_xyzz(x, y, zz, zzz);
+  };
   for (int b = 0; b < batch; b++) {
     tph::HG1 acc = tph::HG1::identity();
-    for (int w = (int)pl.nwin - 1; w >= 0; w--) {
-      for (unsigned d = 0; d < pl.c; d++) acc = tph::g1_dbl(acc);
-      const uint8_t* q = ws + ((size_t)b * pl.nwin + w) * 192;
-      tph::HFq x, y, zz, zzz;
-      memcpy(x.v, q, 48);
-      memcpy(y.v, q + 48, 48);
-      memcpy(zz.v, q + 96, 48);
-      memcpy(zzz.v, q + 144, 48);
-      acc = tph::g1_add(acc, tph::g1_from_xyzz(x, y, zz, zzz));
+    for (int q = (int)pl.nsets - 1; q >= 0; q--) {
+      if (q != (int)pl.nsets - 1)
+        for (unsigned d = 0; d < pl.c * pl.levels; d++) acc = tph::g1_dbl(acc);
+      unsigned set = (unsigned)b * pl.nsets + (unsigned)q;
+      tph::HG1 f = tph::HG1::identity();  // F(R) = sum_k 2^k bit_k
+      for (int k = (int)nbits - 1; k >= 0; k--) {
+        f = tph::g1_dbl(f);
+        f = tph::g1_add(f, point(set, 1 + (unsigned)k));
+      }
+      for (int l = nl; l >= 1; l--) {  // F(level l-1) = T_l + S_l * F(level l)
+        for (unsigned d = 1; d < seg_level[l]; d <<= 1) f = tph::g1_dbl(f);
+        f = tph::g1_add(f, point(set, 1 + nbits + (unsigned)(l - 1)));
+      }
+      f = tph::g1_add(f, point(set, 0));
+      acc = tph::g1_add(acc, f);
     }
     results[b] = acc;
   }
@@ -467,7 +671,7 @@ int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, 
   ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
   tph::HG1 res[MSM_MAX_BATCH];
   if (ctx->world <= 1) {
-    TP_TRY(msm_local(ctx, srs->g1, scalars_dev, batch, len, res));
+    TP_TRY(msm_local(ctx, srs, 0, scalars_dev, batch, len, res));
   } else {
     // contiguous point-range shard; every rank holds the full SRS and scalar vectors
     size_t per = (len + ctx->world - 1) / ctx->world;
@@ -476,7 +680,7 @@ int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, 
     const Fr* shifted[MSM_MAX_BATCH];
     for (int b = 0; b < batch; b++) shifted[b] = scalars_dev[b] + first;
     tph::HG1 part[MSM_MAX_BATCH];
-    TP_TRY(msm_local(ctx, srs->g1 + first, shifted, batch, cnt, part));
+    TP_TRY(msm_local(ctx, srs, first, shifted, batch, cnt, part));
     const size_t per_rank = (size_t)144 * batch;
     std::vector<uint8_t> send(per_rank), recv(per_rank * ctx->world);
     for (int b = 0; b < batch; b++) {

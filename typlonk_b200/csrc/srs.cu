@@ -103,6 +103,60 @@ __global__ void __launch_bounds__(64) k_srs_generate(const G1Affine* __restrict_
   }
 }
 
+// Fixed-base window tables: level k+1 = 2^c * level k.  Every thread doubles SRS_PER consecutive
+// points c times in XYZZ and normalises them with one shared inversion.
+__global__ void __launch_bounds__(64) k_srs_next_level(const G1Affine* __restrict__ in, size_t len, unsigned c,
+                                                       G1Affine* __restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t lo = t * SRS_PER;
+  if (lo >= len) return;
+  int cnt = (int)(lo + SRS_PER < len ? SRS_PER : len - lo);
+  G1Xyzz pts[SRS_PER];
+  for (int i = 0; i < cnt; i++) {
+    G1Affine p = affine_load(in + lo + i);
+    G1Xyzz acc = xyzz_identity();
+    if (!affine_is_identity(p)) {
+      xyzz_mdbl(acc, p);
+      for (unsigned d = 1; d < c; d++) xyzz_dbl(acc);
+    }
+    pts[i] = acc;
+  }
+  Fq pre[SRS_PER];
+  Fq acc = fq_one();
+  for (int i = 0; i < cnt; i++) {
+    pre[i] = acc;
+    Fq d = xyzz_is_identity(pts[i]) ? fq_one() : fq_mul(pts[i].zz, pts[i].zzz);
+    acc = fq_mul(acc, d);
+  }
+  Fq inv = fq_inv(acc);
+  for (int i = cnt - 1; i >= 0; i--) {
+    G1Affine r;
+    if (xyzz_is_identity(pts[i])) {
+      r.x = fq_zero();
+      r.y = fq_zero();
+    } else {
+      Fq d = fq_mul(pts[i].zz, pts[i].zzz);
+      Fq di = fq_mul(inv, pre[i]);  // 1 / (zz zzz)
+      inv = fq_mul(inv, d);
+      r.x = fq_mul(pts[i].x, fq_mul(di, pts[i].zzz));  // X / ZZ
+      r.y = fq_mul(pts[i].y, fq_mul(di, pts[i].zz));   // Y / ZZZ
+    }
+    fq_store(&out[lo + i].x, r.x);
+    fq_store(&out[lo + i].y, r.y);
+  }
+}
+
+int srs_build_levels_dev(tp_ctx* ctx, tp_srs* srs) {
+  if (srs->len == 0) return TP_OK;
+  size_t nth = (srs->len + SRS_PER - 1) / SRS_PER;
+  for (unsigned k = 1; k < srs->levels; k++) {
+    k_srs_next_level<<<(unsigned)((nth + 63) / 64), 64, 0, ctx->stream>>>(srs->g1 + (size_t)(k - 1) * srs->len, srs->len,
+                                                                          srs->c, srs->g1 + (size_t)k * srs->len);
+    TP_LAUNCH(ctx, "k_srs_next_level");
+  }
+  return TP_OK;
+}
+
 int srs_generate_dev(tp_ctx* ctx, const tph::HFr& tau, size_t len, G1Affine* out) {
   TP_TRY(build_fixed_base(ctx));
   size_t nth = (len + SRS_PER - 1) / SRS_PER;

@@ -11,13 +11,13 @@ def _events(torch):
     return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
 
-def run(ctx, torch, out, msm_logs=(16, 18, 20, 22, 24), ntt_logs=(16, 18, 20, 22, 24), reps=3):
+def run(ctx, torch, out, msm_logs=(16, 18, 20, 22, 24, 26), ntt_logs=(16, 18, 20, 22, 24), reps=3):
     dev = torch.device("cuda", ctx.device)
     imad, imad_wide = ctx.measure_imad_peak()
-    max_log = max(msm_logs)
-    srs = Srs.from_secret(ctx, synthetic.tau(), (1 << max_log) - 3)
     for lg in msm_logs:
         n = 1 << lg
+        # one SRS per size: its fixed-base tables (window bits, levels) are planned for that length
+        srs = Srs.from_secret(ctx, synthetic.tau(), n - 3)
         # uniform scalars: Fr::rand stream (seed 3) for the first 2^16, then a device-side mix
         base = torch.frombuffer(bytearray(fr_rand_stream(synthetic.SEED_MSM, 1 << 16)), dtype=torch.uint8).to(dev)
         sc = base.repeat(n >> 16).view(n, 32).clone()
@@ -41,7 +41,8 @@ def run(ctx, torch, out, msm_logs=(16, 18, 20, 22, 24), ntt_logs=(16, 18, 20, 22
                               "hbm_gbs_algorithmic": 128.0 * n / ms / 1e6,
                               "phases_ms": {k: v[0] / reps for k, v in prof.items() if k.startswith("msm")}}) + "\n")
         del sc
-    srs.handle.destroy()
+        srs.handle.destroy()
+        torch.cuda.empty_cache()
     for lg in ntt_logs:
         n = 1 << lg
         x = torch.randint(0, 256, (n, 32), dtype=torch.uint8, device=dev)
@@ -61,3 +62,23 @@ def run(ctx, torch, out, msm_logs=(16, 18, 20, 22, 24), ntt_logs=(16, 18, 20, 22
                                   "imad_frac_est": butterflies * 176 / (ms * 1e-3) / imad_wide}) + "\n")
         del x
     out.flush()
+
+
+if __name__ == "__main__":
+    import argparse
+    import sys
+
+    import torch
+
+    from .ffi import Context
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--msm", default="16,18,20,22,24,26")
+    ap.add_argument("--ntt", default="16,18,20,22,24")
+    ap.add_argument("--reps", type=int, default=3)
+    a = ap.parse_args()
+    st = torch.cuda.Stream(device=torch.device("cuda", 0))
+    torch.cuda.set_stream(st)  # torch events must sit on the stream the library launches on
+    c = Context(0, st.cuda_stream)
+    run(c, torch, sys.stdout, tuple(int(x) for x in a.msm.split(",") if x), tuple(int(x) for x in a.ntt.split(",") if x),
+        a.reps)
