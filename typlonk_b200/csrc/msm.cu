@@ -393,8 +393,9 @@ struct MsmSumTasks {
   unsigned mask_base[SUM_MAX_TASKS + 1];
   int ntasks;
 };
-__global__ void __launch_bounds__(128) k_msm_masked_sum(MsmSumTasks tasks, G1Xyzz* __restrict__ out) {
-  __shared__ G1Xyzz sh[128];
+#define SUM_THREADS 64
+__global__ void __launch_bounds__(SUM_THREADS) k_msm_masked_sum(MsmSumTasks tasks, G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[SUM_THREADS];
   int k = 0;
   while (k + 1 < tasks.ntasks && blockIdx.y >= tasks.mask_base[k + 1]) k++;
   G1Xyzz* dst = out + ((size_t)blockIdx.z * tasks.mask_base[tasks.ntasks] + blockIdx.y) * gridDim.x + blockIdx.x;
@@ -613,7 +614,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     }
     G1Xyzz* part = cursor;
     G1Xyzz* fin = (G1Xyzz*)ctx->msm_winsums.p;
-    k_msm_masked_sum<<<dim3(slices, total_masks, nsets_total), 128, 0, ctx->stream>>>(tasks, slices > 1 ? part : fin);
+    k_msm_masked_sum<<<dim3(slices, total_masks, nsets_total), SUM_THREADS, 0, ctx->stream>>>(tasks, slices > 1 ? part : fin);
     TP_LAUNCH(ctx, "k_msm_masked_sum");
     if (slices > 1) {
       MsmSumTasks fold;
@@ -623,7 +624,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
       fold.m[0] = slices;
       fold.slices[0] = 1;
       fold.mask_base[1] = 1;
-      k_msm_masked_sum<<<dim3(1, 1, nsets_total * total_masks), 128, 0, ctx->stream>>>(fold, fin);
+      k_msm_masked_sum<<<dim3(1, 1, nsets_total * total_masks), SUM_THREADS, 0, ctx->stream>>>(fold, fin);
       TP_LAUNCH(ctx, "k_msm_masked_sum");
     }
   }
