@@ -48,7 +48,7 @@ static __device__ __noinline__ void xyzz_mdbl(G1Xyzz& r, const G1Affine p) {
   Fq xx = fq_sqr(p.x);
   Fq m = fq_add(fq_dbl(xx), xx);
   Fq x3 = fq_sub(fq_sqr(m), fq_dbl(s));
-  r.y = fq_sub(fq_mul(m, fq_sub(s, x3)), fq_mul(w, p.y));
+  r.y = fq_mul_sub2(m, fq_sub(s, x3), w, p.y);
   r.x = x3;
   r.zz = v;
   r.zzz = w;
@@ -63,7 +63,7 @@ static __device__ __noinline__ void xyzz_dbl(G1Xyzz& r) {
   Fq xx = fq_sqr(r.x);
   Fq m = fq_add(fq_dbl(xx), xx);
   Fq x3 = fq_sub(fq_sqr(m), fq_dbl(s));
-  Fq y3 = fq_sub(fq_mul(m, fq_sub(s, x3)), fq_mul(w, r.y));
+  Fq y3 = fq_mul_sub2(m, fq_sub(s, x3), w, r.y);
   r.x = x3;
   r.y = y3;
   r.zz = fq_mul(v, r.zz);
@@ -96,7 +96,7 @@ __device__ __forceinline__ void xyzz_madd(G1Xyzz& acc, const G1Affine& p_in, boo
   Fq ppp = fq_mul(pp_, pp);
   Fq q = fq_mul(acc.x, pp);
   Fq x3 = fq_sub(fq_sub(fq_sqr(rr), ppp), fq_dbl(q));
-  Fq y3 = fq_sub(fq_mul(rr, fq_sub(q, x3)), fq_mul(acc.y, ppp));
+  Fq y3 = fq_mul_sub2(rr, fq_sub(q, x3), acc.y, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fq_mul(acc.zz, pp);
@@ -128,7 +128,7 @@ static __device__ __noinline__ void xyzz_add(G1Xyzz& acc, const G1Xyzz& b) {
   Fq ppp = fq_mul(pp_, pp);
   Fq q = fq_mul(u1, pp);
   Fq x3 = fq_sub(fq_sub(fq_sqr(rr), ppp), fq_dbl(q));
-  Fq y3 = fq_sub(fq_mul(rr, fq_sub(q, x3)), fq_mul(s1, ppp));
+  Fq y3 = fq_mul_sub2(rr, fq_sub(q, x3), s1, ppp);
   acc.x = x3;
   acc.y = y3;
   acc.zz = fq_mul(fq_mul(acc.zz, b.zz), pp);

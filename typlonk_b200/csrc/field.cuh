@@ -123,6 +123,12 @@ __device__ __forceinline__ Fq fq_one() {
   for (int i = 0; i < 12; i++) r.v[i] = c[i];
   return r;
 }
+// Multiplier forms (profiles/r1_summary.md, section J): TP_FQ_MUL_FORM 0 = interleaved CIOS
+// (288 wide products), 1 = one-level Karatsuba wide product + separate reduction (252), 2 =
+// schoolbook wide product + separate reduction (288; only for the microbenchmark).
+#ifndef TP_FQ_MUL_FORM
+#define TP_FQ_MUL_FORM 0
+#endif
 #ifdef TP_FQ_MUL_CALL
 // One shared copy of the 381-bit product (keeps hot loops inside the instruction cache).
 static __device__ __noinline__ Fq fq_mul(Fq a, Fq b) {
@@ -133,11 +139,26 @@ static __device__ __noinline__ Fq fq_mul(Fq a, Fq b) {
 #else
 __device__ __forceinline__ Fq fq_mul(const Fq& a, const Fq& b) {
   Fq r;
+#if TP_FQ_MUL_FORM == 1
+  fq_mul_kar_ptx(r.v, a.v, b.v);
+#elif TP_FQ_MUL_FORM == 2
+  fq_mul_sep_ptx(r.v, a.v, b.v);
+#else
   fq_mul_ptx(r.v, a.v, b.v);
+#endif
   return r;
 }
 #endif
-__device__ __forceinline__ Fq fq_sqr(const Fq& a) { return fq_mul(a, a); }
+// Dedicated square: 78 + 144 wide products instead of 288.
+__device__ __forceinline__ Fq fq_sqr(const Fq& a) {
+#ifdef TP_FQ_SQR_AS_MUL
+  return fq_mul(a, a);
+#else
+  Fq r;
+  fq_sqr_ptx(r.v, a.v);
+  return r;
+#endif
+}
 __device__ __forceinline__ Fq fq_add(const Fq& a, const Fq& b) {
   Fq r;
   fq_add_ptx(r.v, a.v, b.v);
@@ -149,6 +170,39 @@ __device__ __forceinline__ Fq fq_sub(const Fq& a, const Fq& b) {
   return r;
 }
 __device__ __forceinline__ Fq fq_neg(const Fq& a) { return fq_sub(fq_zero(), a); }
+// a*b - c*d with ONE Montgomery reduction (lazy pair, 432 wide products instead of 576).  The
+// subtrahend enters as c * (q - d); q - d lies in [1, q], which the pair's bound 2 q^2 < q 2^384 allows.
+__device__ __forceinline__ Fq fq_mul_sub2(const Fq& a, const Fq& b, const Fq& c, const Fq& d) {
+#ifdef TP_FQ_NO_LAZY
+  return fq_sub(fq_mul(a, b), fq_mul(c, d));
+#else
+  const uint32_t q[12] = TP_FQ_MOD;
+  Fq nd, r;
+  asm("sub.cc.u32 %0, %12, %24;\n\t"
+      "subc.cc.u32 %1, %13, %25;\n\t"
+      "subc.cc.u32 %2, %14, %26;\n\t"
+      "subc.cc.u32 %3, %15, %27;\n\t"
+      "subc.cc.u32 %4, %16, %28;\n\t"
+      "subc.cc.u32 %5, %17, %29;\n\t"
+      "subc.cc.u32 %6, %18, %30;\n\t"
+      "subc.cc.u32 %7, %19, %31;\n\t"
+      "subc.cc.u32 %8, %20, %32;\n\t"
+      "subc.cc.u32 %9, %21, %33;\n\t"
+      "subc.cc.u32 %10, %22, %34;\n\t"
+      "subc.u32 %11, %23, %35;"
+      : "=r"(nd.v[0]), "=r"(nd.v[1]), "=r"(nd.v[2]), "=r"(nd.v[3]), "=r"(nd.v[4]), "=r"(nd.v[5]), "=r"(nd.v[6]),
+        "=r"(nd.v[7]), "=r"(nd.v[8]), "=r"(nd.v[9]), "=r"(nd.v[10]), "=r"(nd.v[11])
+      : "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]), "r"(q[8]), "r"(q[9]),
+        "r"(q[10]), "r"(q[11]), "r"(d.v[0]), "r"(d.v[1]), "r"(d.v[2]), "r"(d.v[3]), "r"(d.v[4]), "r"(d.v[5]),
+        "r"(d.v[6]), "r"(d.v[7]), "r"(d.v[8]), "r"(d.v[9]), "r"(d.v[10]), "r"(d.v[11]));
+#if TP_FQ_MUL_FORM == 1
+  fq_mul2_kar_ptx(r.v, a.v, b.v, c.v, nd.v);
+#else
+  fq_mul2_ptx(r.v, a.v, b.v, c.v, nd.v);
+#endif
+  return r;
+#endif
+}
 __device__ __forceinline__ Fq fq_dbl(const Fq& a) { return fq_add(a, a); }
 __device__ __forceinline__ bool fq_is_zero(const Fq& a) {
   uint32_t o = 0;

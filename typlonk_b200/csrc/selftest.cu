@@ -10,7 +10,7 @@ struct SelfIn {
 };
 struct SelfOut {
   Fr mul, add, sub, inv, frommont;
-  Fq qmul, qadd, qsub, qinv;
+  Fq qmul, qadd, qsub, qinv, qsqr, qlazy, qkar, qsep;
   G1Xyzz madd, dbl, add2;
 };
 
@@ -28,6 +28,10 @@ __global__ void k_selftest(const SelfIn* in, SelfOut* out, const G1Affine* pts, 
   o.qadd = fq_add(x.qa, x.qb);
   o.qsub = fq_sub(x.qa, x.qb);
   o.qinv = fq_inv(x.qa);
+  o.qsqr = fq_sqr(x.qa);
+  o.qlazy = fq_mul_sub2(x.qa, x.qb, x.qb, x.qb);  // a*b - b*b
+  fq_mul_kar_ptx(o.qkar.v, x.qa.v, x.qb.v);
+  fq_mul_sep_ptx(o.qsep.v, x.qa.v, x.qb.v);
   // points: P = pts[i], Q = pts[(i+1)%n]
   G1Affine p = affine_load(pts + i), q = affine_load(pts + (i + 1) % n);
   G1Xyzz acc = xyzz_identity();
@@ -136,6 +140,10 @@ int selftest_dev(tp_ctx* ctx, int* failures) {
     bad += !eqq(out[i].qadd, c + d);
     bad += !eqq(out[i].qsub, c - d);
     bad += !eqq(out[i].qinv, c.inv());
+    bad += !eqq(out[i].qsqr, c * c);
+    bad += !eqq(out[i].qlazy, c * d - d * d);
+    bad += !eqq(out[i].qkar, c * d);
+    bad += !eqq(out[i].qsep, c * d);
     tph::HG1 p = hp[i], q = hp[(i + 1) % n];
     if (i & 1) q.y = q.y.neg();
     tph::HG1 pq = tph::g1_add(p, q), p2 = tph::g1_dbl(p);
