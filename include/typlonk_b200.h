@@ -68,6 +68,11 @@ int tp_sync(tp_ctx* ctx);
 typedef int (*tp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
 int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user);
 
+/* Tunables.  "msm_affine_rounds" (0..8, default 0 or $TP_MSM_AFF_ROUNDS): batch-affine pair-addition
+ * rounds run on the bucket-sorted points before the XYZZ accumulation of tp_commit / tp_prove.  Results are
+ * identical for every setting (the affine sum of a bucket is unique). */
+int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value);
+
 /* Per-phase device timers (CUDA events on the ctx stream).  Phase ids: TP_PHASE_*. */
 enum {
   TP_PHASE_MSM_TOTAL = 0,

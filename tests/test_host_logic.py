@@ -113,3 +113,23 @@ def test_host_fr_rand_stream_matches_oracle():
     assert ffi.fr_rand_stream(5, 12) == fields.fr_vec_to_mont_bytes(rng.fr_rand_stream(5, 12))
     assert synthetic.tau() == rng.fr_rand_stream(1, 1)[0]
     assert synthetic.blinders() == rng.fr_rand_stream(2, 9)
+
+
+def test_safegcd_fq_inversion_host_build(tmp_path):
+    """typlonk_b200/csrc/fq_inv.cuh is plain C++: build it for the host and compare the division-step
+    inversion with Python's modular inverse (constants, the 30-round bound, the 0 -> 0 convention)."""
+    import random
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "fq_inv_test"
+    subprocess.run(["g++", "-O2", "-o", str(exe), os.path.join(root, "tools", "host_tests", "fq_inv_test.cpp")], check=True)
+    q = 0x1A0111EA397FE69A4B1BA7B6434BACD764774B84F38512BF6730D2A0F6B0F6241EABFFFEB153FFFFB9FEFFFFFFFFAAAB
+    rnd = random.Random(11)
+    xs = [0, 1, 2, q - 1, q - 2, (q - 1) // 2, (q + 1) // 2, 1 << 380, (1 << 192) + 1]
+    xs += [rnd.randrange(q) for _ in range(2000)] + [rnd.randrange(1 << k) for k in range(1, 381, 2)]
+    out = subprocess.run([str(exe)], input="\n".join("%x" % x for x in xs), capture_output=True, text=True,
+                         check=True).stdout.split()
+    assert len(out) == len(xs)
+    for x, o in zip(xs, out):
+        assert o != "FAIL"
+        assert int(o, 16) == (pow(x, -1, q) if x else 0)

@@ -75,6 +75,10 @@ int tp_ctx_create(int device, void* stream, tp_ctx** out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (const char* v = getenv("TP_MSM_AFF_ROUNDS")) {
+    long r = strtol(v, nullptr, 10);
+    if (r >= 0 && r <= 8) ctx->msm_aff_rounds = (unsigned)r;
+  }
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {
@@ -104,7 +108,8 @@ int tp_ctx_destroy(tp_ctx* ctx) {
   }
   DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_sorted,
                     &ctx->msm_sorted_keys, &ctx->msm_hist, &ctx->msm_offsets, &ctx->msm_blocksums, &ctx->msm_buckets,
-                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->flag};
+                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_aff_pts,
+                    &ctx->msm_sorted2, &ctx->msm_aff_cnt, &ctx->msm_aff_plan, &ctx->msm_aff_rec, &ctx->flag};
   for (auto* b : bufs) release(*b);
   for (auto& b : ctx->scan_tmp) release(b);
   for (auto& b : ctx->misc) release(b);
@@ -135,6 +140,16 @@ int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather
   ctx->allgather = allgather;
   ctx->allgather_user = user;
   return TP_OK;
+}
+
+int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
+  if (!ctx || !name) return TP_ERR_INVALID_ARG;
+  if (strcmp(name, "msm_affine_rounds") == 0) {
+    if (value < 0 || value > 8) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_affine_rounds must be 0..8");
+    ctx->msm_aff_rounds = (unsigned)value;
+    return TP_OK;
+  }
+  return fail(ctx, TP_ERR_INVALID_ARG, "set_option: unknown option");
 }
 
 static int prof_collect(tp_ctx* ctx) {

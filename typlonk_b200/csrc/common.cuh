@@ -43,6 +43,8 @@ struct tp_ctx {
   int rank = 0, world = 1;
   tp_allgather_fn allgather = nullptr;
   void* allgather_user = nullptr;
+  // tunables (tp_ctx_set_option)
+  unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
   // profiling
   bool prof = false;
   double prof_ms[TP_PHASE_COUNT] = {0};
@@ -60,7 +62,7 @@ struct tp_ctx {
   // scratch
   tp::DevBuf ntt_scratch;
   tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_sorted, msm_sorted_keys, msm_hist, msm_offsets, msm_blocksums,
-      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums;
+      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
   tp::DevBuf scan_tmp[8];
   tp::DevBuf misc[16];
   tp::DevBuf flag;

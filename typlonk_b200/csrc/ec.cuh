@@ -4,6 +4,7 @@
 // Mixed addition = 8M + 2S, general addition = 12M + 2S, doubling = 6M + 3S (Fq).
 #pragma once
 #include "field.cuh"
+#include "fq_inv.cuh"
 
 namespace tp {
 
@@ -36,6 +37,60 @@ __device__ __forceinline__ void xyzz_store(G1Xyzz* p, const G1Xyzz& a) {
 __device__ __forceinline__ G1Xyzz xyzz_load(const G1Xyzz* p) {
   G1Xyzz r;
   r.x = fq_load(&p->x); r.y = fq_load(&p->y); r.zz = fq_load(&p->zz); r.zzz = fq_load(&p->zzz);
+  return r;
+}
+
+// Montgomery-form inverse by division steps (fq_inv.cuh); Fermat only if those did not terminate.
+static __device__ __noinline__ Fq fq_inverse(const Fq& a) {
+  Fq plain, r;
+  if (!fqinv_plain(a.v, plain.v)) return fq_inv(a);
+  const uint32_t r3[12] = FQINV_R3;
+  Fq k;
+#pragma unroll
+  for (int i = 0; i < 12; i++) k.v[i] = r3[i];
+  r = fq_mul(plain, k);   // (a R)^-1 * R^3 / R = a^-1 R
+  return r;
+}
+
+// ---- affine pair addition with a shared (batched) inversion ------------------------------
+// kind of a pair P1 + P2: 0 = chord (denominator x2 - x1), 1 = tangent (denominator 2 y1),
+// 2 = result is the identity, 3 = result P1 (P2 is the identity), 4 = result P2.
+// For kinds >= 2 the denominator is 1 so that it can sit in the running product.
+static __device__ __noinline__ int affine_pair_special(const G1Affine& p1, const G1Affine& p2, Fq& d) {
+  d = fq_one();
+  if (affine_is_identity(p1)) return 4;
+  if (affine_is_identity(p2)) return 3;
+  if (fq_eq(p1.x, p2.x)) {
+    if (fq_eq(p1.y, p2.y) && !fq_is_zero(p1.y)) {
+      d = fq_dbl(p1.y);
+      return 1;
+    }
+    return 2;
+  }
+  d = fq_sub(p2.x, p1.x);  // x = 0 on a non-identity point: an ordinary chord after all
+  return 0;
+}
+// P1 + P2 given dinv = 1 / (denominator of `kind`); all cases of affine_pair_special.
+__device__ __forceinline__ G1Affine affine_pair_finish(const G1Affine& p1, const G1Affine& p2, int kind, const Fq& dinv) {
+  if (kind >= 2) {
+    G1Affine r;
+    if (kind == 3) return p1;
+    if (kind == 4) return p2;
+    r.x = fq_zero();
+    r.y = fq_zero();
+    return r;
+  }
+  Fq num;
+  if (kind == 0) {
+    num = fq_sub(p2.y, p1.y);
+  } else {
+    Fq xx = fq_sqr(p1.x);
+    num = fq_add(fq_dbl(xx), xx);
+  }
+  Fq lam = fq_mul(num, dinv);
+  G1Affine r;
+  r.x = fq_sub(fq_sub(fq_sqr(lam), p1.x), p2.x);
+  r.y = fq_sub(fq_mul(lam, fq_sub(p1.x, r.x)), p1.y);
   return r;
 }
 

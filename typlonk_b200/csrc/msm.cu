@@ -154,21 +154,22 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
   }
 }
 
-// ---- 2. exclusive scan of u32 (3 kernels) --------------------------------------------------
+// ---- 2. exclusive scan (3 kernels; T = u32, or u64 carrying two packed u32 counters) -------------
 #define SCAN_BLOCK 1024
-__global__ void k_scan_local(const unsigned* __restrict__ in, unsigned* __restrict__ out, unsigned* __restrict__ sums,
-                             size_t n, unsigned* __restrict__ max_out) {
-  __shared__ unsigned s[SCAN_BLOCK];
+template <typename T>
+__global__ void k_scan_local(const T* __restrict__ in, T* __restrict__ out, T* __restrict__ sums, size_t n,
+                             unsigned* __restrict__ max_out) {
+  __shared__ T s[SCAN_BLOCK];
   size_t g = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
-  unsigned v = g < n ? in[g] : 0;
-  if (max_out) {  // largest bucket (decides whether chunks can consist of a single run)
-    unsigned wmax = __reduce_max_sync(0xffffffffu, v);
+  T v = g < n ? in[g] : 0;
+  if (max_out) {  // largest bucket (decides whether chunks can consist of a single run); u32 only
+    unsigned wmax = __reduce_max_sync(0xffffffffu, (unsigned)v);
     if ((threadIdx.x & 31) == 0 && wmax > 0) atomicMax(max_out, wmax);
   }
   s[threadIdx.x] = v;
   __syncthreads();
   for (unsigned d = 1; d < SCAN_BLOCK; d <<= 1) {
-    unsigned t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+    T t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
     __syncthreads();
     s[threadIdx.x] += t;
     __syncthreads();
@@ -176,19 +177,20 @@ __global__ void k_scan_local(const unsigned* __restrict__ in, unsigned* __restri
   if (g < n) out[g] = s[threadIdx.x] - v;
   if (threadIdx.x == SCAN_BLOCK - 1) sums[blockIdx.x] = s[threadIdx.x];
 }
-__global__ void k_scan_sums(unsigned* sums, size_t nblocks) {
+template <typename T>
+__global__ void k_scan_sums(T* sums, size_t nblocks) {
   // single block, serial over tiles of SCAN_BLOCK
-  __shared__ unsigned s[SCAN_BLOCK];
-  __shared__ unsigned carry;
+  __shared__ T s[SCAN_BLOCK];
+  __shared__ T carry;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   for (size_t base = 0; base < nblocks; base += SCAN_BLOCK) {
     size_t g = base + threadIdx.x;
-    unsigned v = g < nblocks ? sums[g] : 0;
+    T v = g < nblocks ? sums[g] : 0;
     s[threadIdx.x] = v;
     __syncthreads();
     for (unsigned d = 1; d < SCAN_BLOCK; d <<= 1) {
-      unsigned t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
+      T t = threadIdx.x >= d ? s[threadIdx.x - d] : 0;
       __syncthreads();
       s[threadIdx.x] += t;
       __syncthreads();
@@ -199,7 +201,8 @@ __global__ void k_scan_sums(unsigned* sums, size_t nblocks) {
     __syncthreads();
   }
 }
-__global__ void k_scan_add(unsigned* out, const unsigned* sums, size_t n) {
+template <typename T>
+__global__ void k_scan_add(T* out, const T* sums, size_t n) {
   size_t g = (size_t)blockIdx.x * SCAN_BLOCK + threadIdx.x;
   if (g < n) out[g] += sums[blockIdx.x];
 }
@@ -220,19 +223,242 @@ __global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned*
   sorted[pos] = make_uint2(((w % levels) * stride + i) | (key & 0x80000000u), k);  // one 8-byte store
 }
 
-// ---- 4. segmented accumulation ---------------------------------------------------------------
+// ---- 4a. batch-affine rounds --------------------------------------------------------------
+// Before the XYZZ accumulation the bucket-sorted entry list is halved a few times in AFFINE
+// coordinates: in every round each bucket pairs its entries (2q, 2q+1) and replaces a pair by its
+// sum, an odd last entry passes through.  An affine addition is 1 inversion + 2M + 1S; the
+// inversion is shared by the AFF_K pairs one thread owns (Montgomery's trick: 3M per pair) and is
+// itself done by division steps on the ALU pipe (fq_inv.cuh), so a pair costs 5M + 1S = 1662 wide
+// multiplies against 2604 for the XYZZ mixed addition -- the FMA-heavy pipe is what bounds the MSM.
+// Work is assigned by PAIR index (a scan of pairs per bucket), so every lane of a warp has exactly
+// AFF_K real additions whatever the bucket sizes are.
+//
+// Points are addressed through one index space: idx < split -> fixed-base table, else -> scratch
+// array of sums (round outputs); entries that pass through unpaired keep their index (and sign).
+#define AFF_K 32            // most pairs per thread (local array of prefix products)
+#define AFF_MAX_ROUNDS 8
+__device__ __forceinline__ const G1Affine* msm_point(const G1Affine* __restrict__ bases, const G1Affine* __restrict__ scratch,
+                                                     unsigned split, unsigned idx31) {
+  return idx31 < split ? bases + idx31 : scratch + (idx31 - split);
+}
+__device__ __forceinline__ G1Affine msm_point_load(const G1Affine* __restrict__ bases, const G1Affine* __restrict__ scratch,
+                                                   unsigned split, unsigned idx) {
+  G1Affine p = affine_load(msm_point(bases, scratch, split, idx & 0x7fffffffu));
+  if (idx >> 31) p.y = fq_neg(p.y);
+  return p;
+}
+
+// per bucket: pairs this round and entries next round, packed as (next << 32 | pairs) for ONE scan
+__global__ void k_aff_plan(const unsigned* __restrict__ cnt_in, size_t nkeys, unsigned* __restrict__ cnt_out,
+                           unsigned long long* __restrict__ packed) {
+  size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > nkeys) return;
+  unsigned c = b < nkeys ? cnt_in[b] : 0;
+  unsigned nxt = (c + 1) >> 1;
+  if (b < nkeys) cnt_out[b] = nxt;
+  packed[b] = ((unsigned long long)nxt << 32) | (c >> 1);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+
+// One thread per entry of the round's input list: the even entries of a bucket open a pair and
+// write its record (index | sign of both operands, output position, bucket) at the pair's global
+// index, an odd last entry passes through to the next list.  No searching: an entry carries its
+// bucket, the scanned plan gives the bucket's first pair and its first output slot.
+__global__ void k_aff_records(const uint2* __restrict__ l_in, const unsigned* __restrict__ m_ptr,
+                              const unsigned* __restrict__ cnt_in, const unsigned* __restrict__ off_in, unsigned off_stride,
+                              const unsigned long long* __restrict__ plan, uint4* __restrict__ rec,
+                              uint2* __restrict__ l_out) {
+  const unsigned e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= *m_ptr) return;
+  const uint2 ent = l_in[e];
+  const unsigned b = ent.y;
+  const unsigned q = e - off_in[(size_t)b * off_stride];
+  if (q & 1) return;
+  const unsigned long long pl = plan[b];
+  const unsigned o = (unsigned)(pl >> 32) + (q >> 1);
+  if (q + 1 < cnt_in[b]) {
+    rec[(unsigned)pl + (q >> 1)] = make_uint4(ent.x, l_in[e + 1].x, o, b);
+  } else {
+    l_out[o] = ent;
+  }
+}
+
+// AFF_THREADS threads share ONE inversion: every thread multiplies up the denominators of its
+// k_run pairs, the block multiplies the thread products together (prefix and suffix scans in
+// shared memory), warp 0 inverts the block product by division steps, and every thread gets its
+// own inverse back with two more multiplications.
+#define AFF_THREADS 128
+#define AFF_SMEM_STAGE (2 * 12 * AFF_THREADS * 16)              // cp.async staging: [2 stages][12 chunks][thread] x 16 B
+#define AFF_SMEM (AFF_SMEM_STAGE)                                // the scans reuse the staging area
+__device__ __forceinline__ Fq sh_fq_load(const uint32_t* base, unsigned t) {  // limb-major: conflict-free
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.v[i] = base[i * AFF_THREADS + t];
+  return r;
+}
+__device__ __forceinline__ void sh_fq_store(uint32_t* base, unsigned t, const Fq& a) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) base[i * AFF_THREADS + t] = a.v[i];
+}
+
+__global__ void __launch_bounds__(AFF_THREADS, 4) k_aff_round(const G1Affine* __restrict__ bases, G1Affine* __restrict__ scratch,
+                                                              unsigned split, const uint4* __restrict__ rec,
+                                                              const unsigned long long* __restrict__ plan, unsigned nkeys,
+                                                              uint2* __restrict__ l_out, unsigned region, unsigned k_run) {
+  extern __shared__ uint4 aff_sh[];
+  const unsigned pairs_total = (unsigned)plan[nkeys];
+  const unsigned block_p0 = blockIdx.x * AFF_THREADS * k_run;
+  if (block_p0 >= pairs_total) return;  // whole block idle (grid sized from an upper bound)
+  const unsigned p0 = block_p0 + threadIdx.x * k_run;
+  const unsigned np = p0 >= pairs_total ? 0 : (pairs_total - p0 < k_run ? pairs_total - p0 : k_run);
+  const uint4* my = rec + p0;
+  Fq pre[AFF_K];
+  // Operands travel global -> shared with cp.async one pair ahead of the arithmetic (thread-private
+  // slots, chunk-major so that a warp's 16-byte accesses are conflict-free).
+  auto stage_pair = [&](int stage, const uint4& rc, int chunks_per_point) {
+    const uint4* a1 = (const uint4*)msm_point(bases, scratch, split, rc.x & 0x7fffffffu);
+    const uint4* a2 = (const uint4*)msm_point(bases, scratch, split, rc.y & 0x7fffffffu);
+    for (int c = 0; c < chunks_per_point; c++) {
+      cp_async16(&aff_sh[(stage * 12 + c) * AFF_THREADS + threadIdx.x], a1 + c);
+      cp_async16(&aff_sh[(stage * 12 + 6 + c) * AFF_THREADS + threadIdx.x], a2 + c);
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  auto staged_fq = [&](int stage, int chunk0) {
+    Fq r;
+    const uint4 a = aff_sh[(stage * 12 + chunk0) * AFF_THREADS + threadIdx.x],
+                b = aff_sh[(stage * 12 + chunk0 + 1) * AFF_THREADS + threadIdx.x],
+                c = aff_sh[(stage * 12 + chunk0 + 2) * AFF_THREADS + threadIdx.x];
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    r.v[8] = c.x; r.v[9] = c.y; r.v[10] = c.z; r.v[11] = c.w;
+    return r;
+  };
+  Fq acc = fq_one();
+  uint4 rc_next = np ? my[0] : make_uint4(0, 0, 0, 0);
+  uint4 rc_next2 = np > 1 ? my[1] : rc_next;   // records run two pairs ahead, operands one pair ahead
+  if (np) stage_pair(0, rc_next, 3);
+  for (unsigned i = 0; i < np; i++) {
+    const uint4 rc = rc_next;
+    if (i + 1 < np) {
+      rc_next = rc_next2;
+      if (i + 2 < np) rc_next2 = my[i + 2];
+      stage_pair((i + 1) & 1, rc_next, 3);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    const Fq x1 = staged_fq(i & 1, 0), x2 = staged_fq(i & 1, 6);
+    Fq d = fq_sub(x2, x1);
+    if (fq_is_zero(d) || fq_is_zero(x1) || fq_is_zero(x2)) {  // doubling, cancellation or an identity operand
+      G1Affine f1 = msm_point_load(bases, scratch, split, rc.x), f2 = msm_point_load(bases, scratch, split, rc.y);
+      Fq ds;
+      affine_pair_special(f1, f2, ds);
+      d = ds;
+    }
+    pre[i] = acc;
+    acc = fq_mul(acc, d);
+  }
+  // ---- block-wide inversion of the thread products ----
+  __syncthreads();  // staging area is free
+  uint32_t* pa = (uint32_t*)aff_sh;                       // inclusive prefix products
+  uint32_t* sa = pa + 12 * AFF_THREADS;                   // inclusive suffix products
+  uint32_t* tot = sa + 12 * AFF_THREADS;                  // inverse of the block product
+  const unsigned t = threadIdx.x;
+  sh_fq_store(pa, t, acc);
+  sh_fq_store(sa, t, acc);
+  __syncthreads();
+  for (unsigned dlt = 1; dlt < AFF_THREADS; dlt <<= 1) {
+    Fq vp, vs;
+    const bool hp = t >= dlt, hs = t + dlt < AFF_THREADS;
+    if (hp) vp = fq_mul(sh_fq_load(pa, t), sh_fq_load(pa, t - dlt));
+    if (hs) vs = fq_mul(sh_fq_load(sa, t), sh_fq_load(sa, t + dlt));
+    __syncthreads();
+    if (hp) sh_fq_store(pa, t, vp);
+    if (hs) sh_fq_store(sa, t, vs);
+    __syncthreads();
+  }
+  if (t < 32) {
+    Fq all = sh_fq_load(pa, AFF_THREADS - 1);
+    Fq iv = fq_inverse(all);
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < 12; i++) tot[i] = iv.v[i];
+    }
+  }
+  __syncthreads();
+  Fq inv;
+#pragma unroll
+  for (int i = 0; i < 12; i++) inv.v[i] = tot[i];
+  if (t > 0) inv = fq_mul(inv, sh_fq_load(pa, t - 1));
+  if (t + 1 < AFF_THREADS) inv = fq_mul(inv, sh_fq_load(sa, t + 1));
+  __syncthreads();  // scans done: the area goes back to staging
+  // ---- backward: one addition per pair ----
+  if (np) {
+    rc_next = my[np - 1];
+    rc_next2 = np > 1 ? my[np - 2] : rc_next;
+    stage_pair((np - 1) & 1, rc_next, 6);
+  }
+  for (int i = (int)np - 1; i >= 0; i--) {
+    const uint4 rc = rc_next;
+    if (i > 0) {
+      rc_next = rc_next2;
+      if (i > 1) rc_next2 = my[i - 2];
+      stage_pair((i - 1) & 1, rc_next, 6);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    G1Affine p1, p2;
+    p1.x = staged_fq(i & 1, 0);
+    p1.y = staged_fq(i & 1, 3);
+    p2.x = staged_fq(i & 1, 6);
+    p2.y = staged_fq(i & 1, 9);
+    if (rc.x >> 31) p1.y = fq_neg(p1.y);
+    if (rc.y >> 31) p2.y = fq_neg(p2.y);
+    Fq d = fq_sub(p2.x, p1.x);
+    int kind = 0;
+    if (fq_is_zero(d) || fq_is_zero(p1.x) || fq_is_zero(p2.x)) {
+      G1Affine f1 = p1, f2 = p2;  // copies: the hot operands never have their address taken
+      Fq ds;
+      kind = affine_pair_special(f1, f2, ds);
+      d = ds;
+    }
+    const Fq dinv = fq_mul(inv, pre[i]);
+    inv = fq_mul(inv, d);
+    const G1Affine r = affine_pair_finish(p1, p2, kind, dinv);
+    G1Affine* dst = scratch + region + rc.z;
+    fq_store(&dst->x, r.x);
+    fq_store(&dst->y, r.y);
+    l_out[rc.z] = make_uint2(split + region + rc.z, rc.w);
+  }
+}
+
+// ---- 4b. segmented accumulation --------------------------------------------------------------
 // part_keys[2t], part_keys[2t+1]: keys of the head / tail partial of chunk t (MSM_NONE if absent)
 #ifndef TP_ACC_MIN_BLOCKS
 #define TP_ACC_MIN_BLOCKS 1
 #endif
 __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
+                                                        const G1Affine* __restrict__ scratch, unsigned split,
                                                         const uint2* __restrict__ sorted /* (index | sign, key) */,
-                                                        unsigned m_total,
+                                                        const unsigned* __restrict__ m_ptr /* live entry count */,
+                                                        unsigned nchunks,
                                                         G1Xyzz* __restrict__ buckets, unsigned* __restrict__ part_keys,
                                                         G1Xyzz* __restrict__ part_pts, unsigned chunk) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nchunks) return;
+  const unsigned m_total = *m_ptr;
   unsigned start = t * chunk;
-  if (start >= m_total) return;
+  if (start >= m_total) {  // the grid is sized from an upper bound of the list length
+    part_keys[2 * t] = MSM_NONE | MSM_IDENT;
+    part_keys[2 * t + 1] = MSM_NONE | MSM_IDENT;
+    return;
+  }
   unsigned end = start + chunk < m_total ? start + chunk : m_total;
   G1Xyzz acc = xyzz_identity();
   unsigned cur = sorted[start].y;
@@ -252,7 +478,7 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
       cur = key;
     }
     const unsigned idx = ent.x;
-    G1Affine p = affine_load(bases + (idx & 0x7fffffffu));
+    G1Affine p = affine_load(msm_point(bases, scratch, split, idx & 0x7fffffffu));
     if (!affine_is_identity(p)) xyzz_madd(acc, p, (idx >> 31) != 0);
   }
   if (is_first_run) {
@@ -279,6 +505,7 @@ __global__ void __launch_bounds__(128) k_msm_pair_fixup(const unsigned* __restri
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
   const unsigned hk = part_keys[2 * t];
+  if ((hk & MSM_NONE) == MSM_NONE) return;  // chunk beyond the live list
   const unsigned lraw = part_keys[2 * t + 1];
   const bool multi = !(lraw & MSM_IDENT);
   const bool head_starts = t == 0 || (part_keys[2 * t - 1] & MSM_NONE) != hk;
@@ -325,7 +552,7 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
         keys_out[2 * t] = cur;
         xyzz_store(pts_out + 2 * t, acc);
         is_first_run = false;
-      } else {
+      } else if (cur != MSM_NONE) {
         xyzz_store(buckets + cur, acc);
       }
       cur = key;
@@ -336,7 +563,7 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
     }
   }
   if (final_level) {
-    xyzz_store(buckets + cur, acc);
+    if (cur != MSM_NONE) xyzz_store(buckets + cur, acc);
   } else if (is_first_run) {
     keys_out[2 * t] = cur;
     xyzz_store(pts_out + 2 * t, acc);
@@ -447,15 +674,16 @@ void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]) {
   }
 }
 
-static int exclusive_scan_u32(tp_ctx* ctx, const unsigned* in, unsigned* out, size_t n, unsigned* max_out) {
+template <typename T>
+static int exclusive_scan(tp_ctx* ctx, const T* in, T* out, size_t n, unsigned* max_out) {
   size_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-  TP_TRY(ensure(ctx, ctx->msm_blocksums, nblocks * sizeof(unsigned)));
-  unsigned* sums = (unsigned*)ctx->msm_blocksums.p;
-  k_scan_local<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n, max_out);
+  TP_TRY(ensure(ctx, ctx->msm_blocksums, nblocks * sizeof(T)));
+  T* sums = (T*)ctx->msm_blocksums.p;
+  k_scan_local<T><<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(in, out, sums, n, max_out);
   TP_LAUNCH(ctx, "k_scan_local");
-  k_scan_sums<<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nblocks);
+  k_scan_sums<T><<<1, SCAN_BLOCK, 0, ctx->stream>>>(sums, nblocks);
   TP_LAUNCH(ctx, "k_scan_sums");
-  k_scan_add<<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(out, sums, n);
+  k_scan_add<T><<<(unsigned)nblocks, SCAN_BLOCK, 0, ctx->stream>>>(out, sums, n);
   TP_LAUNCH(ctx, "k_scan_add");
   return TP_OK;
 }
@@ -502,7 +730,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, hist, keys,
                                                 ranks);
     TP_LAUNCH(ctx, "k_msm_digits");
-    TP_TRY(exclusive_scan_u32(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
+    TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
     k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
                                                                            pl.levels, (unsigned)srs->len, sorted);
     TP_LAUNCH(ctx, "k_msm_scatter");
@@ -514,19 +742,117 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     max_bucket = ((unsigned*)ctx->pinned)[1];
   }
   if (m_total == 0) return TP_OK;  // all scalars zero
+  // ---- batch-affine rounds (4a): plan on the host from upper bounds, sizes stay on the device ----
+  // bound[r] >= entries before round r + 1: every round leaves ceil(cnt / 2) per bucket.
+  // Off by default: on sm_100a the rounds do not beat the XYZZ accumulation they replace (profiles/r1_summary.md K);
+  // tp_ctx_set_option("msm_affine_rounds", r) or TP_MSM_AFF_ROUNDS=r turn them on.
+  const unsigned aff_rounds_env = ctx->msm_aff_rounds;
+  const unsigned aff_disable = aff_rounds_env == 0;
+  size_t bound[AFF_MAX_ROUNDS + 1];
+  bound[0] = m_total;
+  int rounds = 0;
+  unsigned max_b = max_bucket;
+  const size_t split = (size_t)pl.levels * srs->len - first;  // table indices are < split (relative to `bases`)
+  if (!aff_disable) {
+    const int want = (int)(aff_rounds_env < AFF_MAX_ROUNDS ? aff_rounds_env : AFF_MAX_ROUNDS);
+    while (rounds < want) {
+      // a round needs buckets that hold >= 2 entries on average (the key arrays are reused as counters)
+      if (bound[rounds] < 2 * nkeys || bound[rounds] < 64) break;
+      bound[rounds + 1] = bound[rounds] / 2 + nkeys;
+      rounds++;
+    }
+  }
+  size_t scratch_pts = 0;
+  for (int r = 1; r <= rounds; r++) scratch_pts += bound[r];
+  if (rounds > 0) {
+    // memory: the sums of all rounds stay addressable (later rounds and the accumulation read them)
+    const size_t need = scratch_pts * sizeof(G1Affine) + bound[1] * sizeof(uint2);
+    if (split + scratch_pts >= ((size_t)1 << 31)) {
+      rounds = 0;
+    } else if (need > ctx->msm_aff_pts.cap + ctx->msm_sorted2.cap) {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo(&free_b, &total_b);
+      if (need > (free_b + ctx->msm_aff_pts.cap + ctx->msm_sorted2.cap) / 10 * 8) rounds = 0;  // falls back to XYZZ only
+    }
+  }
+  const uint2* final_list = sorted;
+  const unsigned* final_m = offsets + nkeys;
+  const G1Affine* scratch = nullptr;
+  if (rounds > 0) {
+    ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
+    TP_TRY(ensure(ctx, ctx->msm_aff_pts, scratch_pts * sizeof(G1Affine)));
+    TP_TRY(ensure(ctx, ctx->msm_sorted2, bound[1] * sizeof(uint2)));
+    TP_TRY(ensure(ctx, ctx->msm_aff_cnt, nkeys * sizeof(unsigned)));
+    TP_TRY(ensure(ctx, ctx->msm_aff_plan, 2 * (nkeys + 1) * sizeof(unsigned long long)));
+    G1Affine* sc = (G1Affine*)ctx->msm_aff_pts.p;
+    scratch = sc;
+    uint2* lists[2] = {sorted, (uint2*)ctx->msm_sorted2.p};
+    unsigned* cnts[2] = {hist, (unsigned*)ctx->msm_aff_cnt.p};   // round 1 reads the histogram; it must survive (the
+                                                                 // reduction uses it to skip empty buckets), so the
+                                                                 // ping-pong writes go to aff_cnt / keys scratch
+    unsigned* cnt_alt = keys;  // the digit keys are dead after the scatter: reuse as the second counter array
+    unsigned long long* plans[2] = {(unsigned long long*)ctx->msm_aff_plan.p,
+                                    (unsigned long long*)ctx->msm_aff_plan.p + (nkeys + 1)};
+    const unsigned* off_in = offsets;
+    unsigned off_stride = 1;
+    const unsigned* cnt_in = hist;
+    const unsigned* m_in = offsets + nkeys;
+    TP_TRY(ensure(ctx, ctx->msm_aff_rec, (bound[0] / 2 + 1) * sizeof(uint4)));
+    uint4* rec = (uint4*)ctx->msm_aff_rec.p;
+    size_t region = 0;
+    static bool smem_attr = false;
+    if (!smem_attr) {
+      TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_aff_round, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_SMEM));
+      smem_attr = true;
+    }
+    for (int r = 0; r < rounds; r++) {
+      unsigned* cnt_out = (r & 1) ? cnt_alt : cnts[1];
+      unsigned long long* plan = plans[r & 1];
+      const uint2* l_in = lists[r & 1];
+      uint2* l_out = lists[(r + 1) & 1];
+      k_aff_plan<<<(unsigned)((nkeys + 1 + 255) / 256), 256, 0, ctx->stream>>>(cnt_in, nkeys, cnt_out, plan);
+      TP_LAUNCH(ctx, "k_aff_plan");
+      TP_TRY(exclusive_scan<unsigned long long>(ctx, plan, plan, nkeys + 1, nullptr));
+      const size_t pair_bound = bound[r] / 2;
+      k_aff_records<<<(unsigned)((bound[r] + 255) / 256), 256, 0, ctx->stream>>>(l_in, m_in, cnt_in, off_in, off_stride, plan,
+                                                                                 rec, l_out);
+      TP_LAUNCH(ctx, "k_aff_records");
+      // pairs per thread: as many as the local arrays hold, fewer when that fills whole waves of the GPU more evenly
+      const size_t wave = (size_t)ctx->sm_count * 4 * AFF_THREADS;  // resident threads
+      size_t waves = (pair_bound + wave * AFF_K - 1) / (wave * AFF_K);
+      unsigned k_run = (unsigned)((pair_bound + waves * wave - 1) / (waves * wave));
+      static unsigned k_env = env_uint("TP_MSM_AFF_K", 0);
+      if (k_env) k_run = k_env;
+      if (k_run > AFF_K) k_run = AFF_K;
+      if (k_run < 8) k_run = 8;
+      const unsigned nblocks = (unsigned)((pair_bound + (size_t)k_run * AFF_THREADS - 1) / ((size_t)k_run * AFF_THREADS));
+      k_aff_round<<<nblocks ? nblocks : 1, AFF_THREADS, AFF_SMEM, ctx->stream>>>(bases, sc, (unsigned)split, rec, plan,
+                                                                                 (unsigned)nkeys, l_out, (unsigned)region, k_run);
+      TP_LAUNCH(ctx, "k_aff_round");
+      m_in = (const unsigned*)(plan + nkeys) + 1;
+      region += bound[r + 1];
+      cnt_in = cnt_out;
+      off_in = (const unsigned*)plan + 1;   // high halves of the scanned plan = offsets of the next list
+      off_stride = 2;
+      final_list = l_out;
+      final_m = (const unsigned*)(plan + nkeys) + 1;
+      max_b = (max_b + 1) / 2;
+    }
+  }
   // Entries per accumulate thread: longer chunks when buckets are long (fewer boundary partials),
   // as long as the grid still fills the GPU several times over.
-  unsigned chunk = msm_chunk();
-  while (chunk <= max_bucket && chunk < 1024 && (size_t)m_total / (2 * chunk) >= (size_t)ctx->sm_count * 384 * 4) chunk *= 2;
-  const bool pair_path = max_bucket < PAIR_MAX_SPAN * chunk && !msm_force_levels();
-  unsigned nchunks = (m_total + chunk - 1) / chunk;
+  const size_t m_bound = bound[rounds];
+  unsigned chunk = rounds > 0 ? 16 : msm_chunk();
+  while (chunk <= max_b && chunk < 1024 && m_bound / (2 * chunk) >= (size_t)ctx->sm_count * 384 * 4) chunk *= 2;
+  const bool pair_path = max_b < PAIR_MAX_SPAN * chunk && !msm_force_levels();
+  unsigned nchunks = (unsigned)((m_bound + chunk - 1) / chunk);
   // first half: accumulate's partials; second half: ping-pong space for the merge levels
   TP_TRY(ensure(ctx, ctx->msm_part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
-    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, sorted, m_total, buckets,
-                                                                     (unsigned*)ctx->msm_part_keys.p,
+    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, scratch, (unsigned)split, final_list, final_m,
+                                                                     nchunks, buckets, (unsigned*)ctx->msm_part_keys.p,
                                                                      (G1Xyzz*)ctx->msm_part_pts.p, chunk);
     TP_LAUNCH(ctx, "k_msm_accumulate");
   }

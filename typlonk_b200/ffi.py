@@ -27,7 +27,7 @@ SYMBOLS = [
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
-    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream",
+    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -133,6 +133,10 @@ class Context:
         v = C.c_uint64()
         self._check(lib().tp_launch_count(self._h, C.byref(v)))
         return v.value
+
+    def set_option(self, name, value):
+        """Tunables of the library ("msm_affine_rounds": 0..8); results do not depend on them."""
+        self._check(lib().tp_ctx_set_option(self._h, name.encode(), C.c_long(int(value))))
 
     def set_shard(self, rank, world, allgather=None):
         """allgather(send: bytes) -> bytes of world * len(send) (e.g. via torch.distributed)."""
