@@ -224,16 +224,41 @@ def main():
     ms_step = ms_total / args.steps
     hbm_peak, peak_kind = _peaks()
     # dominant kernel: MSM bucket accumulation.  Algorithmic bytes per MSM = 128 B / point
-    # (96 B base + 32 B scalar); per launch it processes this rank's shard.
+    # (96 B base + 32 B scalar); a launch processes this rank's shard of every
+    # MSM in its batch (13 MSMs per proof go out as batches of 3 + 1 + 9 = 3 launches).
     acc_ms, acc_launches = prof["msm_accum"]
-    pts_per_launch = n / world
-    achieved = (128.0 * pts_per_launch) / (acc_ms / max(acc_launches, 1) * 1e-3) / 1e9 if acc_ms > 0 else None
+    acc_launch_ms = acc_ms / max(acc_launches, 1)
+    msms = ctx.get_stat("msm_calls")
+    entries = ctx.get_stat("msm_entries")
+    pts_per_launch = (n / world) * msms / max(acc_launches, 1)
+    achieved = (128.0 * pts_per_launch) / (acc_launch_ms * 1e-3) / 1e9 if acc_ms > 0 else None
+    affine = bool(int(os.environ.get("TP_MSM_AFFINE", "0")))
+    kernel = "k_msm_accumulate_affine" if affine else "k_msm_accumulate"
+    # DRAM bytes per bucket addition of that kernel, from the committed `ncu --set full` capture
+    # (profiles/traffic.json; dram__bytes_read.sum + dram__bytes_write.sum over the additions of the launch)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)[kernel]["dram_bytes_per_addition"] * entries / max(acc_launches, 1)
+    except Exception:  # noqa: BLE001
+        pass
     imad, imad_wide = ctx.measure_imad_peak()
-    # integer work of one accumulate launch: entries x (8M + 2S) Fq products x 300 wide IMADs
-    roofline = {"bound": "hbm", "kernel": "k_msm_accumulate", "achieved": achieved, "peak": hbm_peak,
-                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm_peak,
+                "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                 "peak_kind": peak_kind,
-                "note": "256/384-bit Montgomery arithmetic makes this kernel integer-pipe bound, see roofline_int"}
+                "note": "381-bit Montgomery arithmetic makes this kernel integer-pipe bound (SURVEY 8d): see roofline_int; "
+                        "traffic exceeds the 128 B/point figure by design: every point is read once per window from "
+                        "its fixed-base table level"}
+    # integer roofline of the same kernel: wide multiply-adds (IMAD.WIDE.U32.X) retired per second against the
+    # measured peak of that instruction (tp_measure_imad_peak, carry-chain form).  Per bucket addition:
+    # XYZZ mixed = 8 x 288 + 2 x 222; affine chain = 5 x 288 + 222 + (3.9e3 + 288)/16 for the shared inversion.
+    per_add = (5 * 288 + 222 + (3900 + 288) / 16.0) if affine else (8 * 288 + 2 * 222)
+    prod_rate = entries * per_add / (acc_ms * 1e-3) if acc_ms > 0 else None
+    roofline_int = {"bound": "fma-heavy pipe (IMAD.WIDE.U32.X)", "kernel": kernel, "achieved": prod_rate,
+                    "peak": imad_wide, "unit": "wide multiply-adds/s", "frac": (prod_rate / imad_wide) if prod_rate else None,
+                    "additions_per_step": entries / args.steps, "wide_products_per_addition": per_add,
+                    "window_bits": ctx.get_stat("msm_window_bits"), "windows": ctx.get_stat("msm_windows"),
+                    "table_levels": ctx.get_stat("msm_table_levels")}
     line = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -245,6 +270,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_int": roofline_int,
         "phases_ms_per_step": {p: round(prof[p][0] / args.steps, 3) for p in PHASES},
         "imad_peak_per_s": imad_wide,
         "proof_sha256": __import__("hashlib").sha256(proof).hexdigest()[:16],

@@ -68,10 +68,17 @@ int tp_sync(tp_ctx* ctx);
 typedef int (*tp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
 int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user);
 
-/* Tunables.  "msm_affine_rounds" (0..8, default 0 or $TP_MSM_AFF_ROUNDS): batch-affine pair-addition
- * rounds run on the bucket-sorted points before the XYZZ accumulation of tp_commit / tp_prove.  Results are
- * identical for every setting (the affine sum of a bucket is unique). */
+/* Tunables of the MSM behind tp_commit / tp_open / tp_prove.  Results are identical for every
+ * setting (the affine sum of a bucket is unique).
+ *   "msm_affine_chains" (0/1, $TP_MSM_AFFINE): accumulate buckets in affine coordinates, 16 chunks of the
+ *       bucket-sorted list per thread in lockstep with one shared inversion per step (5M + 1S per addition);
+ *   "msm_affine_rounds" (0..8, $TP_MSM_AFF_ROUNDS): batch-affine pair-addition rounds run on the bucket-sorted
+ *       points before the XYZZ accumulation (kept for comparison; see profiles/). */
 int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value);
+/* Work counters since the last tp_prof_reset: "msm_entries" (bucket additions issued by the accumulation
+ * kernels), "msm_calls"; and the plan of the last MSM: "msm_window_bits", "msm_windows", "msm_table_levels",
+ * "msm_chunk".  Unknown names fail with TP_ERR_INVALID_ARG. */
+int tp_ctx_get_stat(tp_ctx* ctx, const char* name, double* out);
 
 /* Per-phase device timers (CUDA events on the ctx stream).  Phase ids: TP_PHASE_*. */
 enum {

@@ -1,6 +1,7 @@
-"""GPU parity of the opt-in batch-affine MSM rounds (tp_ctx_set_option "msm_affine_rounds"):
-the commitment must not depend on the number of rounds -- same oracle, same edge cases as the
-default XYZZ accumulation (doubling, cancellation, identity operands, skewed buckets)."""
+"""GPU parity of the batch-affine MSM variants (tp_ctx_set_option "msm_affine_rounds" = pair
+rounds, "msm_affine_chains" = lockstep affine chains): the commitment must not depend on the
+accumulation strategy -- same oracle, same edge cases as the XYZZ accumulation (doubling,
+cancellation, identity operands, skewed buckets)."""
 import pytest
 
 from oracle.pyoracle import curve, fields, rng
@@ -11,10 +12,11 @@ pytestmark = pytest.mark.gpu
 R = fields.R_MOD
 
 
-@pytest.fixture(scope="module", params=[1, 3])
+@pytest.fixture(scope="module", params=["rounds1", "rounds3", "chains", "xyzz"])
 def actx(request):
     c = Context(0)
-    c.set_option("msm_affine_rounds", request.param)
+    c.set_option("msm_affine_chains", 1 if request.param == "chains" else 0)
+    c.set_option("msm_affine_rounds", {"rounds1": 1, "rounds3": 3}.get(request.param, 0))
     yield c
     c.close()
 
@@ -23,6 +25,8 @@ def test_option_validation(actx):
     from typlonk_b200.ffi import TyplonkError
     with pytest.raises(TyplonkError):
         actx.set_option("msm_affine_rounds", 99)
+    with pytest.raises(TyplonkError):
+        actx.set_option("msm_affine_chains", 2)
     with pytest.raises(TyplonkError):
         actx.set_option("no_such_option", 1)
 
@@ -70,3 +74,19 @@ def test_large_vs_trapdoor(actx, kind):
     for s in reversed(scalars):
         acc = (acc * tau + s) % R
     assert KzgScheme(srs).commit(scalars) == curve.g1_mul(curve.G1_GEN, acc)
+
+
+def test_proof_bytes_do_not_depend_on_the_strategy(actx):
+    """Full prove of a 2^12-row mul-chain circuit: byte-identical to the C++ oracle's proof whatever
+    the bucket accumulation does."""
+    from oracle import coracle
+    from typlonk_b200 import field as F, synthetic
+    log_n = 12
+    n = 1 << log_n
+    circuit = synthetic.mul_chain_direct(actx, log_n)
+    cols = synthetic.mul_chain_witness(n - 3, n)
+    proof = circuit.handle.prove([F.fr_vec_to_bytes(c) for c in cols], bytes(32 * n))
+    tau_b, sel, perm, ocols, pi = coracle.mul_chain_inputs(log_n)
+    oc = coracle.Circuit(tau_b, sel, perm, n)
+    assert oc.prove(ocols, pi) == proof
+    oc.close()

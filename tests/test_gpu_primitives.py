@@ -46,6 +46,41 @@ def test_coset_ntt_round_trip(ctx, log_n):
     assert F.fr_vec_from_bytes(back) == data
 
 
+@pytest.mark.parametrize("log_n", list(range(1, 23)))
+def test_ntt_every_pass_geometry_vs_c_oracle(ctx, log_n):
+    """Every pass plan of the radix-8 kernel (1-3 passes, 1-3 rounds per pass, remainders 0/1/2)
+    against the C++ oracle's radix-2 NTT, forward and inverse, bit-exact."""
+    import numpy as np
+    from oracle import coracle
+    n = 1 << log_n
+    rs = np.random.RandomState(100 + log_n)
+    raw = rs.randint(0, 2**32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    raw[:, 7] &= 0x3FFFFFFF
+    data = raw.tobytes()
+    assert ctx.ntt(data, log_n) == coracle.ntt(data, log_n)
+    assert ctx.ntt(data, log_n, inverse=True) == coracle.ntt(data, log_n, inverse=True)
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 5, 12, 15, 19])
+def test_coset_ntt_vs_scaled_plain(ctx, log_n):
+    """coset NTT(x)_i = NTT(x_j g^j)_i, and the inverse coset transform undoes it (multi-pass sizes)."""
+    import numpy as np
+    n = 1 << log_n
+    rs = np.random.RandomState(200 + log_n)
+    raw = rs.randint(0, 2**32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
+    raw[:, 7] &= 0x3FFFFFFF
+    data = raw.tobytes()
+    g = F.fr_to_bytes(7)
+    ev = ctx.ntt(data, log_n, coset_mont=g)
+    vals = F.fr_vec_from_bytes(data)
+    gp, scaled = 1, []
+    for v in vals:
+        scaled.append(v * gp % R)
+        gp = gp * 7 % R
+    assert ev == ctx.ntt(F.fr_vec_to_bytes(scaled), log_n)
+    assert ctx.ntt(ev, log_n, inverse=True, coset_mont=g) == data
+
+
 def test_ntt_linearity_large(ctx):
     """Size-independent property at a BASELINE-scale size (2^20): NTT(a + b) = NTT(a) + NTT(b),
     iNTT(NTT(a)) = a."""

@@ -79,6 +79,7 @@ int tp_ctx_create(int device, void* stream, tp_ctx** out) {
     long r = strtol(v, nullptr, 10);
     if (r >= 0 && r <= 8) ctx->msm_aff_rounds = (unsigned)r;
   }
+  if (const char* v = getenv("TP_MSM_AFFINE")) ctx->msm_affine_chains = strtol(v, nullptr, 10) != 0 ? 1u : 0u;
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {
@@ -149,7 +150,25 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
     ctx->msm_aff_rounds = (unsigned)value;
     return TP_OK;
   }
+  if (strcmp(name, "msm_affine_chains") == 0) {
+    if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_affine_chains must be 0 or 1");
+    ctx->msm_affine_chains = (unsigned)value;
+    return TP_OK;
+  }
   return fail(ctx, TP_ERR_INVALID_ARG, "set_option: unknown option");
+}
+
+int tp_ctx_get_stat(tp_ctx* ctx, const char* name, double* out) {
+  if (!ctx || !name || !out) return TP_ERR_INVALID_ARG;
+  const struct { const char* n; double v; } stats[] = {
+      {"msm_entries", ctx->stat_msm_entries}, {"msm_calls", ctx->stat_msm_calls}, {"msm_window_bits", ctx->stat_msm_c},
+      {"msm_windows", ctx->stat_msm_nwin},    {"msm_table_levels", ctx->stat_msm_levels}, {"msm_chunk", ctx->stat_msm_chunk}};
+  for (auto& st : stats)
+    if (strcmp(name, st.n) == 0) {
+      *out = st.v;
+      return TP_OK;
+    }
+  return fail(ctx, TP_ERR_INVALID_ARG, "get_stat: unknown counter");
 }
 
 static int prof_collect(tp_ctx* ctx) {
@@ -177,6 +196,8 @@ int tp_prof_reset(tp_ctx* ctx) {
     ctx->prof_ms[i] = 0;
     ctx->prof_launch[i] = 0;
   }
+  ctx->stat_msm_entries = 0;
+  ctx->stat_msm_calls = 0;
   return TP_OK;
 }
 int tp_prof_get(tp_ctx* ctx, double* ms, uint64_t* launches) {

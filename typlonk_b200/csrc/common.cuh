@@ -26,8 +26,9 @@ struct NttTables {
 struct CosetTable {
   unsigned log_n;
   uint64_t g[4];
-  Fr* lo = nullptr;  // g^i, i < 2^LO
-  Fr* hi = nullptr;  // g^(i << LO)
+  int scaled = 0;    // 1: every entry carries the factor n^-1 (inverse transforms)
+  Fr* lo = nullptr;  // scale * g^i, i < 2^log_n
+  Fr* hi = nullptr;  // unused (kept so that tp_ctx_destroy frees both)
 };
 
 }  // namespace tp
@@ -45,6 +46,9 @@ struct tp_ctx {
   void* allgather_user = nullptr;
   // tunables (tp_ctx_set_option)
   unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
+  unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
+  // work counters (tp_ctx_get_stat)
+  double stat_msm_entries = 0, stat_msm_calls = 0, stat_msm_c = 0, stat_msm_nwin = 0, stat_msm_levels = 0, stat_msm_chunk = 0;
   // profiling
   bool prof = false;
   double prof_ms[TP_PHASE_COUNT] = {0};

@@ -23,8 +23,12 @@
 
 namespace tp {
 
+#ifndef FQINV_UNROLL
+#define FQINV_UNROLL 30   // division steps unrolled per loop trip (instruction footprint vs loop overhead)
+#endif
 #define FQINV_L 13
 #define FQINV_ROUNDS 30   // 900 division steps >= the 879 needed for a 381-bit modulus
+constexpr int kFqinvUnroll = FQINV_UNROLL;
 struct S30 {
   int32_t v[FQINV_L];
 };
@@ -40,7 +44,7 @@ struct S30 {
 TP_HD int32_t fqinv_divsteps_30(int32_t zeta, uint32_t f0, uint32_t g0, int32_t t[4]) {
   uint32_t u = 1, v = 0, q = 0, r = 1;
   uint32_t f = f0, g = g0;
-#pragma unroll
+#pragma unroll kFqinvUnroll
   for (int i = 0; i < 30; i++) {
     uint32_t c1 = (uint32_t)(zeta >> 31);      // all ones if zeta < 0
     uint32_t c2 = (uint32_t)0 - (g & 1);       // all ones if g is odd

@@ -491,6 +491,178 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
   }
 }
 
+// ---- 4c. segmented accumulation in AFFINE coordinates ("chains") -------------------------------
+// Same chunking of the bucket-sorted entry list and same outputs as k_msm_accumulate, but a
+// thread walks AFC_J chunks ("chains") in lockstep and keeps their running sums affine.  Step s
+// adds entry s of every chain: the AFC_J denominators (x_P - x_acc) are multiplied up, inverted
+// ONCE per thread by division steps (fq_inv.cuh: ALU pipe, the multiplier pipe is the bound) and
+// unwound with Montgomery's trick, so an addition costs 5M + 1S (+ 1/AFC_J inversion) = ~1.7e3
+// wide multiplies against 2.7e3 for the XYZZ mixed addition.  The running sums live in global
+// memory (96 B read + written per addition; HBM is ~3 % utilised by this kernel), the prefix
+// products in thread-local memory.  No pairing pass, no sorting by size, no intermediate lists.
+// kinds: 0 chord, 1 tangent, 2 sum is the identity, 3 nothing to add, 4 first point of a run.
+#define AFC_J 16
+#ifndef AFC_MIN_BLOCKS
+#define AFC_MIN_BLOCKS 4
+#endif
+// One shared copy of the multiplier / squarer: the three phases of the kernel (collect, invert,
+// unwind) run in different warps at the same time, so the instruction footprint matters more than a call.
+static __device__ __noinline__ Fq afc_mul(Fq a, Fq b) { return fq_mul(a, b); }
+static __device__ __noinline__ Fq afc_sqr(Fq a) { return fq_sqr(a); }
+
+__device__ __forceinline__ void afc_flush(G1Xyzz* dst, const G1Affine* acc, bool empty) {
+  G1Xyzz o;
+  if (empty) {
+    o = xyzz_identity();
+  } else {
+    o.x = fq_load(&acc->x);
+    o.y = fq_load(&acc->y);
+    o.zz = fq_one();
+    o.zzz = fq_one();
+  }
+  xyzz_store(dst, o);
+}
+
+__global__ void __launch_bounds__(128, AFC_MIN_BLOCKS) k_msm_accumulate_affine(const G1Affine* __restrict__ bases,
+                                                                  const uint2* __restrict__ sorted,
+                                                                  const unsigned* __restrict__ m_ptr, unsigned nchunks,
+                                                                  unsigned chunk, G1Affine* __restrict__ acc_buf,
+                                                                  G1Xyzz* __restrict__ buckets,
+                                                                  unsigned* __restrict__ part_keys,
+                                                                  G1Xyzz* __restrict__ part_pts) {
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned c0 = t * AFC_J;
+  if (c0 >= nchunks) return;
+  const unsigned m_total = *m_ptr;
+  unsigned cur[AFC_J];
+  Fq den[AFC_J];   // denominators on the way in, prefix products after the multiply-up
+  unsigned first_mask = 0xffffffffu, empty_mask = 0xffffffffu;
+#pragma unroll 1
+  for (int j = 0; j < AFC_J; j++) {
+    const unsigned c = c0 + j;
+    const unsigned start = c * chunk;
+    cur[j] = (c < nchunks && start < m_total) ? sorted[start].y : MSM_NONE;
+  }
+#pragma unroll 1
+  for (unsigned s = 0; s < chunk; s++) {
+    unsigned long long kinds = 0;
+    // ---- collect: close finished runs, fetch operands, form the denominators (no products: the
+    //      loads of different chains are independent and overlap) ----
+#pragma unroll 4
+    for (int j = 0; j < AFC_J; j++) {
+      const unsigned c = c0 + j;
+      const unsigned e = c * chunk + s;
+      unsigned kind = 3;
+      Fq d = fq_zero();
+      if (c < nchunks && e < m_total) {
+        const uint2 ent = sorted[e];
+        if (ent.y != cur[j]) {
+          const bool empty = (empty_mask >> j) & 1;
+          if ((first_mask >> j) & 1) {
+            part_keys[2 * c] = cur[j];
+            afc_flush(part_pts + 2 * c, acc_buf + c, empty);
+            first_mask &= ~(1u << j);
+          } else {
+            afc_flush(buckets + cur[j], acc_buf + c, empty);
+          }
+          empty_mask |= 1u << j;
+          cur[j] = ent.y;
+        }
+        const G1Affine* pp = bases + (ent.x & 0x7fffffffu);
+        const Fq px = fq_load(&pp->x);
+        if (fq_is_zero(px) && fq_is_zero(fq_load(&pp->y))) {
+          kind = 3;                                   // the SRS holds the identity here
+        } else if ((empty_mask >> j) & 1) {
+          kind = 4;
+        } else {
+          d = fq_sub(px, fq_load(&acc_buf[c].x));
+          kind = 0;
+          if (fq_is_zero(d)) {                        // same x: doubling or cancellation
+            Fq py = fq_load(&pp->y);
+            if (ent.x >> 31) py = fq_neg(py);
+            const Fq ay = fq_load(&acc_buf[c].y);
+            if (fq_eq(py, ay)) {
+              d = fq_dbl(ay);
+              kind = 1;
+            } else {
+              kind = 2;
+            }
+          }
+        }
+      }
+      den[j] = d;
+      kinds |= (unsigned long long)kind << (4 * j);
+    }
+    // ---- multiply up ----
+    Fq run = fq_one();
+#pragma unroll 1
+    for (int j = 0; j < AFC_J; j++) {
+      const Fq d = den[j];
+      den[j] = run;
+      if (((unsigned)(kinds >> (4 * j)) & 15u) <= 1) run = afc_mul(run, d);
+    }
+    Fq inv = fq_inverse(run);
+    // ---- unwind: one affine addition per chain ----
+#pragma unroll 1
+    for (int j = AFC_J - 1; j >= 0; j--) {
+      const unsigned kind = (unsigned)(kinds >> (4 * j)) & 15u;
+      if (kind == 3) continue;
+      const unsigned c = c0 + j;
+      if (kind == 2) {
+        empty_mask |= 1u << j;
+        continue;
+      }
+      const uint2 ent = sorted[c * chunk + s];
+      G1Affine p = affine_load(bases + (ent.x & 0x7fffffffu));
+      if (ent.x >> 31) p.y = fq_neg(p.y);
+      G1Affine* ap = acc_buf + c;
+      if (kind == 4) {
+        fq_store(&ap->x, p.x);
+        fq_store(&ap->y, p.y);
+        empty_mask &= ~(1u << j);
+        continue;
+      }
+      const G1Affine a = affine_load(ap);
+      Fq d, num;
+      if (kind == 0) {
+        d = fq_sub(p.x, a.x);
+        num = fq_sub(p.y, a.y);
+      } else {
+        d = fq_dbl(a.y);
+        const Fq xx = afc_sqr(a.x);
+        num = fq_add(fq_dbl(xx), xx);
+      }
+      const Fq dinv = afc_mul(inv, den[j]);
+      inv = afc_mul(inv, d);
+      const Fq lam = afc_mul(num, dinv);
+      const Fq x3 = fq_sub(fq_sub(afc_sqr(lam), a.x), p.x);
+      const Fq y3 = fq_sub(afc_mul(lam, fq_sub(a.x, x3)), a.y);
+      fq_store(&ap->x, x3);
+      fq_store(&ap->y, y3);
+    }
+  }
+  // ---- head / tail partials of every chain (same contract as k_msm_accumulate) ----
+#pragma unroll 1
+  for (int j = 0; j < AFC_J; j++) {
+    const unsigned c = c0 + j;
+    if (c >= nchunks) break;
+    if (c * chunk >= m_total) {
+      part_keys[2 * c] = MSM_NONE | MSM_IDENT;
+      part_keys[2 * c + 1] = MSM_NONE | MSM_IDENT;
+      continue;
+    }
+    const bool empty = (empty_mask >> j) & 1;
+    if ((first_mask >> j) & 1) {
+      part_keys[2 * c] = cur[j];
+      afc_flush(part_pts + 2 * c, acc_buf + c, empty);
+      part_keys[2 * c + 1] = cur[j] | MSM_IDENT;
+    } else {
+      part_keys[2 * c + 1] = cur[j];
+      afc_flush(part_pts + 2 * c + 1, acc_buf + c, empty);
+    }
+  }
+}
+
 // ---- 5a. boundary fix-up, common case ---------------------------------------------------------
 // A chunk's head run is complete if it starts in that chunk and the chunk has further runs.  The
 // run that is still open at the end of chunk t (its tail, or its head when the whole chunk is one
@@ -844,17 +1016,41 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
   const size_t m_bound = bound[rounds];
   unsigned chunk = rounds > 0 ? 16 : msm_chunk();
   while (chunk <= max_b && chunk < 1024 && m_bound / (2 * chunk) >= (size_t)ctx->sm_count * 384 * 4) chunk *= 2;
+  // affine chains (4c): AFC_J chunks per thread, so the chunks shrink until the grid fills the GPU
+  const bool chains = rounds == 0 && ctx->msm_affine_chains != 0;
+  if (chains) {
+    static unsigned chunk_env = env_uint("TP_MSM_AFC_CHUNK", 0);
+    const size_t want = (size_t)ctx->sm_count * 128 * AFC_MIN_BLOCKS * AFC_J;
+    size_t ch = m_bound / want;
+    chunk = ch < 16 ? 16u : (ch > 64 ? 64u : (unsigned)ch);
+    if (chunk_env) chunk = chunk_env;
+  }
   const bool pair_path = max_b < PAIR_MAX_SPAN * chunk && !msm_force_levels();
   unsigned nchunks = (unsigned)((m_bound + chunk - 1) / chunk);
   // first half: accumulate's partials; second half: ping-pong space for the merge levels
   TP_TRY(ensure(ctx, ctx->msm_part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
   TP_TRY(ensure(ctx, ctx->msm_part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
+  ctx->stat_msm_entries += (double)m_total;
+  ctx->stat_msm_calls += batch;
+  ctx->stat_msm_c = pl.c;
+  ctx->stat_msm_nwin = pl.nwin;
+  ctx->stat_msm_levels = pl.levels;
+  ctx->stat_msm_chunk = chunk;
   {
     ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
-    k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, scratch, (unsigned)split, final_list, final_m,
-                                                                     nchunks, buckets, (unsigned*)ctx->msm_part_keys.p,
-                                                                     (G1Xyzz*)ctx->msm_part_pts.p, chunk);
-    TP_LAUNCH(ctx, "k_msm_accumulate");
+    if (chains) {
+      TP_TRY(ensure(ctx, ctx->msm_aff_pts, (size_t)nchunks * sizeof(G1Affine)));
+      const unsigned nthreads = (nchunks + AFC_J - 1) / AFC_J;
+      k_msm_accumulate_affine<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(
+          bases, final_list, final_m, nchunks, chunk, (G1Affine*)ctx->msm_aff_pts.p, buckets,
+          (unsigned*)ctx->msm_part_keys.p, (G1Xyzz*)ctx->msm_part_pts.p);
+      TP_LAUNCH(ctx, "k_msm_accumulate_affine");
+    } else {
+      k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, scratch, (unsigned)split, final_list, final_m,
+                                                                       nchunks, buckets, (unsigned*)ctx->msm_part_keys.p,
+                                                                       (G1Xyzz*)ctx->msm_part_pts.p, chunk);
+      TP_LAUNCH(ctx, "k_msm_accumulate");
+    }
   }
   // reduction plan: levels of running sums (segment 8, then 4), then masked sums over what is left
   unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1];

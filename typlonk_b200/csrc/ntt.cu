@@ -6,11 +6,18 @@
 // permutation/src/lib.rs:171,188).  Natural order in, natural order out.
 //
 // Structure: decimation-in-time with the bit-reversal folded into the first pass's
-// gather, ceil(log N / 8) passes over HBM.  Each CTA stages a tile of 2^(k+cw) <= 1024
-// elements (32 KB) in shared memory as two uint4 planes, runs k butterfly stages on
-// 2^cw independent columns, and writes back with 128-byte-contiguous accesses.  Twiddles
-// come from one table omega_N^i, i in [0, N/2]; the inverse transform reads the same table
-// mirrored (omega^-i = -omega^(N/2-i)) so no second table is kept.
+// gather, ceil(log N / 9) passes over HBM.  A CTA owns a tile of 2^(k+cw) <= 2048 elements
+// (2^cw adjacent columns x 2^k rows, rows 2^s0 apart in memory) and runs k butterfly stages on
+// it.  Every thread keeps EIGHT elements in registers and does three stages (a radix-8
+// butterfly: 12 products, 7 twiddle loads) between two exchanges through shared memory; the
+// first round of a pass is loaded straight from global memory and the last one is stored
+// straight back, so a 9-stage pass crosses shared memory twice instead of nine times.  The first
+// round of the first pass has twiddles 1, w4, w8^q only: the products by 1 are skipped (4 instead
+// of 12).  Shared memory holds two uint4 planes with an XOR swizzle (slot i -> i ^ ((i >> 3) & 7))
+// that makes every exchange conflict-free for every round geometry.  Twiddles come from one
+// table omega_N^i, i in [0, N/2]; the inverse transform reads the same table mirrored
+// (omega^-i = -omega^(N/2-i)) so no second table is kept.  Coset scaling uses one table
+// scale * g^i per (size, generator), applied at the first load / last store (one product).
 #include "common.cuh"
 
 namespace tp {
@@ -25,12 +32,12 @@ tph::HFr omega_for_log(unsigned log_n) {
 }
 
 // out[i] = base^(i * stride_exp) ... generic power table: out[i] = base^i for i < count.
-__global__ void k_pow_table(Fr* out, Fr base, size_t count) {
+__global__ void k_pow_table(Fr* out, Fr base, size_t count, Fr scale) {
   const int PER = 16;
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t start = t * PER;
   if (start >= count) return;
-  Fr cur = fr_pow_u64(base, (unsigned long long)start);
+  Fr cur = fr_mul(scale, fr_pow_u64(base, (unsigned long long)start));
   for (int i = 0; i < PER && start + i < count; i++) {
     fr_store(out + start + i, cur);
     cur = fr_mul(cur, base);
@@ -46,74 +53,36 @@ struct NttPassArgs {
   unsigned L, s0, k, cw;
   int first, inverse, last;
   Fr ninv;
-  const Fr* coset_lo;  // nullptr when no coset
-  const Fr* coset_hi;
+  const Fr* coset;  // scale * g^i (forward: applied at the first load; inverse: at the last store, n^-1 folded in)
 };
 
-#define NTT_COSET_LO_BITS 12
-
-__device__ __forceinline__ Fr coset_power(const NttPassArgs& a, unsigned idx) {
-  Fr lo = fr_load(a.coset_lo + (idx & ((1u << NTT_COSET_LO_BITS) - 1)));
-  Fr hi = fr_load(a.coset_hi + (idx >> NTT_COSET_LO_BITS));
-  return fr_mul(lo, hi);
-}
-
-__global__ void __launch_bounds__(512) k_ntt_pass(NttPassArgs a) {
-  __shared__ uint4 s_lo[1024];
-  __shared__ uint4 s_hi[1024];
-  const unsigned T = 1u << (a.k + a.cw);
-  const unsigned cmask = (1u << a.cw) - 1;
-  const unsigned K = 1u << a.k;
-  unsigned base = 0, lo_grp = 0;
-  if (!a.first) {
-    unsigned hi_idx = blockIdx.x >> (a.s0 - a.cw);
-    lo_grp = blockIdx.x & ((1u << (a.s0 - a.cw)) - 1);
-    base = (hi_idx << (a.s0 + a.k)) + (lo_grp << a.cw);
-  }
-  // ---- load -----------------------------------------------------------------------
+// ---- small transforms (log N < 3) and reference structure: one stage per shared-memory round ----
+__global__ void __launch_bounds__(512) k_ntt_small(NttPassArgs a) {
+  __shared__ uint4 s_lo[8];
+  __shared__ uint4 s_hi[8];
+  const unsigned T = 1u << a.k;
   for (unsigned e = threadIdx.x; e < T; e += blockDim.x) {
-    unsigned l = e & cmask, m = e >> a.cw;
-    unsigned src, spos;
-    if (a.first) {
-      src = (m << (a.L - a.k)) + (blockIdx.x << a.cw) + l;
-      spos = (l << a.k) + bitrev(m, a.k);
-    } else {
-      src = base + (m << a.s0) + l;
-      spos = (l << a.k) + m;
-    }
-    Fr x = fr_load(a.in + src);
-    if (a.first && a.coset_lo && !a.inverse) x = fr_mul(x, coset_power(a, src));
+    Fr x = fr_load(a.in + e);
+    if (a.coset && !a.inverse) x = fr_mul(x, fr_load(a.coset + e));
+    unsigned spos = bitrev(e, a.k);
     s_lo[spos] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     s_hi[spos] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
   }
   __syncthreads();
-  // ---- butterflies ------------------------------------------------------------------
   const unsigned half_n = 1u << (a.L - 1);
   for (unsigned t = 1; t <= a.k; t++) {
     for (unsigned b = threadIdx.x; b < (T >> 1); b += blockDim.x) {
-      unsigned col = b >> (a.k - 1);
-      unsigned q = b & ((K >> 1) - 1);
-      unsigned j = q & ((1u << (t - 1)) - 1);
-      unsigned blk = q >> (t - 1);
-      unsigned p0 = (col << a.k) + (blk << t) + j;
-      unsigned p1 = p0 + (1u << (t - 1));
-      unsigned s = a.s0 + t;
-      unsigned lo_val = a.first ? 0u : ((lo_grp << a.cw) + col);
-      unsigned idx = ((j << a.s0) + lo_val) << (a.L - s);
+      unsigned j = b & ((1u << (t - 1)) - 1);
+      unsigned p0 = ((b >> (t - 1)) << t) + j, p1 = p0 + (1u << (t - 1));
+      unsigned idx = j << (a.L - t);
       Fr w = fr_load(a.tw + (a.inverse ? (half_n - idx) : idx));
       uint4 ul = s_lo[p0], uh = s_hi[p0], vl = s_lo[p1], vh = s_hi[p1];
       Fr u, v;
       u.v[0] = ul.x; u.v[1] = ul.y; u.v[2] = ul.z; u.v[3] = ul.w; u.v[4] = uh.x; u.v[5] = uh.y; u.v[6] = uh.z; u.v[7] = uh.w;
       v.v[0] = vl.x; v.v[1] = vl.y; v.v[2] = vl.z; v.v[3] = vl.w; v.v[4] = vh.x; v.v[5] = vh.y; v.v[6] = vh.z; v.v[7] = vh.w;
       Fr wv = fr_mul(w, v);
-      Fr r0, r1;
-      if (a.inverse) {
-        r0 = fr_sub(u, wv);
-        r1 = fr_add(u, wv);
-      } else {
-        r0 = fr_add(u, wv);
-        r1 = fr_sub(u, wv);
-      }
+      Fr r0 = a.inverse ? fr_sub(u, wv) : fr_add(u, wv);
+      Fr r1 = a.inverse ? fr_add(u, wv) : fr_sub(u, wv);
       s_lo[p0] = make_uint4(r0.v[0], r0.v[1], r0.v[2], r0.v[3]);
       s_hi[p0] = make_uint4(r0.v[4], r0.v[5], r0.v[6], r0.v[7]);
       s_lo[p1] = make_uint4(r1.v[0], r1.v[1], r1.v[2], r1.v[3]);
@@ -121,30 +90,134 @@ __global__ void __launch_bounds__(512) k_ntt_pass(NttPassArgs a) {
     }
     __syncthreads();
   }
-  // ---- store ------------------------------------------------------------------------
   for (unsigned e = threadIdx.x; e < T; e += blockDim.x) {
-    unsigned dst, spos;
-    if (a.first) {
-      unsigned l = e >> a.k, pos = e & (K - 1);
-      unsigned bidx = bitrev((blockIdx.x << a.cw) + l, a.L - a.k);
-      dst = (bidx << a.k) + pos;
-      spos = e;
-    } else {
-      unsigned l = e & cmask, m = e >> a.cw;
-      dst = base + (m << a.s0) + l;
-      spos = (l << a.k) + m;
+    uint4 xl = s_lo[e], xh = s_hi[e];
+    Fr x;
+    x.v[0] = xl.x; x.v[1] = xl.y; x.v[2] = xl.z; x.v[3] = xl.w; x.v[4] = xh.x; x.v[5] = xh.y; x.v[6] = xh.z; x.v[7] = xh.w;
+    if (a.inverse) x = fr_mul(x, a.coset ? fr_load(a.coset + e) : a.ninv);
+    fr_store(a.out + e, x);
+  }
+}
+
+// ---- register radix-8 passes ---------------------------------------------------------------
+// Tile coordinates: row m in [0, 2^k) (the dimension the butterflies run along), column l in
+// [0, 2^cw).  Slot of (m, l) in shared memory = swizzle((m << cw) | l).  In a round with field
+// base f a thread owns the eight rows m = (m_hi << (f + 3)) | (e << f) | m_lo, e = 0..7, of one
+// column; stage bit beta = f + d pairs e with e ^ (1 << d).  Global stage s = s0 + beta + 1 uses
+// twiddle omega_N^idx, idx = (((m mod 2^beta) << s0) + lo_val) << (L - s), lo_val = position of
+// the column inside its 2^s0 block (0 in the first pass).
+__device__ __forceinline__ unsigned ntt_swz(unsigned i) { return i ^ ((i >> 3) & 7u); }
+
+template <int D0, int NST, bool TRIV>
+__device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw, unsigned A, unsigned sh, unsigned L,
+                                          bool inverse, unsigned half_n) {
+#pragma unroll
+  for (int d = D0; d < D0 + NST; d++) {
+    const unsigned base_idx = A << (sh - d);
+#pragma unroll
+    for (int e0 = 0; e0 < 8; e0++) {
+      if (e0 & (1 << d)) continue;
+      const int e1 = e0 | (1 << d);
+      const unsigned q = e0 & ((1 << d) - 1);
+      if (TRIV && q == 0) {  // A == 0 and q == 0: twiddle 1 in both directions
+        const Fr u = x[e0], v = x[e1];
+        x[e0] = fr_add(u, v);
+        x[e1] = fr_sub(u, v);
+      } else {
+        const unsigned idx = base_idx + (q << (L - d - 1));
+        const Fr w = fr_load(tw + (inverse ? half_n - idx : idx));
+        const Fr t = fr_mul(w, x[e1]);
+        const Fr u = x[e0];
+        const Fr p = fr_add(u, t), m = fr_sub(u, t);
+        x[e0] = inverse ? m : p;   // mirrored table entry is -omega^-idx
+        x[e1] = inverse ? p : m;
+      }
     }
-    uint4 xl = s_lo[spos], xh = s_hi[spos];
-    if (a.last && (a.inverse)) {
-      Fr x;
-      x.v[0] = xl.x; x.v[1] = xl.y; x.v[2] = xl.z; x.v[3] = xl.w; x.v[4] = xh.x; x.v[5] = xh.y; x.v[6] = xh.z; x.v[7] = xh.w;
-      x = fr_mul(x, a.ninv);
-      if (a.coset_lo) x = fr_mul(x, coset_power(a, dst));
-      fr_store(a.out + dst, x);
-    } else {
-      uint4* o = reinterpret_cast<uint4*>(a.out + dst);
-      o[0] = xl;
-      o[1] = xh;
+  }
+}
+
+#define NTT_MAX_TILE_LOG 11
+#define NTT_SMEM_BYTES ((2u << NTT_MAX_TILE_LOG) * 16u)
+
+__global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
+  extern __shared__ uint4 ntt_sh[];
+  const unsigned T = 1u << (a.k + a.cw);
+  uint4* s_lo = ntt_sh;
+  uint4* s_hi = ntt_sh + T;
+  const unsigned tau = threadIdx.x;
+  const unsigned l = tau & ((1u << a.cw) - 1), rho = tau >> a.cw;
+  const unsigned half_n = 1u << (a.L - 1);
+  unsigned base = 0, lo_val = 0;
+  if (!a.first) {
+    const unsigned hi_idx = blockIdx.x >> (a.s0 - a.cw);
+    const unsigned lo_grp = blockIdx.x & ((1u << (a.s0 - a.cw)) - 1);
+    base = (hi_idx << (a.s0 + a.k)) + (lo_grp << a.cw) + l;
+    lo_val = (lo_grp << a.cw) + l;
+  } else {
+    base = (blockIdx.x << a.cw) + l;
+  }
+  Fr x[8];
+  // ---- first round: operands straight from global memory (field base 0: m = rho * 8 + e) ----
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const unsigned m = (rho << 3) | e;
+    const unsigned g = a.first ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
+    x[e] = fr_load(a.in + g);
+    if (a.first && a.coset && !a.inverse) x[e] = fr_mul(x[e], fr_load(a.coset + g));
+  }
+  if (a.first)
+    ntt_round<0, 3, true>(x, a.tw, 0u, a.L - 1, a.L, a.inverse, half_n);
+  else
+    ntt_round<0, 3, false>(x, a.tw, lo_val, a.L - a.s0 - 1, a.L, a.inverse, half_n);
+  // ---- further rounds: exchange through shared memory ----
+  const unsigned rem = a.k % 3;
+  unsigned f_prev = 0;
+  for (unsigned f = 3; f < a.k; f += 3) {
+    const bool tail = f + 3 > a.k;          // fewer than three stages left: field sits at the top
+    const unsigned fb = tail ? a.k - 3 : f;
+    {
+      const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
+      const unsigned i0 = (((m_hi << (f_prev + 3)) | m_lo) << a.cw) | l;
+      if (f_prev != 0) __syncthreads();     // the previous exchange has been read by everyone
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const unsigned p = ntt_swz(i0 | ((unsigned)e << (f_prev + a.cw)));
+        s_lo[p] = make_uint4(x[e].v[0], x[e].v[1], x[e].v[2], x[e].v[3]);
+        s_hi[p] = make_uint4(x[e].v[4], x[e].v[5], x[e].v[6], x[e].v[7]);
+      }
+      __syncthreads();
+    }
+    const unsigned m_lo = rho & ((1u << fb) - 1), m_hi = rho >> fb;
+    const unsigned i0 = (((m_hi << (fb + 3)) | m_lo) << a.cw) | l;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const unsigned p = ntt_swz(i0 | ((unsigned)e << (fb + a.cw)));
+      const uint4 lo = s_lo[p], hi = s_hi[p];
+      x[e].v[0] = lo.x; x[e].v[1] = lo.y; x[e].v[2] = lo.z; x[e].v[3] = lo.w;
+      x[e].v[4] = hi.x; x[e].v[5] = hi.y; x[e].v[6] = hi.z; x[e].v[7] = hi.w;
+    }
+    const unsigned A = (m_lo << a.s0) + lo_val;
+    const unsigned sh = a.L - a.s0 - fb - 1;
+    if (!tail)
+      ntt_round<0, 3, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+    else if (rem == 1)
+      ntt_round<2, 1, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+    else
+      ntt_round<1, 2, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+    f_prev = fb;
+  }
+  // ---- store from the last round's field ----
+  {
+    const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
+    const unsigned m0 = (m_hi << (f_prev + 3)) | m_lo;
+    const unsigned obase = a.first ? (bitrev(base, a.L - a.k) << a.k) : base;
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const unsigned m = m0 | ((unsigned)e << f_prev);
+      const unsigned g = a.first ? obase + m : obase + (m << a.s0);
+      Fr y = x[e];
+      if (a.last && a.inverse) y = fr_mul(y, a.coset ? fr_load(a.coset + g) : a.ninv);
+      fr_store(a.out + g, y);
     }
   }
 }
@@ -157,7 +230,7 @@ int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw) {
     TP_CUDA_OK(ctx, cudaMalloc(&t.tw, count * sizeof(Fr)));
     Fr w = to_dev(omega_for_log(log_n));
     size_t threads = (count + 15) / 16;
-    k_pow_table<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(t.tw, w, count);
+    k_pow_table<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(t.tw, w, count, to_dev(tph::HFr::one()));
     TP_LAUNCH(ctx, "k_pow_table");
     it = ctx->ntt_tables.emplace(log_n, t).first;
   }
@@ -165,30 +238,48 @@ int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw) {
   return TP_OK;
 }
 
-static int get_coset_table(tp_ctx* ctx, unsigned log_n, const tph::HFr& g, const Fr** lo, const Fr** hi) {
+// scale * g^i for i < 2^log_n (scale = n^-1 for the inverse transform's output table)
+static int get_coset_table(tp_ctx* ctx, unsigned log_n, const tph::HFr& g, bool scaled, const Fr** out) {
   for (auto& c : ctx->coset_tables) {
-    if (c.log_n == log_n && memcmp(c.g, g.v, 32) == 0) {
-      *lo = c.lo;
-      *hi = c.hi;
+    if (c.log_n == log_n && c.scaled == (scaled ? 1 : 0) && memcmp(c.g, g.v, 32) == 0) {
+      *out = c.lo;
       return TP_OK;
     }
   }
   CosetTable c;
   c.log_n = log_n;
+  c.scaled = scaled ? 1 : 0;
   memcpy(c.g, g.v, 32);
-  size_t nlo = (size_t)1 << NTT_COSET_LO_BITS;
-  size_t nhi = (((size_t)1 << log_n) >> NTT_COSET_LO_BITS) + 1;
-  TP_CUDA_OK(ctx, cudaMalloc(&c.lo, nlo * sizeof(Fr)));
-  TP_CUDA_OK(ctx, cudaMalloc(&c.hi, nhi * sizeof(Fr)));
-  k_pow_table<<<(unsigned)((nlo / 16 + 127) / 128), 128, 0, ctx->stream>>>(c.lo, to_dev(g), nlo);
-  TP_LAUNCH(ctx, "k_pow_table");
-  tph::HFr gh = g.pow_u64((uint64_t)1 << NTT_COSET_LO_BITS);
-  k_pow_table<<<(unsigned)(((nhi + 15) / 16 + 127) / 128), 128, 0, ctx->stream>>>(c.hi, to_dev(gh), nhi);
+  size_t n = (size_t)1 << log_n;
+  TP_CUDA_OK(ctx, cudaMalloc(&c.lo, n * sizeof(Fr)));
+  tph::HFr scale = scaled ? tph::HFr::from_u64((uint64_t)n).inv() : tph::HFr::one();
+  k_pow_table<<<(unsigned)(((n + 15) / 16 + 127) / 128), 128, 0, ctx->stream>>>(c.lo, to_dev(g), n, to_dev(scale));
   TP_LAUNCH(ctx, "k_pow_table");
   ctx->coset_tables.push_back(c);
-  *lo = c.lo;
-  *hi = c.hi;
+  *out = c.lo;
   return TP_OK;
+}
+
+// Pass plan: as few passes as the 2048-element tile allows (k <= 9 with four columns per tile),
+// every pass at least three stages, and as many of them as possible a multiple of three.  The
+// first pass has four columns per tile (its rows are far apart: 128-byte runs); later passes with
+// fewer stages widen the tile instead (2^(11-k) adjacent columns), so every CTA has 256 threads.
+static int ntt_plan(unsigned log_n, unsigned* ks) {
+  if (log_n <= NTT_MAX_TILE_LOG) {
+    ks[0] = log_n;
+    return 1;
+  }
+  const unsigned kmax = NTT_MAX_TILE_LOG - 2;
+  int npass = (int)((log_n + kmax - 1) / kmax);
+  unsigned left = log_n;
+  for (int i = 0; i < npass; i++) {
+    unsigned passes_after = (unsigned)(npass - 1 - i);
+    unsigned k = left < kmax ? left : kmax;
+    if (left - k < 3 * passes_after) k = left - 3 * passes_after;  // leave >= 3 stages for each later pass
+    ks[i] = k;
+    left -= k;
+  }
+  return npass;
 }
 
 int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset) {
@@ -200,55 +291,58 @@ int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, co
   ProfScope prof(ctx, TP_PHASE_NTT);
   const Fr* tw;
   TP_TRY(ntt_get_twiddles(ctx, log_n, &tw));
-  const Fr *clo = nullptr, *chi = nullptr;
+  const Fr* ctab = nullptr;
   if (coset) {
     tph::HFr g;
     memcpy(g.v, coset, 32);
     if (inverse) g = g.inv();
-    TP_TRY(get_coset_table(ctx, log_n, g, &clo, &chi));
+    TP_TRY(get_coset_table(ctx, log_n, g, inverse, &ctab));
   }
   size_t n = (size_t)1 << log_n;
-  // pass plan
-  unsigned ks[8];
-  int npass;
-  if (log_n <= 10) {
-    npass = 1;
-    ks[0] = log_n;
-  } else {
-    npass = (log_n + 7) / 8;
-    unsigned q = log_n / npass, r = log_n % npass;
-    for (int i = 0; i < npass; i++) ks[i] = q + (i < (int)r ? 1 : 0);
+  tph::HFr ninv = tph::HFr::from_u64((uint64_t)n).inv();
+  NttPassArgs a;
+  a.tw = tw;
+  a.L = log_n;
+  a.inverse = inverse ? 1 : 0;
+  a.ninv = to_dev(ninv);
+  a.coset = ctab;
+  if (log_n < 3) {
+    a.in = in;
+    a.out = out;
+    a.s0 = 0;
+    a.k = log_n;
+    a.cw = 0;
+    a.first = a.last = 1;
+    k_ntt_small<<<1, 32, 0, ctx->stream>>>(a);
+    TP_LAUNCH(ctx, "k_ntt_small");
+    return TP_OK;
   }
+  static bool smem_attr = false;
+  if (!smem_attr) {
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+    smem_attr = true;
+  }
+  unsigned ks[8];
+  const int npass = ntt_plan(log_n, ks);
   Fr* scratch = nullptr;
   if (npass > 1 && in == out) {
     TP_TRY(ensure(ctx, ctx->ntt_scratch, n * sizeof(Fr)));
     scratch = (Fr*)ctx->ntt_scratch.p;
   }
-  tph::HFr ninv = tph::HFr::from_u64((uint64_t)n).inv();
   const Fr* src = in;
   unsigned s0 = 0;
   for (int p = 0; p < npass; p++) {
-    NttPassArgs a;
     a.in = src;
     a.out = (p == 0 && scratch) ? scratch : out;
-    a.tw = tw;
-    a.L = log_n;
     a.s0 = s0;
     a.k = ks[p];
+    a.cw = npass == 1 ? 0 : (p == 0 ? 2 : NTT_MAX_TILE_LOG - a.k);
     a.first = (p == 0);
-    a.inverse = inverse ? 1 : 0;
     a.last = (p == npass - 1);
-    a.ninv = to_dev(ninv);
-    a.coset_lo = clo;
-    a.coset_hi = chi;
-    unsigned cw = (npass == 1) ? 0 : 2;
-    if (a.first && log_n - a.k < cw) cw = log_n - a.k;
-    a.cw = cw;
-    unsigned T = 1u << (a.k + a.cw);
-    unsigned threads = T / 2 < 32 ? 32 : T / 2;
-    unsigned grid = (unsigned)(n >> (a.k + a.cw));
-    k_ntt_pass<<<grid, threads, 0, ctx->stream>>>(a);
-    TP_LAUNCH(ctx, "k_ntt_pass");
+    const unsigned T = 1u << (a.k + a.cw);
+    const unsigned grid = (unsigned)(n >> (a.k + a.cw));
+    k_ntt_r8<<<grid, T / 8, 2 * T * sizeof(uint4), ctx->stream>>>(a);
+    TP_LAUNCH(ctx, "k_ntt_r8");
     src = a.out;
     s0 += a.k;
   }

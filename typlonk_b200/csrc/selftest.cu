@@ -171,22 +171,28 @@ __global__ void k_imad_bench(unsigned* out, unsigned a, unsigned b, int iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
 }
+// Wide multiply-add in the form the Montgomery multipliers use: a carry chain of
+// mad.lo.cc / madc.hi.cc pairs (ptxas fuses each pair into one IMAD.WIDE.U32.X).  The multiplier
+// of every row comes out of the previous row, so nothing is loop-invariant (an earlier version
+// with constant operands was folded into 64-bit additions and over-reported by 2x).
 __global__ void k_imad_wide_bench(unsigned long long* out, unsigned a, unsigned b, int iters) {
-  unsigned long long x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
-                     x7 = x0 + 7;
+  unsigned r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
   unsigned m = a + threadIdx.x;
+  const unsigned b0 = b, b1 = b + 2, b2 = b + 4, b3 = b + 6;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
+    for (int u = 0; u < 16; u++) {
       asm volatile(
-          "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\tmad.wide.u32 %2, %8, %9, %2;\n\t"
-          "mad.wide.u32 %3, %8, %9, %3;\n\tmad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-          "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-          : "+l"(x0), "+l"(x1), "+l"(x2), "+l"(x3), "+l"(x4), "+l"(x5), "+l"(x6), "+l"(x7)
-          : "r"(m), "r"(b));
+          "mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+          "madc.lo.cc.u32 %2, %8, %10, %2;\n\tmadc.hi.cc.u32 %3, %8, %10, %3;\n\t"
+          "madc.lo.cc.u32 %4, %8, %11, %4;\n\tmadc.hi.cc.u32 %5, %8, %11, %5;\n\t"
+          "madc.lo.cc.u32 %6, %8, %12, %6;\n\tmadc.hi.u32 %7, %8, %12, %7;"
+          : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7)
+          : "r"(m), "r"(b0), "r"(b1), "r"(b2), "r"(b3));
+      m = r7;
     }
   }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 ^ x1 ^ x2 ^ x3 ^ x4 ^ x5 ^ x6 ^ x7;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((unsigned long long)(r0 ^ r2 ^ r4 ^ r6) << 32) | (r1 ^ r3 ^ r5 ^ r7);
 }
 
 int measure_imad_dev(tp_ctx* ctx, double* imad, double* wide) {

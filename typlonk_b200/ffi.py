@@ -27,7 +27,7 @@ SYMBOLS = [
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
-    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option",
+    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option", "tp_ctx_get_stat",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -135,8 +135,15 @@ class Context:
         return v.value
 
     def set_option(self, name, value):
-        """Tunables of the library ("msm_affine_rounds": 0..8); results do not depend on them."""
+        """Tunables of the library ("msm_affine_chains": 0/1, "msm_affine_rounds": 0..8); results do not
+        depend on them."""
         self._check(lib().tp_ctx_set_option(self._h, name.encode(), C.c_long(int(value))))
+
+    def get_stat(self, name) -> float:
+        """Work counters / last MSM plan ("msm_entries", "msm_window_bits", ...), see the header."""
+        v = C.c_double()
+        self._check(lib().tp_ctx_get_stat(self._h, name.encode(), C.byref(v)))
+        return v.value
 
     def set_shard(self, rank, world, allgather=None):
         """allgather(send: bytes) -> bytes of world * len(send) (e.g. via torch.distributed)."""
