@@ -8,7 +8,8 @@ One JSON line on stdout (rank 0).  A "step" is one complete proof (13 G1 MSMs, 1
 4n-NTTs, grand product, quotient, 6 openings).  `value` = prove ms with the witness resident
 in HBM; `e2e` = the same through tp_prove with pinned HOST buffers (H2D of the 3 witness columns
 + public inputs and D2H of the proof inside the timed region).  N > 1: one process per GPU, every
-MSM sharded by point range, partial points all-gathered with NCCL (strong scaling).
+MSM sharded by point range, partial points all-gathered with NCCL, and the quotient sharded by
+coset of the 4n domain with one NCCL broadcast per coset (strong scaling).
 
 `--impl reference` times the CPU oracle port (oracle/c, all host threads) on a bounded sample.
 """
@@ -158,6 +159,14 @@ def main():
             return recv.cpu().numpy().tobytes()
         ctx.set_shard(rank, world, allgather)
 
+        from typlonk_b200.ffi import DeviceView
+
+        def bcast(ptr: int, nbytes: int, root: int):
+            # aliases the library's device buffer; NCCL orders itself after the current (= ctx) stream
+            dist.broadcast(torch.as_tensor(DeviceView(ptr, nbytes), device=dev), src=root)
+        if os.environ.get("TP_NO_COSET_SHARD", "0") != "1":
+            ctx.set_broadcast(bcast)
+
     log_n = args.log_n
     n = 1 << log_n
     t0 = time.time()
@@ -264,7 +273,7 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32-limb Montgomery Fr/Fq (integer)", "data": "synthetic",
         "config": {"workload": "mulchain_prove_n=2^%d" % log_n, "gates": n - 3, "srs_points": n + 3,
-                   "parallelism": "msm-shard x%d" % world, "l2": l2_flush, "setup_s": round(setup_s, 1)},
+                   "parallelism": "msm point-range shard + quotient coset shard x%d" % world if world > 1 else "single GPU", "l2": l2_flush, "setup_s": round(setup_s, 1)},
         "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 4 * 32 * n,
                 "d2h_bytes_per_step": 1472},
         "gpu_launches": launches,

@@ -67,6 +67,14 @@ int tp_sync(tp_ctx* ctx);
  * NCCL (torch.distributed.all_gather over NVLink).  rank/world = 0/1 disables sharding. */
 typedef int (*tp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
 int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user);
+/* Optional second collective: broadcast `bytes` of DEVICE memory at `dev_ptr` from rank `root` to every
+ * rank, ordered with respect to the ctx stream (the host language wires it to ncclBroadcast, e.g.
+ * torch.distributed.broadcast on a tensor aliasing dev_ptr).  With it, tp_prove shards the quotient
+ * (plonk/src/proof.rs:292-375) over ranks by coset of the 4n evaluation domain: a rank evaluates the
+ * numerator on its cosets only and the four n-coefficient interpolants (n x 32 B each) are exchanged.
+ * Without it every rank evaluates all four cosets itself.  Call after tp_ctx_set_shard. */
+typedef int (*tp_bcast_dev_fn)(void* user, void* dev_ptr, size_t bytes, int root);
+int tp_ctx_set_broadcast(tp_ctx* ctx, tp_bcast_dev_fn bcast, void* user);
 
 /* Tunables of the MSM behind tp_commit / tp_open / tp_prove.  Results are identical for every
  * setting (the affine sum of a bucket is unique).

@@ -143,6 +143,13 @@ int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather
   return TP_OK;
 }
 
+int tp_ctx_set_broadcast(tp_ctx* ctx, tp_bcast_dev_fn bcast, void* user) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  ctx->bcast = bcast;
+  ctx->bcast_user = user;
+  return TP_OK;
+}
+
 int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
   if (!ctx || !name) return TP_ERR_INVALID_ARG;
   if (strcmp(name, "msm_affine_rounds") == 0) {
@@ -379,9 +386,15 @@ static int circuit_alloc(tp_ctx* ctx, tp_circuit* c) {
   return TP_OK;
 }
 
+// coefficients (n) -> evaluations on coset k of the 4n domain, out4 coset-major (slot k * n + i)
+static int to_coset(tp_ctx* ctx, tp_circuit* c, const Fr* coef, Fr* out4, unsigned k) {
+  if (k == 0) return ntt_dev(ctx, coef, out4, c->log_n, false, nullptr);
+  HFr g = omega_for_log(c->log_n + 2).pow_u64(k);
+  return ntt_dev(ctx, coef, out4 + (size_t)k * c->n, c->log_n, false, g.v);
+}
 static int to_4n(tp_ctx* ctx, tp_circuit* c, const Fr* coef, Fr* out4) {
-  TP_TRY(pad_copy_dev(ctx, coef, c->n, out4, 4 * c->n));
-  return ntt_dev(ctx, out4, out4, c->log_n + 2, false, nullptr);
+  for (unsigned k = 0; k < 4; k++) TP_TRY(to_coset(ctx, c, coef, out4, k));
+  return TP_OK;
 }
 
 // derived data once sel_coef, id, sig_eval, k are in place
@@ -535,10 +548,19 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   HFr alpha, zeta;
   tph::challenges2({com[0], com[1], com[2], com[3]}, &alpha, &zeta);
 
-  // quotient (proof.rs:292-375) on the 4n domain
+  // quotient (proof.rs:292-375) on the 4n domain, coset by coset: five coset NTTs, the pointwise
+  // numerator, one inverse coset NTT each.  Sharded over ranks by coset when the caller wired a
+  // device broadcast (tp_ctx_set_broadcast); every rank then rebuilds t from the four interpolants.
   {
     const Fr* src[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->pi_coef};
-    for (int i = 0; i < 5; i++) TP_TRY(to_4n(ctx, c, src[i], c->buf4[i]));
+    const bool shard = ctx->world > 1 && ctx->bcast != nullptr;
+    auto owner = [&](unsigned k) { return !shard ? ctx->rank : (ctx->world < 4 ? (int)(k % ctx->world) : (int)(k * (ctx->world / 4))); };
+    unsigned mine[4];
+    int nmine = 0;
+    for (unsigned k = 0; k < 4; k++)
+      if (owner(k) == ctx->rank) mine[nmine++] = k;
+    for (int m = 0; m < nmine; m++)
+      for (int i = 0; i < 5; i++) TP_TRY(to_coset(ctx, c, src[i], c->buf4[i], mine[m]));
     QuotientArgs qa;
     for (int i = 0; i < 5; i++) qa.sel4[i] = c->sel4[i];
     for (int i = 0; i < 3; i++) {
@@ -555,9 +577,22 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
     qa.gamma = to_dev(gamma);
     qa.out = c->buf4[5];
     qa.n = n;
-    TP_TRY(quotient_numerator_dev(ctx, qa));
-    TP_TRY(ntt_dev(ctx, c->buf4[5], c->buf4[5], c->log_n + 2, true, nullptr));
-    TP_TRY(divide_by_vanishing_dev(ctx, c->buf4[5], n, c->t));
+    TP_TRY(quotient_numerator_dev(ctx, qa, mine, nmine));
+    for (int m = 0; m < nmine; m++) {
+      Fr* e = c->buf4[5] + (size_t)mine[m] * n;
+      if (mine[m] == 0) {
+        TP_TRY(ntt_dev(ctx, e, e, c->log_n, true, nullptr));
+      } else {
+        HFr g = omega_for_log(c->log_n + 2).pow_u64(mine[m]);
+        TP_TRY(ntt_dev(ctx, e, e, c->log_n, true, g.v));
+      }
+    }
+    if (shard) {
+      for (unsigned k = 0; k < 4; k++)
+        if (ctx->bcast(ctx->bcast_user, c->buf4[5] + (size_t)k * n, n * sizeof(Fr), owner(k)) != 0)
+          return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a quotient coset failed");
+    }
+    TP_TRY(quotient_combine_dev(ctx, c->buf4[5], n, qa.tw4, c->t));
   }
 
   // openings (proof.rs:147-163)

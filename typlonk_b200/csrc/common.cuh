@@ -44,6 +44,8 @@ struct tp_ctx {
   int rank = 0, world = 1;
   tp_allgather_fn allgather = nullptr;
   void* allgather_user = nullptr;
+  tp_bcast_dev_fn bcast = nullptr;   // device-buffer broadcast (quotient cosets); null = every rank computes all four
+  void* bcast_user = nullptr;
   // tunables (tp_ctx_set_option)
   unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
@@ -188,7 +190,7 @@ int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* con
 int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out /* len, may be null */, tph::HFr* y);
 int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
                    bool* ok);
-struct QuotientArgs {
+struct QuotientArgs {   // every 4n-sized array is coset-major: slot k * n + i <-> omega_4n^(4i + k)
   const Fr* sel4[5];   // 4n evaluations
   const Fr* sig4[3];
   const Fr* adv4[3];
@@ -201,9 +203,9 @@ struct QuotientArgs {
   Fr* out;             // 4n numerator evaluations
   size_t n;
 };
-int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a);
-// t[k] = sum_{m>=1} c[k + m n] for k < 3n from the 4n numerator coefficients
-int divide_by_vanishing_dev(tp_ctx* ctx, const Fr* c4, size_t n, Fr* t /* 3n */);
+int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a, const unsigned* cosets, int ncosets);
+// t = floor(N / (X^n - 1)) (3n coefficients) from the four per-coset interpolants of N (coset-major, 4n)
+int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, const Fr* tw4, Fr* t /* 3n */);
 int l0_evals_4n_dev(tp_ctx* ctx, const Fr* tw4, size_t n, Fr* out /* 4n */);
 struct LinTerm {
   const Fr* p;

@@ -285,8 +285,12 @@ int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const ad
 }
 
 // =====================================================================================
-// quotient numerator on the 4n domain
+// quotient numerator on the 4n domain, one coset of H at a time
 // =====================================================================================
+// The 4n-point domain <omega_4n> is the union of the four cosets omega_4n^k H, k = 0..3.  Every
+// 4n-sized table here is COSET-MAJOR: entry k * n + i belongs to the point omega_4n^(4i + k).  A
+// coset is a self-contained unit of work (five size-n coset NTTs, this kernel, one inverse coset
+// NTT), which is what lets the quotient be sharded over GPUs by coset (api.cu).
 struct QuotKernelArgs {
   const Fr* sel4[5];
   const Fr* sig4[3];
@@ -299,39 +303,42 @@ struct QuotKernelArgs {
   Fr bk[3];  // beta * k_i
   Fr* out;
   size_t n;
+  unsigned cosets[4];  // blockIdx.y selects the coset
 };
 __global__ void __launch_bounds__(EW_THREADS) k_quotient_numerator(QuotKernelArgs q) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n4 = q.n * 4;
-  if (i >= n4) return;
-  size_t half = q.n * 2;
-  Fr x = i < half ? fr_load(q.tw4 + i) : fr_neg(fr_load(q.tw4 + (i - half)));
-  Fr a = fr_load(q.adv4[0] + i), b = fr_load(q.adv4[1] + i), c = fr_load(q.adv4[2] + i);
-  Fr z = fr_load(q.z4 + i);
-  size_t iw = i + 4 < n4 ? i + 4 : i + 4 - n4;
-  Fr zw = fr_load(q.z4 + iw);
+  if (i >= q.n) return;
+  const unsigned k = q.cosets[blockIdx.y];
+  const size_t half = q.n * 2;
+  const size_t i4 = 4 * i + k;               // exponent of omega_4n at this point
+  const size_t o = (size_t)k * q.n + i;      // coset-major slot
+  Fr x = i4 < half ? fr_load(q.tw4 + i4) : fr_neg(fr_load(q.tw4 + (i4 - half)));
+  Fr a = fr_load(q.adv4[0] + o), b = fr_load(q.adv4[1] + o), c = fr_load(q.adv4[2] + o);
+  Fr z = fr_load(q.z4 + o);
+  Fr zw = fr_load(q.z4 + (size_t)k * q.n + (i + 1 < q.n ? i + 1 : 0));   // z(omega x): next point of the same coset
   // gate line (proof.rs:317-320)
-  Fr acc = fr_mul(fr_load(q.sel4[0] + i), a);
-  acc = fr_add(acc, fr_mul(fr_load(q.sel4[1] + i), b));
-  acc = fr_sub(acc, fr_mul(fr_load(q.sel4[2] + i), c));
-  acc = fr_add(acc, fr_mul(fr_mul(fr_load(q.sel4[3] + i), a), b));
-  acc = fr_add(acc, fr_load(q.sel4[4] + i));
-  acc = fr_add(acc, fr_load(q.pi4 + i));
+  Fr acc = fr_mul(fr_load(q.sel4[0] + o), a);
+  acc = fr_add(acc, fr_mul(fr_load(q.sel4[1] + o), b));
+  acc = fr_sub(acc, fr_mul(fr_load(q.sel4[2] + o), c));
+  acc = fr_add(acc, fr_mul(fr_mul(fr_load(q.sel4[3] + o), a), b));
+  acc = fr_add(acc, fr_load(q.sel4[4] + o));
+  acc = fr_add(acc, fr_load(q.pi4 + o));
   // permutation lines (proof.rs:323-354)
   Fr ag = fr_add(a, q.gamma), bg = fr_add(b, q.gamma), cg = fr_add(c, q.gamma);
   Fr l2 = fr_mul(fr_add(ag, fr_mul(q.bk[0], x)), fr_add(bg, fr_mul(q.bk[1], x)));
   l2 = fr_mul(l2, fr_add(cg, fr_mul(q.bk[2], x)));
   l2 = fr_mul(l2, z);
-  Fr l3 = fr_mul(fr_add(ag, fr_mul(q.beta, fr_load(q.sig4[0] + i))), fr_add(bg, fr_mul(q.beta, fr_load(q.sig4[1] + i))));
-  l3 = fr_mul(l3, fr_add(cg, fr_mul(q.beta, fr_load(q.sig4[2] + i))));
+  Fr l3 = fr_mul(fr_add(ag, fr_mul(q.beta, fr_load(q.sig4[0] + o))), fr_add(bg, fr_mul(q.beta, fr_load(q.sig4[1] + o))));
+  l3 = fr_mul(l3, fr_add(cg, fr_mul(q.beta, fr_load(q.sig4[2] + o))));
   l3 = fr_mul(l3, zw);
   acc = fr_add(acc, fr_mul(q.alpha, fr_sub(l2, l3)));
   // L0 line (proof.rs:355-360)
-  Fr l4 = fr_mul(fr_sub(z, fr_one()), fr_load(q.l0_4 + i));
+  Fr l4 = fr_mul(fr_sub(z, fr_one()), fr_load(q.l0_4 + o));
   acc = fr_add(acc, fr_mul(q.alpha2, l4));
-  fr_store(q.out + i, acc);
+  fr_store(q.out + o, acc);
 }
-int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a) {
+int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a, const unsigned* cosets, int ncosets) {
+  if (ncosets <= 0) return TP_OK;
   ProfScope prof(ctx, TP_PHASE_QUOTIENT);
   QuotKernelArgs q;
   for (int i = 0; i < 5; i++) q.sel4[i] = a.sel4[i];
@@ -351,29 +358,46 @@ int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a) {
   for (int i = 0; i < 3; i++) q.bk[i] = to_dev(be * to_host(a.k[i]));
   q.out = a.out;
   q.n = a.n;
-  k_quotient_numerator<<<ew_grid(a.n * 4), EW_THREADS, 0, ctx->stream>>>(q);
+  for (int i = 0; i < 4; i++) q.cosets[i] = cosets[i < ncosets ? i : 0];
+  k_quotient_numerator<<<dim3(ew_grid(a.n), (unsigned)ncosets), EW_THREADS, 0, ctx->stream>>>(q);
   TP_LAUNCH(ctx, "k_quotient_numerator");
   return TP_OK;
 }
 
-__global__ void k_divide_vanishing(const Fr* c4, size_t n, Fr* t) {
-  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  Fr t2 = fr_load(c4 + k + 3 * n);
-  Fr t1 = fr_add(fr_load(c4 + k + 2 * n), t2);
-  Fr t0 = fr_add(fr_load(c4 + k + n), t1);
-  fr_store(t + k + 2 * n, t2);
-  fr_store(t + k + n, t1);
-  fr_store(t + k, t0);
+// Numerator coefficients from its four per-coset interpolants, and the floor division by X^n - 1
+// (proof.rs:373, 504-508; the remainder is discarded as the reference does).  Write
+// N(X) = sum_j X^(jn) N_j(X), deg N_j < n.  On coset k, x^n = iota^k (iota = omega_4n^n, iota^2 = -1),
+// so the interpolant of coset k is C_k = sum_j iota^(kj) N_j and N_j = 1/4 sum_k iota^(-kj) C_k.
+// Then t_2 = N_3, t_1 = N_2 + t_2, t_0 = N_1 + t_1.
+__global__ void k_quotient_combine(const Fr* __restrict__ c4, size_t n, Fr iota_inv, Fr quarter, Fr* __restrict__ t) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Fr c0 = fr_load(c4 + i), c1 = fr_load(c4 + n + i), c2 = fr_load(c4 + 2 * n + i), c3 = fr_load(c4 + 3 * n + i);
+  const Fr e = fr_add(c0, c2), f = fr_sub(c0, c2), g = fr_add(c1, c3);
+  const Fr h = fr_mul(iota_inv, fr_sub(c1, c3));
+  const Fr n1 = fr_mul(quarter, fr_add(f, h));
+  const Fr n2 = fr_mul(quarter, fr_sub(e, g));
+  const Fr n3 = fr_mul(quarter, fr_sub(f, h));
+  const Fr t1 = fr_add(n2, n3);
+  fr_store(t + 2 * n + i, n3);
+  fr_store(t + n + i, t1);
+  fr_store(t + i, fr_add(n1, t1));
 }
-int divide_by_vanishing_dev(tp_ctx* ctx, const Fr* c4, size_t n, Fr* t) {
+int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, const Fr* tw4, Fr* t) {
   ProfScope prof(ctx, TP_PHASE_QUOTIENT);
-  k_divide_vanishing<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(c4, n, t);
-  TP_LAUNCH(ctx, "k_divide_vanishing");
+  // iota^-1 = -iota is read back once per call from the twiddle table (tw4[n]); quarter = 4^-1
+  Fr iota;
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, tw4 + n, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(&iota, ctx->pinned, sizeof(Fr));
+  tph::HFr iota_inv = to_host(iota).neg();
+  tph::HFr quarter = tph::HFr::from_u64(4).inv();
+  k_quotient_combine<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(c4, n, to_dev(iota_inv), to_dev(quarter), t);
+  TP_LAUNCH(ctx, "k_quotient_combine");
   return TP_OK;
 }
 
-// L0(x) = (x^n - 1) / (n (x - 1)) on the 4n domain; chunked batch inversion (8 per thread).
+// L0(x) = (x^n - 1) / (n (x - 1)) on the 4n domain (coset-major output); chunked batch inversion (8 per thread).
 #define L0_CH 8
 __global__ void k_l0_evals(const Fr* tw4, size_t n, Fr ninv, Fr* out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -407,7 +431,7 @@ __global__ void k_l0_evals(const Fr* tw4, size_t n, Fr ninv, Fr* out) {
       Fr xn = m == 1 ? iota : (m == 2 ? fr_neg(one) : fr_neg(iota));
       r = fr_mul(fr_mul(fr_sub(xn, one), ninv), di);
     }
-    fr_store(out + idx, r);
+    fr_store(out + (size_t)m * n + (idx >> 2), r);
   }
 }
 int l0_evals_4n_dev(tp_ctx* ctx, const Fr* tw4, size_t n, Fr* out) {

@@ -22,7 +22,7 @@ ERRORS = {
 
 # every symbol include/typlonk_b200.h declares
 SYMBOLS = [
-    "tp_ctx_create", "tp_ctx_destroy", "tp_last_error", "tp_sync", "tp_ctx_set_shard",
+    "tp_ctx_create", "tp_ctx_destroy", "tp_last_error", "tp_sync", "tp_ctx_set_shard", "tp_ctx_set_broadcast",
     "tp_prof_enable", "tp_prof_reset", "tp_prof_get", "tp_launch_count",
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
@@ -31,6 +31,15 @@ SYMBOLS = [
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+BCAST_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+
+
+class DeviceView:
+    """`nbytes` of device memory at `ptr` as a __cuda_array_interface__ object (torch.as_tensor aliases it)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
 
 
 class TyplonkError(RuntimeError):
@@ -164,6 +173,26 @@ class Context:
         else:
             self._cb = None
             self._check(lib().tp_ctx_set_shard(self._h, 0, 1, C.cast(None, ALLGATHER_FN), None))
+
+    def set_broadcast(self, bcast=None):
+        """bcast(dev_ptr: int, nbytes: int, root: int): in-place broadcast of device memory from rank
+        `root`, ordered after the work already queued on the ctx stream (e.g. torch.distributed.broadcast
+        on torch.as_tensor(DeviceView(dev_ptr, nbytes), device=...)).  Enables coset sharding of the quotient."""
+        if bcast is None:
+            self._bcb = None
+            self._check(lib().tp_ctx_set_broadcast(self._h, C.cast(None, BCAST_DEV_FN), None))
+            return
+
+        def cb(_user, ptr, nbytes, root):
+            try:
+                bcast(int(ptr), int(nbytes), int(root))
+                return 0
+            except Exception:  # noqa: BLE001 -- must not unwind through C
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._bcb = BCAST_DEV_FN(cb)
+        self._check(lib().tp_ctx_set_broadcast(self._h, self._bcb, None))
 
     # ---- SRS ---------------------------------------------------------------------------
     def srs_from_secret(self, tau_mont: bytes, gates: int):
