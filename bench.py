@@ -223,6 +223,7 @@ def main():
     ms_total, proof = timed(step_resident, args.steps)
     launches = ctx.launch_count() - l0
     prof = ctx.prof_get()
+    msms, entries = ctx.get_stat("msm_calls"), ctx.get_stat("msm_entries")   # of the K timed steps only
     ctx.prof_enable(False)
     for _ in range(1):
         step_e2e()
@@ -237,8 +238,6 @@ def main():
     # MSM in its batch (13 MSMs per proof go out as batches of 3 + 1 + 9 = 3 launches).
     acc_ms, acc_launches = prof["msm_accum"]
     acc_launch_ms = acc_ms / max(acc_launches, 1)
-    msms = ctx.get_stat("msm_calls")
-    entries = ctx.get_stat("msm_entries")
     pts_per_launch = (n / world) * msms / max(acc_launches, 1)
     achieved = (128.0 * pts_per_launch) / (acc_launch_ms * 1e-3) / 1e9 if acc_ms > 0 else None
     affine = bool(int(os.environ.get("TP_MSM_AFFINE", "0")))
