@@ -38,14 +38,46 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: an NVML polling thread (20 ms period;
+    the main thread sits in ctypes / CUDA calls that release the GIL), nvidia-smi -lms as the fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = threading.Event()
+        self.thread = None
         self.proc = None
         self.lines = []
 
     def start(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {N.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                    N.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                    N.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                    N.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
+
+            def poll():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for bit, name in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:  # noqa: BLE001
+                        pass
+                    self.stop_flag.wait(0.02)
+            self.thread = threading.Thread(target=poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.thread = None
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
@@ -63,6 +95,12 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.proc is None and self.thread is not None:      # NVML path
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.proc.terminate()
@@ -71,7 +109,6 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
@@ -81,12 +118,12 @@ class ClockSampler:
                 mx = float(parts[1])
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
+            for nm, v in zip(self.NAMES, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 def run_reference(args):

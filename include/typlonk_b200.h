@@ -72,7 +72,9 @@ int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather
  * torch.distributed.broadcast on a tensor aliasing dev_ptr).  With it, tp_prove shards the quotient
  * (plonk/src/proof.rs:292-375) over ranks by coset of the 4n evaluation domain: a rank evaluates the
  * numerator on its cosets only and the four n-coefficient interpolants (n x 32 B each) are exchanged.
- * Without it every rank evaluates all four cosets itself.  Call after tp_ctx_set_shard. */
+ * Without it every rank evaluates all four cosets itself.  tp_prove (host buffers) also uses it to upload the
+ * witness in row slices: each rank copies 1/world of every column over PCIe and the slices travel over
+ * NVLink.  Call after tp_ctx_set_shard. */
 typedef int (*tp_bcast_dev_fn)(void* user, void* dev_ptr, size_t bytes, int root);
 int tp_ctx_set_broadcast(tp_ctx* ctx, tp_bcast_dev_fn bcast, void* user);
 

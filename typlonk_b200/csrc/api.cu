@@ -518,8 +518,11 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   const size_t n = c->n;
   const tp_srs* srs = c->srs;
   // witness + public-input polynomials (proof.rs:50, 105-106)
-  for (int i = 0; i < 3; i++) TP_TRY(ntt_dev(ctx, c->adv_eval[i], c->adv_coef[i], c->log_n, true, nullptr));
-  TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
+  {
+    const Fr* ins[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
+    Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
+    TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, 4, c->log_n, true));
+  }
   // round 1 commitments (proof.rs:107-110)
   uint8_t com[4][TP_G1_BYTES];
   {
@@ -559,8 +562,22 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
     int nmine = 0;
     for (unsigned k = 0; k < 4; k++)
       if (owner(k) == ctx->rank) mine[nmine++] = k;
-    for (int m = 0; m < nmine; m++)
-      for (int i = 0; i < 5; i++) TP_TRY(to_coset(ctx, c, src[i], c->buf4[i], mine[m]));
+    HFr gens[4];
+    for (unsigned k = 0; k < 4; k++) gens[k] = omega_for_log(c->log_n + 2).pow_u64(k);
+    {
+      const Fr* ins[20];
+      Fr* outs[20];
+      const uint64_t* cos[20];
+      int cnt = 0;
+      for (int m = 0; m < nmine; m++)
+        for (int i = 0; i < 5; i++) {
+          ins[cnt] = src[i];
+          outs[cnt] = c->buf4[i] + (size_t)mine[m] * n;
+          cos[cnt] = mine[m] == 0 ? nullptr : gens[mine[m]].v;
+          cnt++;
+        }
+      TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, cnt, c->log_n, false));
+    }
     QuotientArgs qa;
     for (int i = 0; i < 5; i++) qa.sel4[i] = c->sel4[i];
     for (int i = 0; i < 3; i++) {
@@ -578,34 +595,47 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
     qa.out = c->buf4[5];
     qa.n = n;
     TP_TRY(quotient_numerator_dev(ctx, qa, mine, nmine));
-    for (int m = 0; m < nmine; m++) {
-      Fr* e = c->buf4[5] + (size_t)mine[m] * n;
-      if (mine[m] == 0) {
-        TP_TRY(ntt_dev(ctx, e, e, c->log_n, true, nullptr));
-      } else {
-        HFr g = omega_for_log(c->log_n + 2).pow_u64(mine[m]);
-        TP_TRY(ntt_dev(ctx, e, e, c->log_n, true, g.v));
+    {
+      // out of place into the (now dead) coset slots of buf4[0]; the interpolants are gathered there
+      const Fr* ins[4];
+      Fr* outs[4];
+      const uint64_t* cos[4];
+      for (int m = 0; m < nmine; m++) {
+        ins[m] = c->buf4[5] + (size_t)mine[m] * n;
+        outs[m] = c->buf4[0] + (size_t)mine[m] * n;
+        cos[m] = mine[m] == 0 ? nullptr : gens[mine[m]].v;
       }
+      TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, nmine, c->log_n, true));
     }
     if (shard) {
       for (unsigned k = 0; k < 4; k++)
-        if (ctx->bcast(ctx->bcast_user, c->buf4[5] + (size_t)k * n, n * sizeof(Fr), owner(k)) != 0)
+        if (ctx->bcast(ctx->bcast_user, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)) != 0)
           return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a quotient coset failed");
     }
-    TP_TRY(quotient_combine_dev(ctx, c->buf4[5], n, qa.tw4, c->t));
+    TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, qa.tw4, c->t));
   }
 
   // openings (proof.rs:147-163)
   uint8_t wit[6][TP_G1_BYTES];
   HFr ev[5];
   HFr omega = omega_for_log(c->log_n);
-  const Fr* polys[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->z_coef};
-  HFr points[5] = {zeta, zeta, zeta, zeta, zeta * omega};
-  for (int i = 0; i < 5; i++) TP_TRY(poly_open_dev(ctx, polys[i], n, to_dev(points[i]), c->q[i], &ev[i]));
-  // linearisation (proof.rs:376-439)
+  // ... together with the three plain evaluations the linearisation needs (proof.rs:416,429): eight
+  // recurrences of length n in one batched scan, one read-back.
   HFr sig_bar[2], pi_bar;
-  for (int i = 0; i < 2; i++) TP_TRY(poly_open_dev(ctx, c->sig_coef[i], n, to_dev(zeta), nullptr, &sig_bar[i]));
-  TP_TRY(poly_open_dev(ctx, c->pi_coef, n, to_dev(zeta), nullptr, &pi_bar));
+  {
+    const Fr* polys[8] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->z_coef,
+                          c->sig_coef[0], c->sig_coef[1], c->pi_coef};
+    Fr* quots[8] = {c->q[0], c->q[1], c->q[2], c->q[3], c->q[4], nullptr, nullptr, nullptr};
+    Fr points[8];
+    for (int i = 0; i < 8; i++) points[i] = to_dev(i == 4 ? zeta * omega : zeta);
+    HFr ys[8];
+    TP_TRY(poly_open_batch_dev(ctx, polys, n, points, quots, 8, ys));
+    for (int i = 0; i < 5; i++) ev[i] = ys[i];
+    sig_bar[0] = ys[5];
+    sig_bar[1] = ys[6];
+    pi_bar = ys[7];
+  }
+  // linearisation (proof.rs:376-439)
   HFr a = ev[0], b = ev[1], cc = ev[2], zw = ev[4];
   HFr l2 = HFr::one();
   for (int i = 0; i < 3; i++) l2 = l2 * (ev[i] + c->k[i] * beta * zeta + gamma);
@@ -677,8 +707,25 @@ int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const 
              uint8_t* proof_out, size_t proof_cap) {
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
   size_t bytes = c->n * sizeof(Fr);
-  for (int i = 0; i < 3; i++) TP_TRY(h2d(ctx, c->adv_eval[i], advice[i], bytes));
-  TP_TRY(h2d(ctx, c->pi_eval, public_inputs, bytes));
+  const uint64_t* cols[4] = {advice[0], advice[1], advice[2], public_inputs};
+  Fr* dst[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
+  const size_t world = (size_t)ctx->world;
+  if (ctx->world > 1 && ctx->bcast && c->n % world == 0 && c->n / world >= 64) {
+    // Sharded upload: every rank holds the same host columns, so each one sends only its row slice over PCIe
+    // and the slices are exchanged over NVLink (one device broadcast per rank), then scattered into the columns.
+    const size_t rows = c->n / world, slice = rows * sizeof(Fr);
+    uint8_t* stage = (uint8_t*)c->buf4[0];                       // [rank][column][rows], 4n Fr in total
+    for (int j = 0; j < 4; j++)
+      TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * 4 + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
+    for (int r = 0; r < ctx->world; r++)
+      if (ctx->bcast(ctx->bcast_user, stage + (size_t)r * 4 * slice, 4 * slice, r) != 0)
+        return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a witness slice failed");
+    for (int j = 0; j < 4; j++)
+      TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, 4 * slice, slice, world,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+  } else {
+    for (int j = 0; j < 4; j++) TP_TRY(h2d(ctx, dst[j], cols[j], bytes));
+  }
   return prove_resident(ctx, c, proof_out);
 }
 

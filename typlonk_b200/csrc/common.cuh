@@ -176,6 +176,8 @@ struct ProfScope {
 // ---- device-level entry points (each implemented in its own .cu) -----------------------
 // ntt.cu
 int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset);
+int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64_t* const* coset, int count,
+                  unsigned log_n, bool inverse);
 int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw);
 // msm.cu : result as host Jacobian (this rank's shard only when sharded = false, else combined)
 int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]);
@@ -188,6 +190,8 @@ int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* con
                            size_t n, const Fr& beta, const Fr& gamma, Fr* out /* n+1 */);
 // q[k-1] = p[k] + z q[k]; writes q (len-1 coeffs, then a zero at [len-1]) and returns y = p(z)
 int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out /* len, may be null */, tph::HFr* y);
+// up to 8 polynomials of the same length at once (own point each; q_out[b] may be null = evaluation only)
+int poly_open_batch_dev(tp_ctx* ctx, const Fr* const* p, size_t len, const Fr* z, Fr* const* q_out, int batch, tph::HFr* y);
 int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
                    bool* ok);
 struct QuotientArgs {   // every 4n-sized array is coset-major: slot k * n + i <-> omega_4n^(4i + k)

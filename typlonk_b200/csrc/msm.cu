@@ -441,7 +441,7 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) k_aff_round(const G1Affine* __
 // ---- 4b. segmented accumulation --------------------------------------------------------------
 // part_keys[2t], part_keys[2t+1]: keys of the head / tail partial of chunk t (MSM_NONE if absent)
 #ifndef TP_ACC_MIN_BLOCKS
-#define TP_ACC_MIN_BLOCKS 1
+#define TP_ACC_MIN_BLOCKS 3   // 162 registers, 3 warps per scheduler: FMA-heavy pipe 80 % -> 87 % busy (profiles N)
 #endif
 __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
                                                         const G1Affine* __restrict__ scratch, unsigned split,
@@ -1016,6 +1016,17 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
   const size_t m_bound = bound[rounds];
   unsigned chunk = rounds > 0 ? 16 : msm_chunk();
   while (chunk <= max_b && chunk < 1024 && m_bound / (2 * chunk) >= (size_t)ctx->sm_count * 384 * 4) chunk *= 2;
+  // Whole waves: with 3 x 128 resident threads per SM a grid of 1.1 waves costs two; when only a few waves are
+  // in play, resize the chunks so that the thread count is a multiple of what the GPU holds at once.
+  if (rounds == 0 && !env_uint("TP_MSM_CHUNK", 0)) {
+    const double resident = (double)ctx->sm_count * 128 * TP_ACC_MIN_BLOCKS;
+    const double waves = (double)m_bound / (resident * chunk);
+    if (waves < 8.0) {
+      const double w = waves < 1.0 ? 1.0 : (double)(unsigned)(waves + 0.5);
+      size_t ch = (size_t)((double)m_bound / (w * resident)) + 1;
+      chunk = ch < 32 ? 32u : (ch > 1024 ? 1024u : (unsigned)ch);
+    }
+  }
   // affine chains (4c): AFC_J chunks per thread, so the chunks shrink until the grid fills the GPU
   const bool chains = rounds == 0 && ctx->msm_affine_chains != 0;
   if (chains) {

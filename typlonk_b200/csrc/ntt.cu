@@ -46,14 +46,17 @@ __global__ void k_pow_table(Fr* out, Fr base, size_t count, Fr scale) {
 
 __device__ __forceinline__ unsigned bitrev(unsigned x, unsigned bits) { return bits == 0 ? 0u : (__brev(x) >> (32 - bits)); }
 
+// Up to NTT_MAX_BATCH transforms of the same size and direction run in one launch (blockIdx.y):
+// the prover's 20 coset NTTs of a proof fill whole waves of CTAs instead of one and a half each.
+#define NTT_MAX_BATCH 20
 struct NttPassArgs {
-  const Fr* in;
-  Fr* out;
+  const Fr* in[NTT_MAX_BATCH];
+  Fr* out[NTT_MAX_BATCH];
+  const Fr* coset[NTT_MAX_BATCH];  // scale * g^i (forward: applied at the first load; inverse: at the last store, n^-1 folded in)
   const Fr* tw;
   unsigned L, s0, k, cw;
   int first, inverse, last;
   Fr ninv;
-  const Fr* coset;  // scale * g^i (forward: applied at the first load; inverse: at the last store, n^-1 folded in)
 };
 
 // ---- small transforms (log N < 3) and reference structure: one stage per shared-memory round ----
@@ -61,9 +64,12 @@ __global__ void __launch_bounds__(512) k_ntt_small(NttPassArgs a) {
   __shared__ uint4 s_lo[8];
   __shared__ uint4 s_hi[8];
   const unsigned T = 1u << a.k;
+  const Fr* in = a.in[blockIdx.y];   // may alias out (later passes run in place)
+  Fr* out = a.out[blockIdx.y];
+  const Fr* coset = a.coset[blockIdx.y];
   for (unsigned e = threadIdx.x; e < T; e += blockDim.x) {
-    Fr x = fr_load(a.in + e);
-    if (a.coset && !a.inverse) x = fr_mul(x, fr_load(a.coset + e));
+    Fr x = fr_load(in + e);
+    if (coset && !a.inverse) x = fr_mul(x, fr_load(coset + e));
     unsigned spos = bitrev(e, a.k);
     s_lo[spos] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
     s_hi[spos] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
@@ -94,8 +100,8 @@ __global__ void __launch_bounds__(512) k_ntt_small(NttPassArgs a) {
     uint4 xl = s_lo[e], xh = s_hi[e];
     Fr x;
     x.v[0] = xl.x; x.v[1] = xl.y; x.v[2] = xl.z; x.v[3] = xl.w; x.v[4] = xh.x; x.v[5] = xh.y; x.v[6] = xh.z; x.v[7] = xh.w;
-    if (a.inverse) x = fr_mul(x, a.coset ? fr_load(a.coset + e) : a.ninv);
-    fr_store(a.out + e, x);
+    if (a.inverse) x = fr_mul(x, coset ? fr_load(coset + e) : a.ninv);
+    fr_store(out + e, x);
   }
 }
 
@@ -147,6 +153,9 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
   const unsigned tau = threadIdx.x;
   const unsigned l = tau & ((1u << a.cw) - 1), rho = tau >> a.cw;
   const unsigned half_n = 1u << (a.L - 1);
+  const Fr* in = a.in[blockIdx.y];   // may alias out (later passes run in place)
+  Fr* out = a.out[blockIdx.y];
+  const Fr* coset = a.coset[blockIdx.y];
   unsigned base = 0, lo_val = 0;
   if (!a.first) {
     const unsigned hi_idx = blockIdx.x >> (a.s0 - a.cw);
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
   for (int e = 0; e < 8; e++) {
     const unsigned m = (rho << 3) | e;
     const unsigned g = a.first ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
-    x[e] = fr_load(a.in + g);
-    if (a.first && a.coset && !a.inverse) x[e] = fr_mul(x[e], fr_load(a.coset + g));
+    x[e] = fr_load(in + g);
+    if (a.first && coset && !a.inverse) x[e] = fr_mul(x[e], fr_load(coset + g));
   }
   if (a.first)
     ntt_round<0, 3, true>(x, a.tw, 0u, a.L - 1, a.L, a.inverse, half_n);
@@ -216,8 +225,8 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
       const unsigned m = m0 | ((unsigned)e << f_prev);
       const unsigned g = a.first ? obase + m : obase + (m << a.s0);
       Fr y = x[e];
-      if (a.last && a.inverse) y = fr_mul(y, a.coset ? fr_load(a.coset + g) : a.ninv);
-      fr_store(a.out + g, y);
+      if (a.last && a.inverse) y = fr_mul(y, coset ? fr_load(coset + g) : a.ninv);
+      fr_store(out + g, y);
     }
   }
 }
@@ -282,22 +291,25 @@ static int ntt_plan(unsigned log_n, unsigned* ks) {
   return npass;
 }
 
-int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset) {
+// `count` transforms of size 2^log_n in one set of launches; coset[i] (Montgomery generator, may be
+// null) selects the coset of entry i.  in[i] == out[i] is allowed (a scratch copy takes the first pass).
+int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64_t* const* coset, int count,
+                  unsigned log_n, bool inverse) {
+  if (count <= 0) return TP_OK;
+  if (count > NTT_MAX_BATCH) {
+    TP_TRY(ntt_batch_dev(ctx, in, out, coset, NTT_MAX_BATCH, log_n, inverse));
+    return ntt_batch_dev(ctx, in + NTT_MAX_BATCH, out + NTT_MAX_BATCH, coset ? coset + NTT_MAX_BATCH : nullptr,
+                         count - NTT_MAX_BATCH, log_n, inverse);
+  }
   if (log_n == 0) {
-    if (in != out) TP_CUDA_OK(ctx, cudaMemcpyAsync(out, in, sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+    for (int i = 0; i < count; i++)
+      if (in[i] != out[i]) TP_CUDA_OK(ctx, cudaMemcpyAsync(out[i], in[i], sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
     return TP_OK;
   }
   if (log_n > 28) return fail(ctx, TP_ERR_INVALID_ARG, "ntt: log_n > 28");
   ProfScope prof(ctx, TP_PHASE_NTT);
   const Fr* tw;
   TP_TRY(ntt_get_twiddles(ctx, log_n, &tw));
-  const Fr* ctab = nullptr;
-  if (coset) {
-    tph::HFr g;
-    memcpy(g.v, coset, 32);
-    if (inverse) g = g.inv();
-    TP_TRY(get_coset_table(ctx, log_n, g, inverse, &ctab));
-  }
   size_t n = (size_t)1 << log_n;
   tph::HFr ninv = tph::HFr::from_u64((uint64_t)n).inv();
   NttPassArgs a;
@@ -305,15 +317,26 @@ int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, co
   a.L = log_n;
   a.inverse = inverse ? 1 : 0;
   a.ninv = to_dev(ninv);
-  a.coset = ctab;
+  for (int i = 0; i < NTT_MAX_BATCH; i++) {
+    const int s = i < count ? i : 0;
+    a.coset[i] = nullptr;
+    if (coset && coset[s]) {
+      tph::HFr g;
+      memcpy(g.v, coset[s], 32);
+      if (inverse) g = g.inv();
+      TP_TRY(get_coset_table(ctx, log_n, g, inverse, &a.coset[i]));
+    }
+  }
   if (log_n < 3) {
-    a.in = in;
-    a.out = out;
+    for (int i = 0; i < NTT_MAX_BATCH; i++) {
+      a.in[i] = in[i < count ? i : 0];
+      a.out[i] = out[i < count ? i : 0];
+    }
     a.s0 = 0;
     a.k = log_n;
     a.cw = 0;
     a.first = a.last = 1;
-    k_ntt_small<<<1, 32, 0, ctx->stream>>>(a);
+    k_ntt_small<<<dim3(1, (unsigned)count), 32, 0, ctx->stream>>>(a);
     TP_LAUNCH(ctx, "k_ntt_small");
     return TP_OK;
   }
@@ -324,16 +347,30 @@ int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, co
   }
   unsigned ks[8];
   const int npass = ntt_plan(log_n, ks);
+  // the first pass of a multi-pass transform is out of place: in-place entries go through scratch
   Fr* scratch = nullptr;
-  if (npass > 1 && in == out) {
-    TP_TRY(ensure(ctx, ctx->ntt_scratch, n * sizeof(Fr)));
-    scratch = (Fr*)ctx->ntt_scratch.p;
+  if (npass > 1) {
+    int inplace = 0;
+    for (int i = 0; i < count; i++) inplace += in[i] == out[i];
+    if (inplace) {
+      TP_TRY(ensure(ctx, ctx->ntt_scratch, (size_t)inplace * n * sizeof(Fr)));
+      scratch = (Fr*)ctx->ntt_scratch.p;
+    }
   }
-  const Fr* src = in;
+  const Fr* src[NTT_MAX_BATCH];
+  for (int i = 0; i < count; i++) src[i] = in[i];
   unsigned s0 = 0;
   for (int p = 0; p < npass; p++) {
-    a.in = src;
-    a.out = (p == 0 && scratch) ? scratch : out;
+    Fr* sc = scratch;
+    for (int i = 0; i < NTT_MAX_BATCH; i++) {
+      const int s = i < count ? i : 0;
+      a.in[i] = src[s];
+      a.out[i] = out[s];
+      if (i < count && p == 0 && npass > 1 && in[i] == out[i]) {
+        a.out[i] = sc;
+        sc += n;
+      }
+    }
     a.s0 = s0;
     a.k = ks[p];
     a.cw = npass == 1 ? 0 : (p == 0 ? 2 : NTT_MAX_TILE_LOG - a.k);
@@ -341,12 +378,19 @@ int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, co
     a.last = (p == npass - 1);
     const unsigned T = 1u << (a.k + a.cw);
     const unsigned grid = (unsigned)(n >> (a.k + a.cw));
-    k_ntt_r8<<<grid, T / 8, 2 * T * sizeof(uint4), ctx->stream>>>(a);
+    k_ntt_r8<<<dim3(grid, (unsigned)count), T / 8, 2 * T * sizeof(uint4), ctx->stream>>>(a);
     TP_LAUNCH(ctx, "k_ntt_r8");
-    src = a.out;
+    for (int i = 0; i < count; i++) src[i] = a.out[i];
     s0 += a.k;
   }
   return TP_OK;
+}
+
+int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset) {
+  const Fr* ins[1] = {in};
+  Fr* outs[1] = {out};
+  const uint64_t* cos[1] = {coset};
+  return ntt_batch_dev(ctx, ins, outs, cos, 1, log_n, inverse);
 }
 
 }  // namespace tp

@@ -173,75 +173,120 @@ int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* con
 // =====================================================================================
 #define LIN_CH 32
 #define LIN_BASE 64
+#define LIN_MAX_BATCH 8
+// Up to LIN_MAX_BATCH independent recurrences of the same length run side by side (blockIdx.y):
+// the scans are latency-bound chains of small launches, so the prover's eight evaluations /
+// openings at one Fiat-Shamir point cost what one costs.
+struct LinBatch {
+  const Fr* p[LIN_MAX_BATCH];
+  Fr* q[LIN_MAX_BATCH];       // may be null: evaluation only
+  Fr z[LIN_MAX_BATCH];
+};
 
 // h[t] = sum_{k in chunk t} p[k] z^(k - lo)
-__global__ void k_linrec_reduce(const Fr* p, size_t n, Fr z, Fr* h) {
+__global__ void k_linrec_reduce(LinBatch a, size_t n, Fr* h, size_t h_stride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = t * LIN_CH;
   if (lo >= n) return;
+  const Fr* p = a.p[blockIdx.y];
+  const Fr z = a.z[blockIdx.y];
   size_t hi = lo + LIN_CH < n ? lo + LIN_CH : n;
   Fr acc = fr_zero();
   for (size_t k = hi; k-- > lo;) acc = fr_add(fr_load(p + k), fr_mul(z, acc));
-  fr_store(h + t, acc);
+  fr_store(h + blockIdx.y * h_stride + t, acc);
 }
 // q[k-1] = p[k] + z q[k] inside chunk t, starting from carry = qprime[t] (q at index hi-1)
-__global__ void k_linrec_apply(const Fr* p, size_t n, Fr z, const Fr* qprime, Fr* q) {
+__global__ void k_linrec_apply(LinBatch a, size_t n, const Fr* qprime, size_t qp_stride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = t * LIN_CH;
   if (lo >= n) return;
+  Fr* q = a.q[blockIdx.y];
+  if (!q) return;
+  const Fr* p = a.p[blockIdx.y];
+  const Fr z = a.z[blockIdx.y];
   size_t hi = lo + LIN_CH < n ? lo + LIN_CH : n;
-  Fr acc = fr_load(qprime + t);
+  Fr acc = fr_load(qprime + blockIdx.y * qp_stride + t);
   if (hi == n) fr_store(q + n - 1, fr_zero());
   for (size_t k = hi; k-- > lo;) {
     acc = fr_add(fr_load(p + k), fr_mul(z, acc));
     if (k >= 1) fr_store(q + k - 1, acc);
   }
 }
-// serial base case: q (may alias nothing) and y = p(z) -> yout
-__global__ void k_linrec_serial(const Fr* p, size_t n, Fr z, Fr* q, Fr* yout) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// serial base case (one thread per recurrence): q and y = p(z) -> yout[b]
+__global__ void k_linrec_serial(LinBatch a, size_t n, Fr* yout) {
+  const unsigned b = threadIdx.x;
+  if (b >= LIN_MAX_BATCH) return;
+  const Fr* p = a.p[b];
+  if (!p) return;
+  Fr* q = a.q[b];
+  const Fr z = a.z[b];
   Fr acc = fr_zero();
   if (q) fr_store(q + n - 1, fr_zero());
   for (size_t k = n; k-- > 0;) {
     acc = fr_add(fr_load(p + k), fr_mul(z, acc));
     if (q && k >= 1) fr_store(q + k - 1, acc);
   }
-  fr_store(yout, acc);
+  fr_store(yout + b, acc);
 }
 
-// q may be null (evaluation only).  y is written to the device word yout.
-static int linrec(tp_ctx* ctx, const Fr* p, size_t n, const tph::HFr& z, Fr* q, Fr* yout, int level) {
+// y[b] is written to the device words yout[b].
+static int linrec(tp_ctx* ctx, const LinBatch& in, int batch, size_t n, Fr* yout, int level) {
   if (n <= LIN_BASE) {
-    k_linrec_serial<<<1, 1, 0, ctx->stream>>>(p, n, to_dev(z), q, yout);
+    LinBatch a = in;
+    for (int b = batch; b < LIN_MAX_BATCH; b++) a.p[b] = nullptr;
+    k_linrec_serial<<<1, LIN_MAX_BATCH, 0, ctx->stream>>>(a, n, yout);
     TP_LAUNCH(ctx, "k_linrec_serial");
     return TP_OK;
   }
   size_t nch = (n + LIN_CH - 1) / LIN_CH;
-  // level buffers: h (nch) and qprime (nch)
-  TP_TRY(ensure(ctx, ctx->scan_tmp[level], 2 * nch * sizeof(Fr)));
+  // level buffers: h (nch per recurrence) and qprime (nch per recurrence)
+  TP_TRY(ensure(ctx, ctx->scan_tmp[level], 2 * nch * LIN_MAX_BATCH * sizeof(Fr)));
   Fr* h = (Fr*)ctx->scan_tmp[level].p;
-  Fr* qp = h + nch;
-  k_linrec_reduce<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(p, n, to_dev(z), h);
+  Fr* qp = h + nch * LIN_MAX_BATCH;
+  k_linrec_reduce<<<dim3(ew_grid(nch), (unsigned)batch), EW_THREADS, 0, ctx->stream>>>(in, n, h, nch);
   TP_LAUNCH(ctx, "k_linrec_reduce");
-  tph::HFr zc = z.pow_u64(LIN_CH);
-  TP_TRY(linrec(ctx, h, nch, zc, q ? qp : nullptr, yout, level + 1));
-  if (q) {
-    k_linrec_apply<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(p, n, to_dev(z), qp, q);
+  LinBatch next;
+  bool any_q = false;
+  for (int b = 0; b < LIN_MAX_BATCH; b++) {
+    const int s = b < batch ? b : 0;
+    next.p[b] = h + (size_t)s * nch;
+    next.q[b] = in.q[s] ? qp + (size_t)s * nch : nullptr;
+    next.z[b] = to_dev(to_host(in.z[s]).pow_u64(LIN_CH));
+    any_q = any_q || (b < batch && in.q[b]);
+  }
+  TP_TRY(linrec(ctx, next, batch, nch, yout, level + 1));
+  if (any_q) {
+    k_linrec_apply<<<dim3(ew_grid(nch), (unsigned)batch), EW_THREADS, 0, ctx->stream>>>(in, n, qp, nch);
     TP_LAUNCH(ctx, "k_linrec_apply");
   }
   return TP_OK;
 }
 
-int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out, tph::HFr* y) {
+// Evaluate (and, where q_out[b] is non-null, divide by X - z[b]) `batch` polynomials of `len` coefficients.
+int poly_open_batch_dev(tp_ctx* ctx, const Fr* const* p, size_t len, const Fr* z, Fr* const* q_out, int batch,
+                        tph::HFr* y) {
   if (len == 0) return fail(ctx, TP_ERR_EMPTY_POLY, "open: empty polynomial");
+  if (batch < 1 || batch > LIN_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "open: bad batch size");
   ProfScope prof(ctx, TP_PHASE_SCAN);
-  TP_TRY(ensure(ctx, ctx->misc[2], sizeof(Fr)));
+  TP_TRY(ensure(ctx, ctx->misc[2], LIN_MAX_BATCH * sizeof(Fr)));
   Fr* yd = (Fr*)ctx->misc[2].p;
-  TP_TRY(linrec(ctx, p, len, to_host(z), q_out, yd, 0));
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, yd, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  LinBatch in;
+  for (int b = 0; b < LIN_MAX_BATCH; b++) {
+    const int s = b < batch ? b : 0;
+    in.p[b] = p[s];
+    in.q[b] = q_out ? q_out[s] : nullptr;
+    in.z[b] = z[s];
+  }
+  TP_TRY(linrec(ctx, in, batch, len, yd, 0));
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, yd, batch * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(y->v, ctx->pinned, 32);
+  for (int b = 0; b < batch; b++) memcpy(y[b].v, (const uint8_t*)ctx->pinned + 32 * b, 32);
   return TP_OK;
+}
+int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out, tph::HFr* y) {
+  const Fr* ps[1] = {p};
+  Fr* qs[1] = {q_out};
+  return poly_open_batch_dev(ctx, ps, len, &z, qs, 1, y);
 }
 
 // =====================================================================================
