@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--ref-log-n", type=int, default=16, help="size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sweep", action="store_true", help="also run the MSM / NTT sweeps (extra lines on stderr)")
+    ap.add_argument("--dump-proof", default=None, help="write the proof bytes of the last timed step to this file (rank 0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -334,6 +335,9 @@ def main():
                     rl, res["ms_per_step"], res["threads"], scale, log_n)}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
+    if rank == 0 and args.dump_proof:
+        with open(args.dump_proof, "wb") as f:
+            f.write(proof)
     if rank == 0:
         print(json.dumps(line))
     if args.sweep and rank == 0 and world == 1:

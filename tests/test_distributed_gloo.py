@@ -85,3 +85,66 @@ def test_shard_ranges_cover_exactly():
                 if cnt:
                     assert first == pos
                     pos += cnt
+
+
+# ---- quotient sharded by coset (api.cu prove_resident, tp_ctx_set_broadcast) ------------------------------
+def _coset_owner(k, world):
+    return k % world if world < 4 else k * (world // 4)   # typlonk_b200/csrc/api.cu: owner(k)
+
+
+def _coset_worker(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import random
+    from oracle.pyoracle import fields, poly
+    M = fields.R_MOD
+    rnd = random.Random(5)                      # same numerator polynomial on every rank
+    N = [rnd.randrange(M) for _ in range(4 * n - 1)]
+    dom = poly.Domain(n)
+    w4n = fields.root_of_unity(4 * n)
+    slots = [torch.zeros(n * 32, dtype=torch.uint8) for _ in range(4)]
+    for k in range(4):
+        if _coset_owner(k, world) != rank:
+            continue
+        g = pow(w4n, k, M)
+        evals = [poly.evaluate(N, g * dom.element(i) % M) for i in range(n)]
+        coeffs = dom.ifft(evals)
+        ginv = pow(g, M - 2, M)
+        ck = [coeffs[i] * pow(ginv, i, M) % M for i in range(n)]
+        slots[k] = torch.frombuffer(bytearray(b"".join(v.to_bytes(32, "little") for v in ck)), dtype=torch.uint8)
+    for k in range(4):                          # the broadcast callback shape: (buffer, bytes, root)
+        dist.broadcast(slots[k], src=_coset_owner(k, world))
+    C = [[int.from_bytes(slots[k].numpy().tobytes()[32 * i:32 * i + 32], "little") for i in range(n)] for k in range(4)]
+    iota = pow(w4n, n, M)
+    s, quarter = (M - iota) % M, pow(4, M - 2, M)
+    Nj = [[quarter * sum(pow(s, k * j, M) * C[k][i] for k in range(4)) % M for i in range(n)] for j in range(4)]
+    t2 = Nj[3]
+    t1 = [(a + b) % M for a, b in zip(Nj[2], t2)]
+    t0 = [(a + b) % M for a, b in zip(Nj[1], t1)]
+    quo, _ = poly.divide_by_vanishing_poly(N, n)
+    q.put((rank, poly.strip(t0 + t1 + t2) == poly.strip(list(quo))))
+    dist.destroy_process_group()
+
+
+def test_coset_sharded_quotient_recombines():
+    world, n = 2, 8
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_coset_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_coset_owner_map():
+    for world in (1, 2, 3, 4, 8):
+        owners = [_coset_owner(k, world) for k in range(4)]
+        assert all(0 <= o < world for o in owners)
+        if world >= 4:
+            assert len(set(owners)) == 4        # one coset per rank, the other ranks idle in this phase

@@ -133,3 +133,39 @@ def test_safegcd_fq_inversion_host_build(tmp_path):
     for x, o in zip(xs, out):
         assert o != "FAIL"
         assert int(o, 16) == (pow(x, -1, q) if x else 0)
+
+
+def test_quotient_by_cosets_identity():
+    """The algebra behind the coset-sharded quotient (typlonk_b200/csrc/poly.cu k_quotient_combine, api.cu):
+    for N of degree < 4n, the interpolants C_k of N on the cosets w4n^k H satisfy C_k = sum_j iota^(kj) N_j
+    (N = sum_j X^(jn) N_j), so N_j = 1/4 sum_k iota^(-kj) C_k and floor(N / (X^n - 1)) has the chunks
+    t_2 = N_3, t_1 = N_2 + t_2, t_0 = N_1 + t_1 -- checked against the oracle's long division
+    (plonk/src/proof.rs:373, 504-508)."""
+    import random
+    from oracle.pyoracle import fields, poly
+    M = fields.R_MOD
+    rnd = random.Random(11)
+    for n in (2, 8, 32):
+        N = [rnd.randrange(M) for _ in range(4 * n - rnd.randrange(0, 3))]
+        dom = poly.Domain(n)
+        w4n = fields.root_of_unity(4 * n)
+        iota = pow(w4n, n, M)
+        assert iota * iota % M == M - 1
+        C = []
+        for k in range(4):
+            g = pow(w4n, k, M)
+            evals = [poly.evaluate(N, g * dom.element(i) % M) for i in range(n)]
+            # inverse coset transform: interpolate on H the polynomial p(g X), then undo the scaling
+            coeffs = dom.ifft(evals) + [0] * n
+            ginv = pow(g, M - 2, M)
+            C.append([coeffs[i] * pow(ginv, i, M) % M for i in range(n)])
+        quarter = pow(4, M - 2, M)
+        s = (M - iota) % M  # iota^-1
+        Nj = [[quarter * sum(pow(s, k * j, M) * C[k][i] for k in range(4)) % M for i in range(n)] for j in range(4)]
+        flat = [c for j in range(4) for c in Nj[j]]
+        assert poly.strip(flat) == poly.strip(list(N))
+        t2 = Nj[3]
+        t1 = [(a + b) % M for a, b in zip(Nj[2], t2)]
+        t0 = [(a + b) % M for a, b in zip(Nj[1], t1)]
+        q, _r = poly.divide_by_vanishing_poly(N, n)
+        assert poly.strip(t0 + t1 + t2) == poly.strip(list(q))

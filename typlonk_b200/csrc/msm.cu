@@ -16,7 +16,7 @@
 //                       head/tail partials for runs that cross chunk boundaries
 //   5. k_msm_merge    : stitches the boundary partials
 //   6. k_msm_wsum_level / k_msm_masked_sum: sum_v v * B_v of each bucket set without a single
-//                       scalar multiplication: two levels of 8-bucket running sums, then the
+//                       scalar multiplication: levels of 16- then 4-bucket running sums, then the
 //                       remaining index bits as masked tree sums (see "bucket reduction" below)
 //   7. host           : <= 40 additions/doublings per bucket set + affine conversion (serial tail;
 //                       one CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic),
@@ -755,11 +755,12 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
 //     F(R) = sum_k 2^k * (sum of R_m over the m with bit k set),     P = sum_m R_m,
 // all of them masked tree sums (k_msm_masked_sum) that run side by side in one launch together with
 // the plain sums T_l = sum_seg t_seg of every level.  The host then needs ~40 group operations per
-// set (S = 8 is a power of two) instead of a Horner walk over all windows.  No thread ever does a
+// set (S is a power of two) instead of a Horner walk over all windows.  No thread ever does a
 // scalar multiplication and the longest dependent chain is 2 S additions per level.
-#define WSUM_S_FIRST 8       // segment length of the first level (where the work is: 2 additions per bucket)
+#define WSUM_S_FIRST 16      // segment length of the first level (where the work is: 2 additions per bucket)
 #define WSUM_S_NEXT 4        // later levels are latency-bound: shorter chains
-#define WSUM_MIN 32768       // keep levelling while a set still has at least this many entries
+#define WSUM_MIN 8192        // keep levelling while a set still has at least this many entries
+                             // (swept on B200 at 2^20: (32768,8,4) 11.9 ms of reduction per proof, (8192,16,4) 10.1 ms)
 #define WSUM_MAX_LEVELS 6
 __global__ void __launch_bounds__(128) k_msm_wsum_level(const G1Xyzz* __restrict__ in, const unsigned* __restrict__ hist,
                                                         unsigned m_in, unsigned seg, unsigned total_out,
@@ -1063,13 +1064,15 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
       TP_LAUNCH(ctx, "k_msm_accumulate");
     }
   }
-  // reduction plan: levels of running sums (segment 8, then 4), then masked sums over what is left
+  // reduction plan: levels of running sums (segment 16, then 4), then masked sums over what is left
   unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1];
   int nl = 0;
   m_level[0] = pl.nbuck;
   seg_level[0] = 1;
-  while (nl < WSUM_MAX_LEVELS && m_level[nl] >= WSUM_MIN) {
-    seg_level[nl + 1] = nl == 0 ? WSUM_S_FIRST : WSUM_S_NEXT;
+  static const unsigned wsum_min = env_uint("TP_MSM_WSUM_MIN", WSUM_MIN);
+  static const unsigned wsum_s1 = env_uint("TP_MSM_WSUM_S1", WSUM_S_FIRST), wsum_s2 = env_uint("TP_MSM_WSUM_S2", WSUM_S_NEXT);
+  while (nl < WSUM_MAX_LEVELS && m_level[nl] >= wsum_min && m_level[nl] >= 2 * (nl == 0 ? wsum_s1 : wsum_s2)) {
+    seg_level[nl + 1] = nl == 0 ? wsum_s1 : wsum_s2;
     m_level[nl + 1] = m_level[nl] / seg_level[nl + 1];
     nl++;
   }
