@@ -114,6 +114,16 @@ __global__ void __launch_bounds__(512) k_ntt_small(NttPassArgs a) {
 // the column inside its 2^s0 block (0 in the first pass).
 __device__ __forceinline__ unsigned ntt_swz(unsigned i) { return i ^ ((i >> 3) & 7u); }
 
+// The butterfly rounds hold 28 field products (4 round shapes x up to 12).  Inlined they make 210 KB of SASS,
+// more than the instruction cache holds, and small grids stall on instruction fetch (no_instruction 2-6 per
+// issue, profiles/r1_summary.md O); through one shared copy of the multiplier the kernel is 2-7 % faster at
+// every size.  TP_NTT_MUL_INLINE restores the inlined form.
+#ifndef TP_NTT_MUL_INLINE
+static __device__ __noinline__ Fr ntt_mul(Fr a, Fr b) { return fr_mul(a, b); }
+#else
+__device__ __forceinline__ Fr ntt_mul(const Fr& a, const Fr& b) { return fr_mul(a, b); }
+#endif
+
 template <int D0, int NST, bool TRIV>
 __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw, unsigned A, unsigned sh, unsigned L,
                                           bool inverse, unsigned half_n) {
@@ -132,7 +142,7 @@ __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw,
       } else {
         const unsigned idx = base_idx + (q << (L - d - 1));
         const Fr w = fr_load(tw + (inverse ? half_n - idx : idx));
-        const Fr t = fr_mul(w, x[e1]);
+        const Fr t = ntt_mul(w, x[e1]);
         const Fr u = x[e0];
         const Fr p = fr_add(u, t), m = fr_sub(u, t);
         x[e0] = inverse ? m : p;   // mirrored table entry is -omega^-idx
