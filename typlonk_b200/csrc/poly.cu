@@ -13,6 +13,15 @@
 
 namespace tp {
 
+// Element-wise kernels with many field products (the quotient numerator has ~30) are straight-line code far larger than
+// the instruction cache; with TP_POLY_MUL_CALL they go through one shared copy of the multiplier (A/B in profiles/).
+#ifdef TP_POLY_MUL_CALL
+static __device__ __noinline__ Fr pmul(Fr a, Fr b) { return fr_mul(a, b); }
+#else
+__device__ __forceinline__ Fr pmul(const Fr& a, const Fr& b) { return fr_mul(a, b); }
+#endif
+
+
 #define EW_THREADS 256
 static inline unsigned ew_grid(size_t n) { return (unsigned)((n + EW_THREADS - 1) / EW_THREADS); }
 
@@ -100,11 +109,11 @@ __global__ void k_perm_numden(PermArgs a) {
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     Fr v = fr_add(fr_load(a.v[i] + j), a.gamma);
-    Fr nu = fr_add(v, fr_mul(a.beta, fr_load(a.id[i] + j)));
-    Fr de = fr_add(v, fr_mul(a.beta, fr_load(a.sg[i] + j)));
+    Fr nu = fr_add(v, pmul(a.beta, fr_load(a.id[i] + j)));
+    Fr de = fr_add(v, pmul(a.beta, fr_load(a.sg[i] + j)));
     zero |= fr_is_zero(de);
-    num = i == 0 ? nu : fr_mul(num, nu);
-    den = i == 0 ? de : fr_mul(den, de);
+    num = i == 0 ? nu : pmul(num, nu);
+    den = i == 0 ? de : pmul(den, de);
   }
   if (zero) atomicOr(a.flag, 1u);
   fr_store(a.num + j, num);
@@ -121,14 +130,14 @@ __global__ void k_batch_ratio(const Fr* num, const Fr* den, size_t n, Fr* out) {
   Fr acc = fr_one();
   for (int i = 0; i < cnt; i++) {
     pre[i] = acc;  // product of den[lo .. lo+i-1]
-    acc = fr_mul(acc, fr_load(den + lo + i));
+    acc = pmul(acc, fr_load(den + lo + i));
   }
   Fr inv = fr_inv(acc);
   for (int i = cnt - 1; i >= 0; i--) {
     Fr d = fr_load(den + lo + i);
-    Fr di = fr_mul(inv, pre[i]);  // 1 / den[lo+i]
-    inv = fr_mul(inv, d);
-    fr_store(out + lo + i, fr_mul(fr_load(num + lo + i), di));
+    Fr di = pmul(inv, pre[i]);  // 1 / den[lo+i]
+    inv = pmul(inv, d);
+    fr_store(out + lo + i, pmul(fr_load(num + lo + i), di));
   }
 }
 __global__ void k_set_one(Fr* p) {
@@ -362,24 +371,24 @@ __global__ void __launch_bounds__(EW_THREADS) k_quotient_numerator(QuotKernelArg
   Fr z = fr_load(q.z4 + o);
   Fr zw = fr_load(q.z4 + (size_t)k * q.n + (i + 1 < q.n ? i + 1 : 0));   // z(omega x): next point of the same coset
   // gate line (proof.rs:317-320)
-  Fr acc = fr_mul(fr_load(q.sel4[0] + o), a);
-  acc = fr_add(acc, fr_mul(fr_load(q.sel4[1] + o), b));
-  acc = fr_sub(acc, fr_mul(fr_load(q.sel4[2] + o), c));
-  acc = fr_add(acc, fr_mul(fr_mul(fr_load(q.sel4[3] + o), a), b));
+  Fr acc = pmul(fr_load(q.sel4[0] + o), a);
+  acc = fr_add(acc, pmul(fr_load(q.sel4[1] + o), b));
+  acc = fr_sub(acc, pmul(fr_load(q.sel4[2] + o), c));
+  acc = fr_add(acc, pmul(pmul(fr_load(q.sel4[3] + o), a), b));
   acc = fr_add(acc, fr_load(q.sel4[4] + o));
   acc = fr_add(acc, fr_load(q.pi4 + o));
   // permutation lines (proof.rs:323-354)
   Fr ag = fr_add(a, q.gamma), bg = fr_add(b, q.gamma), cg = fr_add(c, q.gamma);
-  Fr l2 = fr_mul(fr_add(ag, fr_mul(q.bk[0], x)), fr_add(bg, fr_mul(q.bk[1], x)));
-  l2 = fr_mul(l2, fr_add(cg, fr_mul(q.bk[2], x)));
-  l2 = fr_mul(l2, z);
-  Fr l3 = fr_mul(fr_add(ag, fr_mul(q.beta, fr_load(q.sig4[0] + o))), fr_add(bg, fr_mul(q.beta, fr_load(q.sig4[1] + o))));
-  l3 = fr_mul(l3, fr_add(cg, fr_mul(q.beta, fr_load(q.sig4[2] + o))));
-  l3 = fr_mul(l3, zw);
-  acc = fr_add(acc, fr_mul(q.alpha, fr_sub(l2, l3)));
+  Fr l2 = pmul(fr_add(ag, pmul(q.bk[0], x)), fr_add(bg, pmul(q.bk[1], x)));
+  l2 = pmul(l2, fr_add(cg, pmul(q.bk[2], x)));
+  l2 = pmul(l2, z);
+  Fr l3 = pmul(fr_add(ag, pmul(q.beta, fr_load(q.sig4[0] + o))), fr_add(bg, pmul(q.beta, fr_load(q.sig4[1] + o))));
+  l3 = pmul(l3, fr_add(cg, pmul(q.beta, fr_load(q.sig4[2] + o))));
+  l3 = pmul(l3, zw);
+  acc = fr_add(acc, pmul(q.alpha, fr_sub(l2, l3)));
   // L0 line (proof.rs:355-360)
-  Fr l4 = fr_mul(fr_sub(z, fr_one()), fr_load(q.l0_4 + o));
-  acc = fr_add(acc, fr_mul(q.alpha2, l4));
+  Fr l4 = pmul(fr_sub(z, fr_one()), fr_load(q.l0_4 + o));
+  acc = fr_add(acc, pmul(q.alpha2, l4));
   fr_store(q.out + o, acc);
 }
 int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a, const unsigned* cosets, int ncosets) {
