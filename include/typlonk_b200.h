@@ -50,6 +50,7 @@ enum {
 };
 
 #define TP_G1_BYTES 97
+#define TP_G2_BYTES 193 /* x.c0 | x.c1 | y.c0 | y.c1 (48 B Montgomery limbs each) | 1 byte infinity flag */
 #define TP_PROOF_FIXED_BYTES 1472 /* 13 G1 x 96 + 7 Fr x 32 (uncompressed ark-serialize 0.3 layout) */
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -119,6 +120,11 @@ int tp_srs_upload(tp_ctx* ctx, const uint8_t* g1_xy, size_t len, tp_srs** out);
 int tp_srs_len(const tp_srs* srs, size_t* len);
 int tp_srs_g1_download(tp_ctx* ctx, const tp_srs* srs, size_t offset, size_t count, uint8_t* out_xy);
 int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs);
+/* Srs::g2_ref / g2s_ref (srs.rs:46-51): (G2, tau G2).  tp_srs_from_secret derives them (Srs::g2, srs.rs:25-28);
+ * an uploaded SRS has none until tp_srs_set_g2, and the verifier entry points fail with TP_ERR_INVALID_ARG
+ * without them. */
+int tp_srs_g2(const tp_srs* srs, uint8_t g2[TP_G2_BYTES], uint8_t g2s[TP_G2_BYTES]);
+int tp_srs_set_g2(tp_srs* srs, const uint8_t g2[TP_G2_BYTES], const uint8_t g2s[TP_G2_BYTES]);
 
 /* ---- KZG  (kzg/src/lib.rs) ------------------------------------------------------------- */
 
@@ -130,6 +136,15 @@ int tp_commit_dev(tp_ctx* ctx, const tp_srs* srs, const void* coeffs_dev, size_t
  * len == 0 -> TP_ERR_EMPTY_POLY. */
 int tp_open(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, const uint64_t z[4],
             uint8_t w_out[TP_G1_BYTES], uint64_t y_out[4]);
+
+/* KzgScheme::verify (lib.rs:66-81): *ok = [ e(W, g2s - z g2) == e(C - y G, g2) ], evaluated as the single product
+ * e(W, g2s) e(-(z W + C - y G), g2) == 1 (the same predicate by bilinearity; one shared Miller loop, one final
+ * exponentiation).  Host arithmetic only -- the pairing is O(1) work per proof and has no data-parallel part; no
+ * device or context is involved.  Points off the curve give *ok = 0. */
+int tp_kzg_verify(const uint8_t g2[TP_G2_BYTES], const uint8_t g2s[TP_G2_BYTES], const uint8_t commitment[TP_G1_BYTES],
+                  const uint8_t w[TP_G1_BYTES], const uint64_t y[4], const uint64_t z[4], int* ok);
+/* *ok = [ prod_i e(g1[i], g2[i]) == 1 ] for `count` pairs (97 B / 193 B records).  Host only. */
+int tp_pairing_check(const uint8_t* g1, const uint8_t* g2, size_t count, int* ok);
 
 /* ---- NTT  (ark-poly Evaluations::interpolate / evaluate_over_domain; call sites
  *      plonk/src/proof.rs:50,106,115,125,128,337,415; builder.rs:85; permutation/src/lib.rs:171,188) */
@@ -177,6 +192,34 @@ int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const 
              uint8_t* proof_out, size_t proof_cap);
 int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
                  uint8_t* proof_out, size_t proof_cap);
+
+/* verify() (proof.rs:195-233, 441-503): `proof` is the TP_PROOF_FIXED_BYTES block tp_prove writes, `public_inputs`
+ * the proof's public-input vector (n_public Montgomery Fr; resized to n like proof.rs:204-205).  The device
+ * interpolates and evaluates the public-input polynomial, evaluates sigma_1..3 at the challenge point and (first call
+ * only; cached in the circuit) computes the five selector and three sigma commitments with the MSM; the host
+ * re-derives the challenges, checks the five openings, assembles the linearisation commitment and checks its
+ * opening (12 pairings as 6 two-pair products).  *ok = 1 accept / 0 reject; a malformed encoding (coordinate >= q,
+ * scalar >= r) is TP_ERR_INVALID_ARG. */
+int tp_verify(tp_ctx* ctx, tp_circuit* c, const uint8_t* proof, size_t proof_len, const uint64_t* public_inputs,
+              size_t n_public, int* ok);
+/* The host half of tp_verify with every circuit-dependent value supplied by the caller, for verifiers that hold a
+ * verification key instead of the circuit: the eight commitments, the domain size n (power of two), the coset
+ * representatives k_i, sigma_1(zeta), sigma_2(zeta) and PI(zeta) for THIS proof's challenge point, [1]G (srs[0]) and
+ * the two G2 points.  No device involved. */
+typedef struct tp_verifier_inputs {
+  uint8_t fixed_commitments[5][TP_G1_BYTES];
+  uint8_t sigma_commitments[3][TP_G1_BYTES];
+  uint8_t identity[TP_G1_BYTES];
+  uint8_t g2[TP_G2_BYTES], g2s[TP_G2_BYTES];
+  uint64_t cosets[3][4];
+  uint64_t sigma_evals[2][4];
+  uint64_t public_eval[4];
+  uint64_t n;
+} tp_verifier_inputs;
+int tp_verify_prepared(const tp_verifier_inputs* in, const uint8_t* proof, size_t proof_len, int* ok);
+/* The challenges verify() derives from a proof (proof.rs:235-244): alpha, beta, gamma, evaluation point. */
+int tp_proof_challenges(const uint8_t* proof, size_t proof_len, uint64_t alpha[4], uint64_t beta[4], uint64_t gamma[4],
+                        uint64_t point[4]);
 
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* Measured dependent-free IMAD throughput of this device (instructions/s), for rooflines. */

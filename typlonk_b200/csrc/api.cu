@@ -4,41 +4,12 @@
 // plonk/src/builder.rs:70-88.  The host only sequences kernels, derives the Fiat-Shamir
 // challenges (transcript.h) and does the O(1) scalar algebra between rounds.
 #include "common.cuh"
+#include "circuit.h"
 #include "transcript.h"
 
 using namespace tp;
 using tph::HFr;
 
-namespace tp {
-tph::HFr omega_for_log(unsigned log_n);
-}
-
-struct tp_circuit {
-  size_t n = 0;
-  unsigned log_n = 0;
-  const tp_srs* srs = nullptr;
-  Fr* sel_coef[5] = {0};
-  Fr* sel_eval[5] = {0};
-  Fr* sel4[5] = {0};
-  Fr* id[3] = {0};
-  Fr* sig_eval[3] = {0};
-  Fr* sig_coef[3] = {0};
-  Fr* sig4[3] = {0};
-  Fr* l0_4 = nullptr;
-  HFr k[3];
-  // per-proof work buffers
-  Fr* adv_eval[3] = {0};
-  Fr* adv_coef[3] = {0};
-  Fr* pi_eval = nullptr;
-  Fr* pi_coef = nullptr;
-  Fr* z_eval = nullptr;  // n + 1
-  Fr* z_coef = nullptr;
-  Fr* buf4[6] = {0};     // a4 b4 c4 z4 pi4 num4
-  Fr* t = nullptr;       // 3n
-  Fr* q[6] = {0};        // opening quotients (a, b, c, z, z-omega, r), n each
-  Fr* r = nullptr;       // n
-  std::vector<void*> allocs;
-};
 
 static int dmalloc(tp_ctx* ctx, tp_circuit* c, Fr** p, size_t count) {
   void* v = nullptr;
@@ -255,8 +226,10 @@ int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs*
   memcpy(t.v, tau, 32);
   int rc = srs_generate_dev(ctx, t, len, s->g1);
   if (rc == TP_OK) rc = srs_build_levels_dev(ctx, s);
+  if (rc == TP_OK) rc = srs_pairing_from_secret(s, t);  // Srs::g2 (srs.rs:25-28), on the host while the device works
   if (rc == TP_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, TP_ERR_CUDA, "srs: generation failed");
   if (rc != TP_OK) {
+    srs_pairing_free(s);
     cudaFree(s->g1);
     delete s;
     return rc;
@@ -292,6 +265,7 @@ int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs) {
   if (!srs) return TP_OK;
   cudaStreamSynchronize(ctx->stream);
   cudaFree(srs->g1);
+  srs_pairing_free(srs);
   delete srs;
   return TP_OK;
 }
@@ -478,8 +452,10 @@ int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const sel
   for (int i = 0; i < 5 && rc == TP_OK; i++) {
     rc = h2d(ctx, c->sel_eval[i], selector_evals[i], n * sizeof(Fr));
     if (rc == TP_OK) rc = ntt_dev(ctx, c->sel_eval[i], c->sel_coef[i], c->log_n, true, nullptr);
-    if (rc == TP_OK && fixed_commitments) rc = msm_dev(ctx, srs, c->sel_coef[i], n, fixed_commitments + i * TP_G1_BYTES);
+    if (rc == TP_OK) rc = msm_dev(ctx, srs, c->sel_coef[i], n, c->fixed_com[i]);
+    if (rc == TP_OK && fixed_commitments) memcpy(fixed_commitments + i * TP_G1_BYTES, c->fixed_com[i], TP_G1_BYTES);
   }
+  c->have_fixed_com = rc == TP_OK;
   // sigma / id tables (permutation/src/lib.rs:101-128)
   if (rc == TP_OK) {
     uint64_t* perm_dev = (uint64_t*)c->buf4[0];  // 3n u64 fits in a 4n Fr buffer
@@ -499,7 +475,12 @@ int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const sel
 }
 
 int tp_circuit_sigma_commitments(tp_ctx* ctx, tp_circuit* c, uint8_t out[3 * TP_G1_BYTES]) {
-  for (int i = 0; i < 3; i++) TP_TRY(msm_dev(ctx, c->srs, c->sig_coef[i], c->n, out + i * TP_G1_BYTES));
+  if (!c->have_sigma_com) {
+    const Fr* sets[3] = {c->sig_coef[0], c->sig_coef[1], c->sig_coef[2]};
+    TP_TRY(msm_batch_dev(ctx, c->srs, sets, 3, c->n, c->sigma_com));
+    c->have_sigma_com = true;
+  }
+  memcpy(out, c->sigma_com, sizeof(c->sigma_com));
   return TP_OK;
 }
 

@@ -85,6 +85,7 @@ struct tp_srs {
   size_t len = 0;
   unsigned c = 0;       // MSM window bits the tables were built for
   unsigned levels = 1;
+  void* pairing = nullptr;  // verify.cu: (G2, tau G2) with their Miller-loop line tables, and srs[0]
 };
 
 namespace tp {
@@ -174,11 +175,15 @@ struct ProfScope {
 };
 
 // ---- device-level entry points (each implemented in its own .cu) -----------------------
+// verify.cu
+int srs_pairing_from_secret(tp_srs* srs, const tph::HFr& tau);
+void srs_pairing_free(tp_srs* srs);
 // ntt.cu
 int ntt_dev(tp_ctx* ctx, const Fr* in, Fr* out, unsigned log_n, bool inverse, const uint64_t* coset);
 int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64_t* const* coset, int count,
                   unsigned log_n, bool inverse);
 int ntt_get_twiddles(tp_ctx* ctx, unsigned log_n, const Fr** tw);
+tph::HFr omega_for_log(unsigned log_n);  // generator of the 2^log_n-th roots of unity (ark-poly Radix2EvaluationDomain)
 // msm.cu : result as host Jacobian (this rank's shard only when sharded = false, else combined)
 int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]);
 // `batch` MSMs over the same bases in one pipeline (out[b] = sum_i scalars[b][i] * srs[i])

@@ -11,6 +11,7 @@ _LIB_PATH = Path(os.environ.get("TYPLONK_B200_LIB") or
                  (Path(__file__).resolve().parent / "lib" / "libtyplonk_b200.so"))
 
 G1_BYTES = 97
+G2_BYTES = 193
 PROOF_FIXED_BYTES = 1472
 PHASES = ["msm_total", "msm_sort", "msm_accum", "msm_reduce", "ntt", "quotient", "perm", "scan"]
 
@@ -28,6 +29,7 @@ SYMBOLS = [
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
     "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option", "tp_ctx_get_stat",
+    "tp_srs_g2", "tp_srs_set_g2", "tp_kzg_verify", "tp_pairing_check", "tp_verify", "tp_verify_prepared", "tp_proof_challenges",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -89,6 +91,62 @@ def fr_rand_stream(seed: int, count: int) -> bytes:
     if rc != 0:
         raise TyplonkError(rc, "tp_fr_rand_stream")
     return bytes(out)
+
+
+# ---- host-only entry points (no device, no context) --------------------------------------------
+def kzg_verify(g2: bytes, g2s: bytes, commitment: bytes, w: bytes, y_mont: bytes, z_mont: bytes) -> bool:
+    """KzgScheme::verify (kzg/src/lib.rs:66-81) on 193-byte G2 / 97-byte G1 ABI records."""
+    ok = C.c_int(0)
+    rc = lib().tp_kzg_verify(_buf(g2), _buf(g2s), _buf(commitment), _buf(w), _buf(y_mont), _buf(z_mont), C.byref(ok))
+    if rc != 0:
+        raise TyplonkError(rc, "tp_kzg_verify")
+    return bool(ok.value)
+
+
+def pairing_check(g1s, g2s) -> bool:
+    """prod_i e(g1s[i], g2s[i]) == 1."""
+    assert len(g1s) == len(g2s)
+    ok = C.c_int(0)
+    rc = lib().tp_pairing_check(_buf(b"".join(g1s)), _buf(b"".join(g2s)), C.c_size_t(len(g1s)), C.byref(ok))
+    if rc != 0:
+        raise TyplonkError(rc, "tp_pairing_check")
+    return bool(ok.value)
+
+
+def proof_challenges(proof_fixed: bytes):
+    """(alpha, beta, gamma, evaluation point) as Montgomery bytes (plonk/src/proof.rs:235-244)."""
+    outs = [(C.c_char * 32)() for _ in range(4)]
+    rc = lib().tp_proof_challenges(_buf(proof_fixed), C.c_size_t(len(proof_fixed)), *outs)
+    if rc != 0:
+        raise TyplonkError(rc, "tp_proof_challenges: malformed proof")
+    return tuple(bytes(o) for o in outs)
+
+
+class VerifierInputs(C.Structure):
+    """tp_verifier_inputs."""
+    _fields_ = [("fixed_commitments", C.c_char * (5 * G1_BYTES)), ("sigma_commitments", C.c_char * (3 * G1_BYTES)),
+                ("identity", C.c_char * G1_BYTES), ("g2", C.c_char * G2_BYTES), ("g2s", C.c_char * G2_BYTES),
+                ("cosets", C.c_uint64 * 12), ("sigma_evals", C.c_uint64 * 8), ("public_eval", C.c_uint64 * 4),
+                ("n", C.c_uint64)]
+
+
+def verify_prepared(fixed, sigma, identity, g2, g2s, cosets_mont, sigma_evals_mont, public_eval_mont, n, proof_fixed) -> bool:
+    """tp_verify_prepared: the host half of the verifier from a verification key (ABI records / Montgomery bytes)."""
+    v = VerifierInputs()
+    C.memmove(C.addressof(v) + VerifierInputs.fixed_commitments.offset, b"".join(fixed), 5 * G1_BYTES)
+    C.memmove(C.addressof(v) + VerifierInputs.sigma_commitments.offset, b"".join(sigma), 3 * G1_BYTES)
+    C.memmove(C.addressof(v) + VerifierInputs.identity.offset, identity, G1_BYTES)
+    C.memmove(C.addressof(v) + VerifierInputs.g2.offset, g2, G2_BYTES)
+    C.memmove(C.addressof(v) + VerifierInputs.g2s.offset, g2s, G2_BYTES)
+    C.memmove(C.addressof(v) + VerifierInputs.cosets.offset, b"".join(cosets_mont), 96)
+    C.memmove(C.addressof(v) + VerifierInputs.sigma_evals.offset, b"".join(sigma_evals_mont), 64)
+    C.memmove(C.addressof(v) + VerifierInputs.public_eval.offset, public_eval_mont, 32)
+    v.n = n
+    ok = C.c_int(0)
+    rc = lib().tp_verify_prepared(C.byref(v), _buf(proof_fixed), C.c_size_t(len(proof_fixed)), C.byref(ok))
+    if rc != 0:
+        raise TyplonkError(rc, "tp_verify_prepared: malformed input")
+    return bool(ok.value)
 
 
 class Context:
@@ -281,6 +339,19 @@ class SrsHandle:
         self.ctx._check(lib().tp_srs_g1_download(self.ctx._h, self._h, C.c_size_t(offset), C.c_size_t(count), out))
         return bytes(out)
 
+    def g2(self):
+        """(G2, tau G2) as 193-byte ABI records (srs.rs:46-51)."""
+        a, b = (C.c_char * G2_BYTES)(), (C.c_char * G2_BYTES)()
+        rc = lib().tp_srs_g2(self._h, a, b)
+        if rc != 0:
+            raise TyplonkError(rc, "tp_srs_g2: this SRS has no G2 points (set_g2)")
+        return bytes(a), bytes(b)
+
+    def set_g2(self, g2: bytes, g2s: bytes):
+        rc = lib().tp_srs_set_g2(self._h, _buf(g2), _buf(g2s))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_srs_set_g2: point not on the twist")
+
     def destroy(self):
         if self._h:
             lib().tp_srs_destroy(self.ctx._h, self._h)
@@ -308,6 +379,13 @@ class CircuitHandle:
         self.ctx._check(lib().tp_prove_dev(self.ctx._h, self._h, adv, C.c_void_p(pi_dptr), out,
                                            C.c_size_t(PROOF_FIXED_BYTES)))
         return bytes(out)
+
+    def verify(self, proof_fixed: bytes, public_inputs_mont: bytes) -> bool:
+        ok = C.c_int(0)
+        self.ctx._check(lib().tp_verify(self.ctx._h, self._h, _buf(proof_fixed), C.c_size_t(len(proof_fixed)),
+                                        _buf(public_inputs_mont) if public_inputs_mont else None,
+                                        C.c_size_t(len(public_inputs_mont) // 32), C.byref(ok)))
+        return bool(ok.value)
 
     def sigma_commitments(self):
         out = (C.c_char * (3 * G1_BYTES))()

@@ -63,3 +63,26 @@ def g1_serialize_unchecked(pt) -> bytes:
         out[95] |= 1 << 6
         return bytes(out)
     return pt[0].to_bytes(48, "little") + pt[1].to_bytes(48, "little")
+
+
+def g1_to_abi(pt) -> bytes:
+    """(x, y) / None -> 97-byte ABI point (infinity = (0, 1), flag 1, like GroupAffine::zero())."""
+    if pt is None:
+        return fq_to_bytes(0) + fq_to_bytes(1) + b"\x01"
+    return fq_to_bytes(pt[0]) + fq_to_bytes(pt[1]) + b"\x00"
+
+
+def g2_to_abi(pt) -> bytes:
+    """((x0, x1), (y0, y1)) / None -> 193-byte ABI G2 record."""
+    if pt is None:
+        return fq_to_bytes(0) * 2 + fq_to_bytes(1) + fq_to_bytes(0) + b"\x01"
+    (x0, x1), (y0, y1) = pt
+    return fq_to_bytes(x0) + fq_to_bytes(x1) + fq_to_bytes(y0) + fq_to_bytes(y1) + b"\x00"
+
+
+def g2_from_abi(b: bytes):
+    assert len(b) == 193
+    if b[192]:
+        return None
+    v = [fq_from_bytes(b[i:i + 48]) for i in range(0, 192, 48)]
+    return ((v[0], v[1]), (v[2], v[3]))

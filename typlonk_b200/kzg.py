@@ -3,7 +3,8 @@ over the CUDA library: same names, argument meaning and error behaviour, so the 
 read like the reference's own tests.  Scalars/points at this level are canonical Python ints /
 affine (x, y) tuples (None = infinity)."""
 from . import field as F
-from .ffi import Context, TyplonkError
+from . import ffi
+from .ffi import Context, TyplonkError  # noqa: F401
 
 
 class Srs:
@@ -25,6 +26,14 @@ class Srs:
     def g1_ref(self, offset=0, count=None):
         raw = self.handle.download(offset, count)
         return [F.g1_from_packed(raw[i:i + 96]) for i in range(0, len(raw), 96)]
+
+    def g2_ref(self):
+        """srs.rs:46-48, as ((x0, x1), (y0, y1)) canonical ints."""
+        return F.g2_from_abi(self.handle.g2()[0])
+
+    def g2s_ref(self):
+        """srs.rs:49-51."""
+        return F.g2_from_abi(self.handle.g2()[1])
 
     def __len__(self):
         return len(self.handle)
@@ -49,6 +58,13 @@ class KzgScheme:
         coeffs = _strip(polynomial)
         w, y = self.ctx.open(self.srs.handle, F.fr_vec_to_bytes(coeffs), F.fr_to_bytes(z))
         return F.g1_from_abi(w), F.fr_from_bytes(y)
+
+    def verify(self, commitment, opening, z: int) -> bool:
+        """KzgScheme::verify (lib.rs:66-81): opening = (witness point, evaluation).  The pairing is O(1) host work
+        inside the library (csrc/pairing.h)."""
+        w, y = opening
+        g2, g2s = self.srs.handle.g2()
+        return ffi.kzg_verify(g2, g2s, F.g1_to_abi(commitment), F.g1_to_abi(w), F.fr_to_bytes(y), F.fr_to_bytes(z))
 
     def identity(self):
         return self.commit([1])

@@ -17,8 +17,8 @@ CircuitDescription / Var (plonk/src/description.rs:4-16), CircuitBuilder::compil
 The tracing DSL and cycle building are host bookkeeping (out of the GPU scope, SURVEY.md 2
 #13/#15); everything numeric -- SRS, selector interpolation and commitments, sigma tables, the
 whole prover -- runs in libtyplonk_b200.  tau and the nine blinders are explicit inputs where the
-reference draws them from thread_rng (builder.rs:71, proof.rs:42-48).  `verify` (pairings) is
-out of scope for the GPU path; tests verify proofs with the CPU oracle.
+reference draws them from thread_rng (builder.rs:71, proof.rs:42-48).  `verify` (proof.rs:59-63) runs
+its circuit-sized parts on the device and the pairings on the host inside the library (csrc/verify.cu).
 """
 import struct
 from dataclasses import dataclass
@@ -181,6 +181,10 @@ class CompiledCircuit:
         pis = ([v % F.R_MOD for v in public_inputs] + [0] * self.rows)[: self.rows]
         fixed = self.handle.prove([F.fr_vec_to_bytes(c) for c in cols], F.fr_vec_to_bytes(pis))
         return Proof(fixed, pis)
+
+    def verify(self, proof: Proof) -> bool:
+        """CompiledCircuit::verify (proof.rs:59-63, 195-233)."""
+        return self.handle.verify(proof.fixed, F.fr_vec_to_bytes(proof.public_inputs))
 
 
 class CircuitDescription:
