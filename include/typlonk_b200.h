@@ -35,6 +35,8 @@ extern "C" {
 typedef struct tp_ctx tp_ctx;
 typedef struct tp_srs tp_srs;
 typedef struct tp_circuit tp_circuit;
+typedef struct tp_trace tp_trace;
+typedef struct tp_permutation_builder tp_permutation_builder;
 
 enum {
   TP_OK = 0,
@@ -46,7 +48,10 @@ enum {
   TP_ERR_GATE_UNSATISFIED = 6,/* vanishes() assert                          plonk/src/proof.rs:321,361,504-508 */
   TP_ERR_NO_DEVICE = 7,
   TP_ERR_COLLECTIVE = 8,
-  TP_ERR_BUFFER_TOO_SMALL = 9
+  TP_ERR_BUFFER_TOO_SMALL = 9,
+  TP_ERR_INVALID_TAG = 10,       /* add_constrain(..) -> Err(()) .unwrap()   permutation/src/lib.rs:48-51, plonk/src/builder.rs:155-159 */
+  TP_ERR_UNPLACED_VARIABLE = 11, /* assert!(inner.pending_eq.is_empty())     plonk/src/builder.rs:177 */
+  TP_ERR_MALFORMED = 12          /* a wire encoding that is not canonical / not on the curve */
 };
 
 #define TP_G1_BYTES 97
@@ -220,6 +225,59 @@ int tp_verify_prepared(const tp_verifier_inputs* in, const uint8_t* proof, size_
 /* The challenges verify() derives from a proof (proof.rs:235-244): alpha, beta, gamma, evaluation point. */
 int tp_proof_challenges(const uint8_t* proof, size_t proof_len, uint64_t alpha[4], uint64_t beta[4], uint64_t gamma[4],
                         uint64_t point[4]);
+
+/* ---- circuit tracing, copy constraints, witness generation (host) --------
+ * The reference records a circuit by running its closure over BuildVar, and computes a witness
+ * by running it again over ComputeVar, under a Mutex and with a println! per gate.  Here the
+ * host language records each `+` / `*` / `assert_eq` of the closure ONCE into a tp_trace (a
+ * flat gate list); padding, selector columns, the copy-constraint permutation and every
+ * witness are derived from it natively.  No device involved; feeds tp_circuit_compile and
+ * tp_prove.  Variables are dense ids: the n_inputs inputs are 0..n_inputs-1 in order. */
+enum { TP_GATE_MUL = 0, TP_GATE_ADD = 1, TP_GATE_DUMMY = 2 }; /* plonk/src/builder.rs:30-36 */
+
+/* Context::default + BuildVar::input per input (plonk/src/builder.rs:371-377, 95-99). */
+int tp_trace_create(size_t n_inputs, tp_trace** out);
+int tp_trace_destroy(tp_trace* t);
+/* BuildVar::binary_operation (plonk/src/builder.rs:339-370): appends a gate row j, gives the
+ * output a new id placed at (2, j), and places each operand at (0, j) / (1, j) -- an operand
+ * that already sits in a cell gets a fresh id there plus a copy constraint old = fresh. */
+int tp_trace_gate(tp_trace* t, int kind, uint64_t lhs, uint64_t rhs, uint64_t* out_var);
+/* The same for `count` gates in one call (out_vars may be NULL). */
+int tp_trace_gates(tp_trace* t, size_t count, const uint8_t* kinds, const uint64_t* lhs, const uint64_t* rhs,
+                   uint64_t* out_vars);
+/* Var::assert_eq on BuildVar -> Context::add_eq (plonk/src/builder.rs:427-433, 148-166): a copy
+ * constraint when both variables are placed, otherwise parked until tp_trace_finish. */
+int tp_trace_assert_eq(tp_trace* t, uint64_t a, uint64_t b);
+/* Context::finish + CircuitBuilder::fill (plonk/src/builder.rs:167-186, 47-58): resolves the
+ * parked equalities (one still unplaced -> TP_ERR_UNPLACED_VARIABLE), pads with Dummy gates to
+ * rows = the first power of two >= gates + 3 (minimum 2).  Idempotent. */
+int tp_trace_finish(tp_trace* t, size_t* rows, size_t* gates);
+/* `rows` gate kinds (TP_GATE_*), Dummy padding included. */
+int tp_trace_gate_kinds(const tp_trace* t, uint8_t* out);
+/* Selector EVALUATIONS q_l | q_r | q_o | q_m | q_c, 5 x rows Montgomery Fr, contiguous
+ * (Gate::to_row, plonk/src/builder.rs:73-84, 316-324) -- tp_circuit_compile's input. */
+int tp_trace_selectors(const tp_trace* t, uint64_t* out);
+/* PermutationBuilder::build(rows) (permutation/src/lib.rs:62-93) over the recorded copy
+ * constraints: perm[3 * rows], index = j + i * rows.  Constraint classes are visited in
+ * first-insertion order (the reference's HashMap order is random per process).  Consumes the
+ * constraints (mem::take), so a second call returns the identity. */
+int tp_trace_permutation(tp_trace* t, uint64_t* perm);
+/* The witness half of CompiledCircuit::prove (plonk/src/proof.rs:33-49; ComputeVar,
+ * plonk/src/builder.rs:380-397): replays the gates over `inputs` (n_inputs Montgomery Fr) and
+ * writes the three advice columns in evaluation form (rows Fr each): left | right | value per
+ * gate, zeros up to rows - 3, then blinders[3k..3k+3] for column k.  Like the reference's
+ * ComputeVar::assert_eq, equalities are NOT checked here. */
+int tp_trace_witness(const tp_trace* t, const uint64_t* inputs, size_t n_inputs, const uint64_t* blinders,
+                     uint64_t* const advice[3]);
+
+/* The permutation crate's builder on its own (permutation/src/lib.rs:28-93): with_rows,
+ * add_row, add_constrain (a tag with i > 3 or j >= rows -> TP_ERR_INVALID_TAG), build. */
+int tp_permutation_builder_create(size_t rows, tp_permutation_builder** out);
+int tp_permutation_builder_destroy(tp_permutation_builder* b);
+int tp_permutation_builder_add_row(tp_permutation_builder* b);
+int tp_permutation_builder_add_constrain(tp_permutation_builder* b, size_t left_i, size_t left_j, size_t right_i,
+                                         size_t right_j);
+int tp_permutation_builder_build(tp_permutation_builder* b, size_t size, uint64_t* perm);
 
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* Measured dependent-free IMAD throughput of this device (instructions/s), for rooflines. */

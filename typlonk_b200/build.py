@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
 LIB = LIBDIR / "libtyplonk_b200.so"
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu", "trace.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -33,7 +33,7 @@ def _nvcc():
 
 def _stamp():
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) +
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) +
                     [ROOT.parent / "include" / "typlonk_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
@@ -55,7 +55,7 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     objdir.mkdir(exist_ok=True)
 
     def compile_one(src):
-        obj = objdir / (src.replace(".cu", ".o"))
+        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

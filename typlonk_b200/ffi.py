@@ -18,7 +18,8 @@ PHASES = ["msm_total", "msm_sort", "msm_accum", "msm_reduce", "ntt", "quotient",
 ERRORS = {
     1: "TP_ERR_INVALID_ARG", 2: "TP_ERR_CUDA", 3: "TP_ERR_SRS_TOO_SHORT", 4: "TP_ERR_EMPTY_POLY",
     5: "TP_ERR_ZERO_DENOMINATOR", 6: "TP_ERR_GATE_UNSATISFIED", 7: "TP_ERR_NO_DEVICE",
-    8: "TP_ERR_COLLECTIVE", 9: "TP_ERR_BUFFER_TOO_SMALL",
+    8: "TP_ERR_COLLECTIVE", 9: "TP_ERR_BUFFER_TOO_SMALL", 10: "TP_ERR_INVALID_TAG",
+    11: "TP_ERR_UNPLACED_VARIABLE", 12: "TP_ERR_MALFORMED",
 }
 
 # every symbol include/typlonk_b200.h declares
@@ -30,6 +31,10 @@ SYMBOLS = [
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
     "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option", "tp_ctx_get_stat",
     "tp_srs_g2", "tp_srs_set_g2", "tp_kzg_verify", "tp_pairing_check", "tp_verify", "tp_verify_prepared", "tp_proof_challenges",
+    "tp_trace_create", "tp_trace_destroy", "tp_trace_gate", "tp_trace_gates", "tp_trace_assert_eq", "tp_trace_finish",
+    "tp_trace_gate_kinds", "tp_trace_selectors", "tp_trace_permutation", "tp_trace_witness",
+    "tp_permutation_builder_create", "tp_permutation_builder_destroy", "tp_permutation_builder_add_row",
+    "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -120,6 +125,130 @@ def proof_challenges(proof_fixed: bytes):
     if rc != 0:
         raise TyplonkError(rc, "tp_proof_challenges: malformed proof")
     return tuple(bytes(o) for o in outs)
+
+
+GATE_MUL, GATE_ADD, GATE_DUMMY = 0, 1, 2
+
+
+class Trace:
+    """tp_trace: a circuit recorded once as a flat gate list; padding, selectors, the copy-constraint permutation
+    and witnesses come from it natively (plonk/src/builder.rs:119-188, 339-397; permutation/src/lib.rs:62-93;
+    plonk/src/proof.rs:33-49).  Host only."""
+
+    def __init__(self, n_inputs: int):
+        self._h = C.c_void_p()
+        self.n_inputs = n_inputs
+        self.rows = None
+        self.gate_count = None
+        rc = lib().tp_trace_create(C.c_size_t(n_inputs), C.byref(self._h))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.tp_trace_destroy(self._h)
+            self._h = None
+
+    def gate(self, kind: int, lhs: int, rhs: int) -> int:
+        out = C.c_uint64(0)
+        rc = lib().tp_trace_gate(self._h, C.c_int(kind), C.c_uint64(lhs), C.c_uint64(rhs), C.byref(out))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_gate(%d, %d, %d)" % (kind, lhs, rhs))
+        return out.value
+
+    def gates(self, kinds, lhs, rhs):
+        """Bulk form over numpy arrays (uint8, uint64, uint64); returns the output ids (uint64)."""
+        import numpy as np
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        lhs = np.ascontiguousarray(lhs, dtype=np.uint64)
+        rhs = np.ascontiguousarray(rhs, dtype=np.uint64)
+        assert len(kinds) == len(lhs) == len(rhs)
+        out = np.empty(len(kinds), dtype=np.uint64)
+        rc = lib().tp_trace_gates(self._h, C.c_size_t(len(kinds)), _buf(kinds), _buf(lhs), _buf(rhs), _buf(out))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_gates")
+        return out
+
+    def assert_eq(self, a: int, b: int):
+        rc = lib().tp_trace_assert_eq(self._h, C.c_uint64(a), C.c_uint64(b))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_assert_eq(%d, %d)" % (a, b))
+
+    def finish(self):
+        rows, gates = C.c_size_t(0), C.c_size_t(0)
+        rc = lib().tp_trace_finish(self._h, C.byref(rows), C.byref(gates))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_finish")
+        self.rows, self.gate_count = rows.value, gates.value
+        return self.rows, self.gate_count
+
+    def gate_kinds(self) -> bytes:
+        out = (C.c_char * self.rows)()
+        rc = lib().tp_trace_gate_kinds(self._h, out)
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_gate_kinds")
+        return bytes(out)
+
+    def selectors(self) -> bytearray:
+        """5 x rows Montgomery Fr, contiguous (q_l | q_r | q_o | q_m | q_c)."""
+        out = bytearray(5 * self.rows * 32)
+        rc = lib().tp_trace_selectors(self._h, _buf(out))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_selectors")
+        return out
+
+    def permutation(self) -> bytearray:
+        """perm[3 * rows] as little-endian u64 (consumes the constraints, like the reference's build)."""
+        out = bytearray(3 * self.rows * 8)
+        rc = lib().tp_trace_permutation(self._h, _buf(out))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_permutation")
+        return out
+
+    def witness(self, inputs_mont: bytes, blinders_mont: bytes):
+        """Three advice columns (rows x 32 B Montgomery each) from n_inputs inputs and nine blinders."""
+        assert len(inputs_mont) == 32 * self.n_inputs and len(blinders_mont) == 9 * 32
+        cols = [bytearray(self.rows * 32) for _ in range(3)]
+        ptrs = (C.c_void_p * 3)(*[C.addressof((C.c_char * len(c)).from_buffer(c)) for c in cols])
+        rc = lib().tp_trace_witness(self._h, _buf(inputs_mont), C.c_size_t(self.n_inputs), _buf(blinders_mont), ptrs)
+        if rc != 0:
+            raise TyplonkError(rc, "tp_trace_witness")
+        return cols
+
+
+class NativePermutationBuilder:
+    """tp_permutation_builder: PermutationBuilder<3> (permutation/src/lib.rs:28-93).  Host only."""
+
+    def __init__(self, rows=0):
+        self._h = C.c_void_p()
+        rc = lib().tp_permutation_builder_create(C.c_size_t(rows), C.byref(self._h))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_permutation_builder_create")
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.tp_permutation_builder_destroy(self._h)
+            self._h = None
+
+    def add_row(self):
+        lib().tp_permutation_builder_add_row(self._h)
+
+    def add_constrain(self, left, right) -> bool:
+        rc = lib().tp_permutation_builder_add_constrain(self._h, C.c_size_t(left[0]), C.c_size_t(left[1]),
+                                                        C.c_size_t(right[0]), C.c_size_t(right[1]))
+        if rc == 10:
+            return False
+        if rc != 0:
+            raise TyplonkError(rc, "tp_permutation_builder_add_constrain")
+        return True
+
+    def build(self, size: int):
+        import struct
+        out = bytearray(3 * size * 8)
+        rc = lib().tp_permutation_builder_build(self._h, C.c_size_t(size), _buf(out))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_permutation_builder_build")
+        return list(struct.unpack("<%dQ" % (3 * size), out))
 
 
 class VerifierInputs(C.Structure):

@@ -14,9 +14,13 @@ CircuitDescription / Var (plonk/src/description.rs:4-16), CircuitBuilder::compil
     circuit = Circuit.build(ctx, tau)                 # description.rs:6-8
     proof = circuit.prove([3, 4, 5], [0], blinders)   # proof.rs:26
 
-The tracing DSL and cycle building are host bookkeeping (out of the GPU scope, SURVEY.md 2
-#13/#15); everything numeric -- SRS, selector interpolation and commitments, sigma tables, the
-whole prover -- runs in libtyplonk_b200.  tau and the nine blinders are explicit inputs where the
+The circuit closure is run ONCE over `TraceVar`, which records every `+` / `*` / `assert_eq` into the
+library's native tracer (csrc/trace.cpp); padding, selector columns, the copy-constraint
+permutation and every proof's witness columns come from that recording in C++ (the reference re-runs
+the closure over ComputeVar for every proof, builder.rs:380-397).  `BuildVar` / `ComputeVar` /
+`_Context` below restate the reference's two-pass scheme in Python and are what the CPU tests
+compare the native tracer with.  Everything numeric -- SRS, selector interpolation and commitments,
+sigma tables, the whole prover -- runs on the device in libtyplonk_b200.  tau and the nine blinders are explicit inputs where the
 reference draws them from thread_rng (builder.rs:71, proof.rs:42-48).  `verify` (proof.rs:59-63) runs
 its circuit-sized parts on the device and the pairings on the host inside the library (csrc/verify.cu).
 """
@@ -25,9 +29,9 @@ from dataclasses import dataclass
 from typing import List
 
 from . import field as F
-from .ffi import Context, GateUnsatisfied, PROOF_FIXED_BYTES  # noqa: F401
+from .ffi import Context, GateUnsatisfied, PROOF_FIXED_BYTES, GATE_ADD, GATE_MUL, Trace  # noqa: F401
 from .kzg import Srs
-from .permutation import PermutationBuilder
+from .permutation import Permutation, PermutationBuilder
 
 GATE_ROWS = {"Mul": (0, 0, 1, 1, 0), "Add": (1, 1, 1, 0, 0), "Dummy": (0, 0, 0, 0, 0)}  # builder.rs:318-324
 
@@ -141,6 +145,28 @@ class ComputeVar(Var):
         pass
 
 
+class TraceVar(Var):
+    """A variable of the native tracer: an id in a tp_trace (BuildVar, builder.rs:327-378, 427-433)."""
+
+    def __init__(self, trace: Trace, vid: int):
+        self.trace, self.id = trace, vid
+
+    def clone(self):
+        return TraceVar(self.trace, self.id)
+
+    def __add__(self, rhs):
+        return TraceVar(self.trace, self.trace.gate(GATE_ADD, self.id, rhs.id))
+
+    def __mul__(self, rhs):
+        return TraceVar(self.trace, self.trace.gate(GATE_MUL, self.id, rhs.id))
+
+    def assert_eq(self, other):
+        self.trace.assert_eq(self.id, other.id)
+
+
+KIND_NAMES = {0: "Mul", 1: "Add", 2: "Dummy"}
+
+
 @dataclass
 class Proof:
     """proof.rs:85-95 as bytes: `fixed` is the 1472-byte block tp_prove writes, followed by the
@@ -156,15 +182,21 @@ class Proof:
 class CompiledCircuit:
     """plonk/src/lib.rs:18-26."""
 
-    def __init__(self, desc, ctx, srs, handle, rows, fixed_commitments, gates, perm):
+    def __init__(self, desc, ctx, srs, handle, rows, fixed_commitments, gates, perm, native_trace=None):
         self.desc, self.ctx, self.srs, self.handle = desc, ctx, srs, handle
         self.rows = rows
         self.fixed_commitments = fixed_commitments
         self.gates = gates
         self.perm = perm
+        self.native_trace = native_trace
+
+    def witness_bytes(self, inputs, blinders):
+        """proof.rs:33-49 through tp_trace_witness: three columns of rows x 32 B Montgomery limbs."""
+        assert len(blinders) == 9
+        return self.native_trace.witness(F.fr_vec_to_bytes(inputs), F.fr_vec_to_bytes(blinders))
 
     def witness(self, inputs, blinders):
-        """proof.rs:33-49."""
+        """proof.rs:33-49 by re-running the closure over ComputeVar, as the reference does (canonical ints)."""
         advice = [[], [], []]
         self.desc.run([ComputeVar(v, advice) for v in inputs])
         assert len(blinders) == 9
@@ -177,9 +209,12 @@ class CompiledCircuit:
     def prove(self, inputs, public_inputs, blinders) -> Proof:
         """CompiledCircuit::prove (proof.rs:26-57).  Raises GateUnsatisfied where the reference
         panics in `vanishes`."""
-        cols = self.witness(inputs, blinders)
+        if self.native_trace is not None:
+            cols = self.witness_bytes(inputs, blinders)
+        else:
+            cols = [F.fr_vec_to_bytes(c) for c in self.witness(inputs, blinders)]
         pis = ([v % F.R_MOD for v in public_inputs] + [0] * self.rows)[: self.rows]
-        fixed = self.handle.prove([F.fr_vec_to_bytes(c) for c in cols], F.fr_vec_to_bytes(pis))
+        fixed = self.handle.prove(cols, F.fr_vec_to_bytes(pis))
         return Proof(fixed, pis)
 
     def verify(self, proof: Proof) -> bool:
@@ -203,12 +238,23 @@ class CircuitDescription:
         return gates, permutation.build(len(gates))
 
     @classmethod
+    def trace_native(cls) -> Trace:
+        """The closure recorded once by the library's tracer (finished: padded, equalities resolved)."""
+        t = Trace(cls.INPUTS)
+        cls.run([TraceVar(t, k) for k in range(cls.INPUTS)])
+        t.finish()
+        return t
+
+    @classmethod
     def build(cls, ctx: Context, tau: int) -> CompiledCircuit:
         """CircuitBuilder::compile (builder.rs:60-113) with the SRS secret as an input."""
-        gates, perm = cls.trace()
-        rows = len(gates)
+        t = cls.trace_native()
+        rows = t.rows
         srs = Srs.from_secret(ctx, tau, rows)
-        sel = [F.fr_vec_to_bytes([GATE_ROWS[g][k] for g in gates]) for k in range(5)]
-        perm_bytes = struct.pack("<%dQ" % len(perm.perm), *perm.perm)
+        sel_all = t.selectors()
+        sel = [bytes(sel_all[k * rows * 32:(k + 1) * rows * 32]) for k in range(5)]
+        perm_bytes = bytes(t.permutation())
         handle, fixed = ctx.circuit_compile(srs.handle, sel, perm_bytes, rows)
-        return CompiledCircuit(cls, ctx, srs, handle, rows, [F.g1_from_abi(c) for c in fixed], gates, perm)
+        gates = [KIND_NAMES[k] for k in t.gate_kinds()]
+        perm = Permutation(list(struct.unpack("<%dQ" % (3 * rows), perm_bytes)))
+        return CompiledCircuit(cls, ctx, srs, handle, rows, [F.g1_from_abi(c) for c in fixed], gates, perm, t)

@@ -3,16 +3,19 @@ circuit `let [x,y]=inputs; for _ in 0..G { x = x * y.clone(); }` with G = n - 3 
 [3, 5], public inputs [0]; tau / blinders / sweep inputs are `Fr::rand` streams of
 `StdRng::seed_from_u64(1|2|3|4)`.
 
-`mul_chain_direct` builds the gate list, copy constraints and witness columns of that circuit
-without running the tracing DSL (same result, checked against the tracer in the CPU tests), so
-that 2^20..2^22-gate setups take seconds of host time."""
+`mul_chain_direct` records that circuit into the library's native tracer with one bulk call
+(tp_trace_gates) instead of running the Python closure gate by gate -- same recording, checked
+against the closure in the CPU tests -- so that 2^20..2^22-gate setups take a fraction of a second
+of host time.  `mul_chain_structure` / `mul_chain_witness` are the pure-Python statement of the same
+circuit the tests compare with."""
 import struct
 
 from . import field as F
-from .ffi import Context, fr_rand_stream
+from .ffi import GATE_MUL, Context, Trace, fr_rand_stream
 from .kzg import Srs
 from .permutation import PermutationBuilder
-from .plonk import GATE_ROWS, CircuitDescription, CompiledCircuit
+from .permutation import Permutation
+from .plonk import KIND_NAMES, CircuitDescription, CompiledCircuit
 
 SEED_TAU, SEED_BLINDERS, SEED_MSM, SEED_NTT = 1, 2, 3, 4
 
@@ -66,18 +69,32 @@ def mul_chain_witness(gates: int, n: int, x0=3, y=5, blind=None):
     return out
 
 
+def mul_chain_trace(gates: int) -> Trace:
+    """The mul-chain closure recorded in bulk.  Variable ids follow builder.rs:339-370: inputs x = 0, y = 1;
+    gate 0 places both and outputs id 2; every later gate allocates its output and then one copy id per
+    (already placed) operand, so gate j >= 1 outputs id 3j."""
+    import numpy as np
+    t = Trace(2)
+    if gates:
+        j = np.arange(gates, dtype=np.uint64)
+        out_ids = np.where(j == 0, 2, 3 * j).astype(np.uint64)
+        lhs = np.concatenate([np.zeros(1, dtype=np.uint64), out_ids[:-1]])
+        got = t.gates(np.full(gates, GATE_MUL, dtype=np.uint8), lhs, np.ones(gates, dtype=np.uint64))
+        assert (got == out_ids).all()
+    t.finish()
+    return t
+
+
 def mul_chain_direct(ctx: Context, log_n: int, tau_value=None) -> CompiledCircuit:
     n = 1 << log_n
     gates = n - 3
-    gate_list, perm = mul_chain_structure(gates)
+    t = mul_chain_trace(gates)
+    assert t.rows == n
     srs = Srs.from_secret(ctx, tau() if tau_value is None else tau_value, n)
-    one = F.fr_to_bytes(1)
-    zero = bytes(32)
-    on = one * gates + zero * (n - gates)
-    off = zero * n
-    sel = [off, off, on, on, off]  # Mul = [0, 0, 1, 1, 0]
-    assert GATE_ROWS["Mul"] == (0, 0, 1, 1, 0)
-    perm_bytes = struct.pack("<%dQ" % len(perm.perm), *perm.perm)
+    sel_all = t.selectors()
+    sel = [bytes(sel_all[k * n * 32:(k + 1) * n * 32]) for k in range(5)]
+    perm_bytes = bytes(t.permutation())
     handle, fixed = ctx.circuit_compile(srs.handle, sel, perm_bytes, n)
+    perm = Permutation(list(struct.unpack("<%dQ" % (3 * n), perm_bytes)))
     return CompiledCircuit(mul_chain_description(gates), ctx, srs, handle, n,
-                           [F.g1_from_abi(c) for c in fixed], gate_list, perm)
+                           [F.g1_from_abi(c) for c in fixed], [KIND_NAMES[k] for k in t.gate_kinds()], perm, t)
