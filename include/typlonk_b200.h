@@ -279,6 +279,33 @@ int tp_permutation_builder_add_constrain(tp_permutation_builder* b, size_t left_
                                          size_t right_j);
 int tp_permutation_builder_build(tp_permutation_builder* b, size_t size, uint64_t* perm);
 
+/* ---- wire formats --------------------------------------------
+ * The reference derives no (de)serialisation for Proof or Srs, so the framing is ours; every
+ * item is encoded the way ark-serialize 0.3 writes that type uncompressed (the encoding the
+ * reference's own transcript uses for G1, plonk/src/proof/challenges.rs:17-22): Fr = 32 B LE
+ * canonical; G1 = x | y, 48 B LE canonical each, bit 6 of the last byte = infinity; G2 =
+ * x.c0 | x.c1 | y.c0 | y.c1 likewise; Vec = u64 LE length + items. */
+#define TP_WIRE_G1_BYTES 96
+#define TP_WIRE_G2_BYTES 192
+/* Proof (plonk/src/proof.rs:85-95) = the TP_PROOF_FIXED_BYTES block of tp_prove | Vec<Fr> of
+ * the n-padded public inputs.  Host only.  `public_inputs` are Montgomery limbs. */
+int tp_proof_encoded_size(size_t n_public, size_t* bytes);
+int tp_proof_encode(const uint8_t* fixed, const uint64_t* public_inputs, size_t n_public, uint8_t* out, size_t cap,
+                    size_t* written);
+/* Checked decoding: exact length, every scalar < r, every coordinate < q, every point on the
+ * curve (or flagged infinity), no compressed-form flag -> otherwise TP_ERR_MALFORMED.
+ * `public_inputs_out` (Montgomery, capacity cap_public elements) and `fixed_out` may be NULL. */
+int tp_proof_decode(const uint8_t* bytes, size_t len, uint8_t fixed_out[TP_PROOF_FIXED_BYTES],
+                    uint64_t* public_inputs_out, size_t cap_public, size_t* n_public);
+/* Srs (kzg/src/srs.rs:8-14) = Vec<G1> | G2 | tau G2.  The device converts the points out of /
+ * into Montgomery form and validates them, one point per thread.  check: 0 = canonical
+ * encoding only (ark `deserialize_unchecked`), 1 = + on the curve, 2 = + in the prime-order
+ * subgroup ([r]P = 0; ark's checked deserialisation).  A rejected point -> TP_ERR_MALFORMED
+ * with its index in tp_last_error. */
+int tp_srs_serialized_size(const tp_srs* srs, size_t* bytes);
+int tp_srs_serialize(tp_ctx* ctx, const tp_srs* srs, uint8_t* out, size_t cap, size_t* written);
+int tp_srs_deserialize(tp_ctx* ctx, const uint8_t* bytes, size_t len, int check, tp_srs** out);
+
 /* ---- helpers ---------------------------------------------------------------------------- */
 /* Measured dependent-free IMAD throughput of this device (instructions/s), for rooflines. */
 int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s);

@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
 LIB = LIBDIR / "libtyplonk_b200.so"
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu", "trace.cpp"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu", "wire.cu", "trace.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -194,7 +194,9 @@ int tp_launch_count(tp_ctx* ctx, uint64_t* out) {
 // ---- SRS ------------------------------------------------------------------------------------
 // Allocates the SRS with as many fixed-base table levels as the MSM plan wants and the device can
 // spare (at most ~45 % of what is free; level 0 alone when nothing more fits).
-static int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
+extern "C++" {
+namespace tp {
+int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
   tp_srs* s = new tp_srs();
   s->len = len;
   size_t free_b = 0, total_b = 0;
@@ -216,6 +218,8 @@ static int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
   delete s;
   return fail(ctx, TP_ERR_CUDA, "srs: out of device memory");
 }
+}  // namespace tp
+}  // extern "C++"
 
 int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out) {
   if (!out || !tau) return fail(ctx, TP_ERR_INVALID_ARG, "srs_from_secret: null argument");

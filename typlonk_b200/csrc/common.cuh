@@ -226,6 +226,12 @@ int sigma_tables_dev(tp_ctx* ctx, const uint64_t* perm_dev, size_t n, const Fr* 
 int pad_copy_dev(tp_ctx* ctx, const Fr* in, size_t len, Fr* out, size_t out_len);
 int rotate_copy_dev(tp_ctx* ctx, const Fr* in, size_t n, size_t shift, Fr* out);
 void msm_choose_tables(size_t len, size_t table_len, size_t budget_bytes, unsigned* c_out, unsigned* levels_out);
+// api.cu: device allocation of an SRS with the fixed-base table levels the MSM plan wants
+int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out);
+// wire.cu: Montgomery SRS records <-> ark-serialize 0.3 uncompressed records, on the device
+int g1_to_wire_dev(tp_ctx* ctx, const G1Affine* in, size_t len, void* out_dev);
+int g1_from_wire_dev(tp_ctx* ctx, const void* in_dev, size_t len, int check, G1Affine* out, size_t* rejected,
+                     size_t* first_rejected);
 // srs.cu
 int srs_generate_dev(tp_ctx* ctx, const tph::HFr& tau, size_t len, G1Affine* out);
 int srs_build_levels_dev(tp_ctx* ctx, tp_srs* srs);

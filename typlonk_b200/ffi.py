@@ -35,6 +35,8 @@ SYMBOLS = [
     "tp_trace_gate_kinds", "tp_trace_selectors", "tp_trace_permutation", "tp_trace_witness",
     "tp_permutation_builder_create", "tp_permutation_builder_destroy", "tp_permutation_builder_add_row",
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
+    "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
+    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
@@ -125,6 +127,39 @@ def proof_challenges(proof_fixed: bytes):
     if rc != 0:
         raise TyplonkError(rc, "tp_proof_challenges: malformed proof")
     return tuple(bytes(o) for o in outs)
+
+
+class Malformed(TyplonkError):
+    """A wire encoding that is not canonical / not on the curve / of the wrong length (TP_ERR_MALFORMED)."""
+
+
+def proof_encode(fixed: bytes, public_inputs_mont: bytes) -> bytes:
+    """tp_proof_encode: the 1472-byte block + Vec<Fr> of public inputs.  Host only."""
+    n = len(public_inputs_mont) // 32
+    need = C.c_size_t(0)
+    lib().tp_proof_encoded_size(C.c_size_t(n), C.byref(need))
+    out = (C.c_char * need.value)()
+    rc = lib().tp_proof_encode(_buf(fixed), _buf(public_inputs_mont) if n else None, C.c_size_t(n), out,
+                               C.c_size_t(need.value), None)
+    if rc != 0:
+        raise TyplonkError(rc, "tp_proof_encode")
+    return bytes(out)
+
+
+def proof_decode(raw: bytes):
+    """tp_proof_decode (checked): -> (fixed block, public inputs as Montgomery bytes).  Raises Malformed."""
+    n = C.c_size_t(0)
+    rc = lib().tp_proof_decode(_buf(raw), C.c_size_t(len(raw)), None, None, C.c_size_t(0), C.byref(n))
+    if rc == 12:
+        raise Malformed(rc, "tp_proof_decode: malformed proof encoding")
+    if rc != 0:
+        raise TyplonkError(rc, "tp_proof_decode")
+    fixed = (C.c_char * PROOF_FIXED_BYTES)()
+    pis = (C.c_char * (32 * n.value or 1))()
+    rc = lib().tp_proof_decode(_buf(raw), C.c_size_t(len(raw)), fixed, pis, C.c_size_t(n.value), C.byref(n))
+    if rc != 0:
+        raise TyplonkError(rc, "tp_proof_decode")
+    return bytes(fixed), bytes(pis)[: 32 * n.value]
 
 
 GATE_MUL, GATE_ADD, GATE_DUMMY = 0, 1, 2
@@ -442,6 +477,16 @@ class Context:
         self._check(lib().tp_circuit_load(self._h, srs._h, sel, idp, sgp, cos, C.c_size_t(n), C.byref(h)))
         return CircuitHandle(self, h, n, srs)
 
+    def srs_deserialize(self, raw, check=2):
+        """tp_srs_deserialize: ark-serialize 0.3 uncompressed Vec<G1> | G2 | tau G2 -> device SRS.
+        check: 0 canonical only, 1 + on curve, 2 + prime-order subgroup.  Raises Malformed."""
+        h = C.c_void_p()
+        rc = lib().tp_srs_deserialize(self._h, _buf(raw), C.c_size_t(len(raw)), C.c_int(check), C.byref(h))
+        if rc == 12:
+            raise Malformed(rc, lib().tp_last_error(self._h).decode())
+        self._check(rc)
+        return SrsHandle(self, h)
+
     def circuit_compile(self, srs, selector_evals, perm_u64: bytes, n):
         keep = [_buf(b) for b in selector_evals]
         sel = (C.c_void_p * 5)(*[C.cast(x, C.c_void_p) for x in keep])
@@ -461,6 +506,14 @@ class SrsHandle:
         v = C.c_size_t()
         lib().tp_srs_len(self._h, C.byref(v))
         return v.value
+
+    def serialize(self) -> bytearray:
+        """tp_srs_serialize: u64 count | count x 96 B G1 | G2 | tau G2 (ark-serialize 0.3 uncompressed)."""
+        need = C.c_size_t(0)
+        lib().tp_srs_serialized_size(self._h, C.byref(need))
+        out = bytearray(need.value)
+        self.ctx._check(lib().tp_srs_serialize(self.ctx._h, self._h, _buf(out), C.c_size_t(len(out)), None))
+        return out
 
     def download(self, offset=0, count=None) -> bytes:
         count = len(self) - offset if count is None else count

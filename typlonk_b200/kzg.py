@@ -23,6 +23,15 @@ class Srs:
     def from_points(cls, ctx: Context, points) -> "Srs":
         return cls(ctx, ctx.srs_upload(b"".join(F.g1_to_packed(p) for p in points)))
 
+    def to_bytes(self) -> bytes:
+        """Vec<G1> | G2 | tau G2 in ark-serialize 0.3 uncompressed encoding (tp_srs_serialize)."""
+        return bytes(self.handle.serialize())
+
+    @classmethod
+    def from_bytes(cls, ctx: Context, raw, check=2) -> "Srs":
+        """tp_srs_deserialize: validated on the device (check = 2: on the curve and in the prime-order subgroup)."""
+        return cls(ctx, ctx.srs_deserialize(raw, check))
+
     def g1_ref(self, offset=0, count=None):
         raw = self.handle.download(offset, count)
         return [F.g1_from_packed(raw[i:i + 96]) for i in range(0, len(raw), 96)]

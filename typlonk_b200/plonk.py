@@ -29,7 +29,8 @@ from dataclasses import dataclass
 from typing import List
 
 from . import field as F
-from .ffi import Context, GateUnsatisfied, PROOF_FIXED_BYTES, GATE_ADD, GATE_MUL, Trace  # noqa: F401
+from .ffi import (Context, GateUnsatisfied, PROOF_FIXED_BYTES, GATE_ADD, GATE_MUL, Trace,  # noqa: F401
+                  proof_decode, proof_encode)
 from .kzg import Srs
 from .permutation import Permutation, PermutationBuilder
 
@@ -175,8 +176,15 @@ class Proof:
     public_inputs: List[int]
 
     def to_bytes(self) -> bytes:
-        return (self.fixed + struct.pack("<Q", len(self.public_inputs)) +
-                b"".join(v.to_bytes(32, "little") for v in self.public_inputs))
+        """tp_proof_encode (the additive `Proof::to_bytes` of SURVEY.md 8 f4)."""
+        return proof_encode(self.fixed, F.fr_vec_to_bytes(self.public_inputs))
+
+    @classmethod
+    def from_bytes(cls, raw: bytes) -> "Proof":
+        """tp_proof_decode: checked (canonical scalars and coordinates, points on the curve, exact length);
+        raises ffi.Malformed otherwise."""
+        fixed, pis = proof_decode(raw)
+        return cls(fixed, F.fr_vec_from_bytes(pis))
 
 
 class CompiledCircuit:
