@@ -284,6 +284,27 @@ def main():
         verify = {"first_call_ms": round(tv[0], 2), "ms": round(min(tv[1:]), 2), "accepted": True,
                   "note": "first call includes the 8 circuit-commitment MSMs, cached afterwards"}
 
+    # BASELINE.json's metric names two more numbers next to the prove time: G1 MSM Mpts/s and NTT GB/s (algorithmic
+    # 64 * N bytes per transform).  Measured here on the prover's own SRS and a witness column, device
+    # resident, after the timed region; the full size sweeps are `--sweep` / typlonk_b200/sweep.py.
+    standalone = None
+    if world == 1:
+        def per_call(fn, reps=5):
+            fn()
+            ms, _ = timed(fn, reps)
+            return ms / reps
+        scal = devt[2].clone()
+        msm_ms = per_call(lambda: ctx.commit_dev(circuit.srs.handle, scal.data_ptr(), n))
+        ntt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n))
+        intt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, inverse=True))
+        cos_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, coset_mont=F.fr_to_bytes(7)))
+        standalone = {"log_n": log_n,
+                      "msm_ms": round(msm_ms, 4), "msm_mpts_per_s": round(n / msm_ms / 1e3, 1),
+                      "ntt_ms": round(ntt_ms, 4), "ntt_gb_per_s": round(64.0 * n / ntt_ms / 1e6, 1),
+                      "intt_ms": round(intt_ms, 4), "coset_ntt_ms": round(cos_ms, 4),
+                      "ntt_hbm_frac": round(64.0 * n / ntt_ms / 1e6 / _peaks()[0], 4)}
+        del scal
+
     ms_step = ms_total / args.steps
     hbm_peak, peak_kind = _peaks()
     # dominant kernel: MSM bucket accumulation.  Algorithmic bytes per MSM = 128 B / point
@@ -336,6 +357,7 @@ def main():
         "imad_peak_per_s": imad_wide,
         "proof_sha256": __import__("hashlib").sha256(proof).hexdigest()[:16],
         "verify": verify,
+        "standalone": standalone,
         "cpu_baseline": None,
     }
     if rank == 0 and not args.no_cpu_baseline and world == 1:

@@ -29,6 +29,22 @@ int main() {
   { uint64_t q4[24] = {0}; for (int i = 0; i < 12; i++) { uint64_t c = 0; for (int j = 0; j < 12; j++) { u128 t = (u128)q2[i] * q2[j] + q4[i + j] + c; q4[i + j] = (uint64_t)t; c = (uint64_t)(t >> 64); } q4[i + 12] += c; }
     for (int i = 0; i < 24; i++) { uint64_t c = 0; for (int j = 0; j < 12; j++) { u128 t = (u128)q4[i] * q2[j] + q6[i + j] + c; q6[i + j] = (uint64_t)t; c = (uint64_t)(t >> 64); } q6[i + 12] += c; } }
   CHECK("conj == x^(q^6)", x.conj() == x.pow(q6, 36));
+  CHECK("frob1 == x^q", x.frob1() == x.pow(FQ_PARAMS.mod, 6));
+  CHECK("frob1 o frob1 == frob2", x.frob1().frob1() == x.frob2());
+  {
+    Fq12 c = x.conj() * x.inv();   // easy part: lands in the cyclotomic subgroup
+    c = c.frob2() * c;
+    CHECK("cyclotomic: inverse == conjugate", (c * c.conj()).is_one());
+    CHECK("cyclotomic_sqr == sqr", c.cyclotomic_sqr() == c.sqr());
+    Fq12 c2 = c.sqr() * y.conj() * y.inv();
+    c2 = c2.frob2() * c2;
+    CHECK("cyclotomic_sqr == sqr (2)", c2.cyclotomic_sqr() == c2.sqr());
+    uint64_t xabs[1] = {PAIRING_X_ABS};
+    CHECK("cyclotomic_exp_x == conj(pow |x|)", c.cyclotomic_exp_x() == c.pow(xabs, 1).conj());
+    uint64_t three[1] = {3};
+    CHECK("fast final exponentiation == reference^3", final_exponentiation(x) == final_exponentiation_reference(x).pow(three, 1));
+    CHECK("fast final exponentiation == reference^3 (2)", final_exponentiation(z) == final_exponentiation_reference(z).pow(three, 1));
+  }
   G2Aff g2 = g2_generator();
   CHECK("g2 generator on twist", g2_on_curve(g2));
   G2Aff rg2 = g2_mul(g2, FR_PARAMS.mod, 4);

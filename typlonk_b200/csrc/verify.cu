@@ -11,6 +11,8 @@
 #include "pairing.h"
 #include "transcript.h"
 
+#include <future>
+
 using namespace tp;
 using namespace tph;
 
@@ -116,11 +118,23 @@ bool verify_host(const SrsPairing& sp, const VerifierValues& v, const ParsedProo
   unsigned log_n = 0;
   while (((uint64_t)1 << log_n) < v.n) log_n++;
   HFr omega = omega_for_log(log_n);
-  // verify_openings (proof.rs:245-281)
-  for (int i = 0; i < 3; i++)
-    if (!kzg_check(sp, gen, p.com[i], p.wit[i], p.ev[i], zeta)) return false;
-  if (!kzg_check(sp, gen, p.com[3], p.wit[3], p.ev[3], zeta)) return false;
-  if (!kzg_check(sp, gen, p.com[3], p.wit[4], p.ev[4], zeta * omega)) return false;
+  // verify_openings (proof.rs:245-281).  The five checks are independent of each other and of the linearisation
+  // commitment below (each is two scalar multiplications, a two-pair Miller loop and a final exponentiation of pure
+  // host arithmetic), so they run on their own threads while this one assembles the commitment.
+  const HFr zeta_omega = zeta * omega;
+  std::future<bool> openings[5];
+  for (int i = 0; i < 5; i++) {
+    const G1Aff* com = &p.com[i < 3 ? i : 3];
+    const HFr* at = i == 4 ? &zeta_omega : &zeta;
+    openings[i] = std::async(std::launch::async, [&sp, &gen, &p, com, at, i] {
+      return kzg_check(sp, gen, *com, p.wit[i], p.ev[i], *at);
+    });
+  }
+  auto openings_ok = [&openings] {
+    bool ok = true;
+    for (auto& f : openings) ok &= f.get();
+    return ok;
+  };
   // linearisation_commitment (proof.rs:441-503)
   const HFr a = p.ev[0], b = p.ev[1], c = p.ev[2], zw = p.ev[4];
   auto mul = [](const G1Aff& g, const HFr& k) { return g1_mul_fr(g1_from_aff(g), k); };
@@ -142,7 +156,7 @@ bool verify_host(const SrsPairing& sp, const VerifierValues& v, const ParsedProo
   HFr constant = alpha * (l3 * (c + gamma) * zw) + l0 * alpha2 + v.public_eval;
   HG1 r = g1_add(g1_add(line1, g1_add(line2, g1_neg(g1_add(line3, mul(v.identity, constant))))), g1_neg(line5));
   bool open_valid = kzg_check(sp, gen, g1_to_aff(r), p.wit[5], p.r_eval, zeta);
-  return open_valid && p.r_eval.is_zero();
+  return openings_ok() && open_valid && p.r_eval.is_zero();
 }
 
 int prepare_pairing(const uint8_t g2[TP_G2_BYTES], const uint8_t g2s[TP_G2_BYTES], SrsPairing* sp) {
