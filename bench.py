@@ -224,8 +224,12 @@ def main():
     def step_resident():
         return circuit.handle.prove_dev([t.data_ptr() for t in devt[:3]], devt[3].data_ptr())
 
+    # the public-input vector as the reference's caller passes it: `circuit.prove(inputs, vec![0])` (README.md:29,
+    # builder/test.rs:28) -- one element; the library zero-fills the other n - 1 rows on the device (proof.rs:52-53)
+    host_pi = torch.zeros(32, dtype=torch.uint8).pin_memory()
+
     def step_e2e():
-        return circuit.handle.prove([h.data_ptr() for h in host[:3]], host[3].data_ptr())
+        return circuit.handle.prove_inputs([h.data_ptr() for h in host[:3]], host_pi.numpy())
 
     def barrier():
         if world > 1:
@@ -347,7 +351,8 @@ def main():
         "dtype": "u32-limb Montgomery Fr/Fq (integer)", "data": "synthetic",
         "config": {"workload": "mulchain_prove_n=2^%d" % log_n, "gates": n - 3, "srs_points": n + 3,
                    "parallelism": "msm point-range shard + quotient coset shard x%d" % world if world > 1 else "single GPU", "l2": l2_flush, "setup_s": round(setup_s, 1)},
-        "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 4 * 32 * n,
+        "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 32,
+                "inputs": "3 witness columns of n Fr + the 1-element public-input vector, pinned host memory",
                 "d2h_bytes_per_step": 1472},
         "gpu_launches": launches,
         "clocks": clocks,

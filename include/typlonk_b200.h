@@ -197,6 +197,12 @@ int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const 
              uint8_t* proof_out, size_t proof_cap);
 int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
                  uint8_t* proof_out, size_t proof_cap);
+/* The same from the public-input vector AS THE CALLER OF CompiledCircuit::prove PASSES IT (proof.rs:26-31: any
+ * length <= n, e.g. `vec![0]`): the first n_public rows are uploaded, the rest are zero-filled on the device --
+ * the `public_inputs.resize(self.rows, Fr::zero())` of proof.rs:52-53.  When every public input is zero (the only
+ * vectors the reference can prove) the prover skips that polynomial's transforms. */
+int tp_prove_inputs(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+                    size_t n_public, uint8_t* proof_out, size_t proof_cap);
 
 /* verify() (proof.rs:195-233, 441-503): `proof` is the TP_PROOF_FIXED_BYTES block tp_prove writes, `public_inputs`
  * the proof's public-input vector (n_public Montgomery Fr; resized to n like proof.rs:204-205).  The device

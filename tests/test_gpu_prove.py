@@ -144,3 +144,39 @@ def test_large_proof_verifies_with_trapdoor_verifier(ctx, log_n):
                                               circuit.fixed_commitments, sig)
     circuit.handle.destroy()
     circuit.srs.handle.destroy()
+
+
+def test_nonzero_public_inputs_general_path_alternating_with_the_zero_fast_path(ctx):
+    """A zero public-input vector skips that polynomial's transforms (api.cu); a non-zero one that the witness
+    compensates (c = a b + PI on a Mul row, so the gate line still vanishes) takes the general path.  Both must match
+    the oracle byte for byte, in any order on the same circuit, with tp_verify in between (it reuses the buffers)."""
+    from typlonk_b200 import field as F
+    gates = 13
+    circuit = mul_chain(gates).build(ctx, TAU)
+    oc = _oracle_circuit(obuilder.make_mul_chain(gates), 2)
+    n = circuit.rows
+    cols = circuit.witness([3, 5], BLINDERS)
+    zero_pis = [0] * n
+    want_zero = oplonk.prove_columns(oc, [list(c) for c in cols], list(zero_pis)).to_bytes()[:1472]
+    pis = list(zero_pis)
+    pis[2], pis[5] = 7, F.R_MOD - 1
+    cols2 = [list(c) for c in cols]
+    for j in (2, 5):
+        cols2[2][j] = (cols2[0][j] * cols2[1][j] + pis[j]) % F.R_MOD
+    want_nz = oplonk.prove_columns(oc, [list(c) for c in cols2], list(pis)).to_bytes()[:1472]
+    assert want_nz != want_zero
+
+    def run(c, p):
+        return circuit.handle.prove([F.fr_vec_to_bytes(x) for x in c], F.fr_vec_to_bytes(p))
+    assert run(cols, zero_pis) == want_zero
+    assert run(cols2, pis) == want_nz
+    assert run(cols, zero_pis) == want_zero
+    assert run(cols, zero_pis) == want_zero
+    assert circuit.handle.verify(want_zero, F.fr_vec_to_bytes(zero_pis))
+    assert run(cols, zero_pis) == want_zero
+    assert not circuit.handle.verify(want_nz, F.fr_vec_to_bytes(pis))   # copy constraints are broken by construction
+    assert run(cols2, pis) == want_nz
+    assert run(cols, zero_pis) == want_zero
+    # a non-zero public input the witness does not compensate still trips the gate check
+    with pytest.raises(GateUnsatisfied):
+        run(cols, pis)

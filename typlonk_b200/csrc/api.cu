@@ -502,11 +502,30 @@ static void put_fr(uint8_t*& w, const HFr& x) {
 static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   const size_t n = c->n;
   const tp_srs* srs = c->srs;
+  // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321) -- first, because it
+  // needs nothing but the uploaded columns and also tells whether the public inputs are all zero.
+  bool pi_zero = false;
+  {
+    bool ok = false;
+    const Fr* sel[5] = {c->sel_eval[0], c->sel_eval[1], c->sel_eval[2], c->sel_eval[3], c->sel_eval[4]};
+    const Fr* adv[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
+    TP_TRY(gate_check_dev(ctx, sel, adv, c->pi_eval, n, &ok, &pi_zero));
+    if (!ok) return fail(ctx, TP_ERR_GATE_UNSATISFIED, "prove: gate constraints do not vanish on the domain");
+  }
+  // A zero public-input vector (the only kind the reference's prover accepts) interpolates to the
+  // zero polynomial: its inverse NTT, its four coset NTTs and its evaluation are skipped and the buffers just hold zeros.
+  if (pi_zero && !c->pi_buffers_zero) {
+    TP_CUDA_OK(ctx, cudaMemsetAsync(c->pi_coef, 0, n * sizeof(Fr), ctx->stream));
+    TP_CUDA_OK(ctx, cudaMemsetAsync(c->buf4[4], 0, 4 * n * sizeof(Fr), ctx->stream));
+    c->pi_buffers_zero = true;
+  } else if (!pi_zero) {
+    c->pi_buffers_zero = false;
+  }
   // witness + public-input polynomials (proof.rs:50, 105-106)
   {
     const Fr* ins[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
     Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
-    TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, 4, c->log_n, true));
+    TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, pi_zero ? 3 : 4, c->log_n, true));
   }
   // round 1 commitments (proof.rs:107-110)
   uint8_t com[4][TP_G1_BYTES];
@@ -516,14 +535,6 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
   }
   HFr beta, gamma;
   tph::challenges2({com[0], com[1], com[2]}, &beta, &gamma);
-  // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321)
-  {
-    bool ok = false;
-    const Fr* sel[5] = {c->sel_eval[0], c->sel_eval[1], c->sel_eval[2], c->sel_eval[3], c->sel_eval[4]};
-    const Fr* adv[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
-    TP_TRY(gate_check_dev(ctx, sel, adv, c->pi_eval, n, &ok));
-    if (!ok) return fail(ctx, TP_ERR_GATE_UNSATISFIED, "prove: gate constraints do not vanish on the domain");
-  }
   // grand product z (proof.rs:117-131)
   {
     const Fr* v[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
@@ -555,7 +566,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
       const uint64_t* cos[20];
       int cnt = 0;
       for (int m = 0; m < nmine; m++)
-        for (int i = 0; i < 5; i++) {
+        for (int i = 0; i < (pi_zero ? 4 : 5); i++) {
           ins[cnt] = src[i];
           outs[cnt] = c->buf4[i] + (size_t)mine[m] * n;
           cos[cnt] = mine[m] == 0 ? nullptr : gens[mine[m]].v;
@@ -614,11 +625,11 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
     Fr points[8];
     for (int i = 0; i < 8; i++) points[i] = to_dev(i == 4 ? zeta * omega : zeta);
     HFr ys[8];
-    TP_TRY(poly_open_batch_dev(ctx, polys, n, points, quots, 8, ys));
+    TP_TRY(poly_open_batch_dev(ctx, polys, n, points, quots, pi_zero ? 7 : 8, ys));
     for (int i = 0; i < 5; i++) ev[i] = ys[i];
     sig_bar[0] = ys[5];
     sig_bar[1] = ys[6];
-    pi_bar = ys[7];
+    pi_bar = pi_zero ? HFr::zero() : ys[7];
   }
   // linearisation (proof.rs:376-439)
   HFr a = ev[0], b = ev[1], cc = ev[2], zw = ev[4];
@@ -688,30 +699,48 @@ int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], co
   TP_CUDA_OK(ctx, cudaMemcpyAsync(c->pi_eval, public_inputs_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return prove_resident(ctx, c, proof_out);
 }
-int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
-             uint8_t* proof_out, size_t proof_cap) {
+// Witness columns (n each) and the first n_public public inputs from host memory; rows n_public..n of the public-input
+// column are zero-filled on the device, which is the `public_inputs.resize(self.rows, Fr::zero())` of proof.rs:52-53.
+static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+                           size_t n_public, uint8_t* proof_out, size_t proof_cap) {
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
+  if (n_public > c->n) return fail(ctx, TP_ERR_INVALID_ARG, "prove: more public inputs than rows");
+  if (!advice || !advice[0] || !advice[1] || !advice[2] || (n_public && !public_inputs))
+    return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
   size_t bytes = c->n * sizeof(Fr);
   const uint64_t* cols[4] = {advice[0], advice[1], advice[2], public_inputs};
   Fr* dst[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
+  const int ncols = n_public == c->n ? 4 : 3;   // a short public-input vector travels whole, outside the column slices
+  if (ncols == 3) {
+    if (n_public) TP_TRY(h2d(ctx, c->pi_eval, public_inputs, n_public * sizeof(Fr)));
+    TP_CUDA_OK(ctx, cudaMemsetAsync(c->pi_eval + n_public, 0, (c->n - n_public) * sizeof(Fr), ctx->stream));
+  }
   const size_t world = (size_t)ctx->world;
   if (ctx->world > 1 && ctx->bcast && c->n % world == 0 && c->n / world >= 64) {
     // Sharded upload: every rank holds the same host columns, so each one sends only its row slice over PCIe
     // and the slices are exchanged over NVLink (one device broadcast per rank), then scattered into the columns.
     const size_t rows = c->n / world, slice = rows * sizeof(Fr);
-    uint8_t* stage = (uint8_t*)c->buf4[0];                       // [rank][column][rows], 4n Fr in total
-    for (int j = 0; j < 4; j++)
-      TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * 4 + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
+    uint8_t* stage = (uint8_t*)c->buf4[0];                       // [rank][column][rows], at most 4n Fr in total
+    for (int j = 0; j < ncols; j++)
+      TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * ncols + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
     for (int r = 0; r < ctx->world; r++)
-      if (ctx->bcast(ctx->bcast_user, stage + (size_t)r * 4 * slice, 4 * slice, r) != 0)
+      if (ctx->bcast(ctx->bcast_user, stage + (size_t)r * ncols * slice, ncols * slice, r) != 0)
         return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a witness slice failed");
-    for (int j = 0; j < 4; j++)
-      TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, 4 * slice, slice, world,
+    for (int j = 0; j < ncols; j++)
+      TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, ncols * slice, slice, world,
                                         cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
-    for (int j = 0; j < 4; j++) TP_TRY(h2d(ctx, dst[j], cols[j], bytes));
+    for (int j = 0; j < ncols; j++) TP_TRY(h2d(ctx, dst[j], cols[j], bytes));
   }
   return prove_resident(ctx, c, proof_out);
+}
+int tp_prove(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+             uint8_t* proof_out, size_t proof_cap) {
+  return prove_from_host(ctx, c, advice, public_inputs, c ? c->n : 0, proof_out, proof_cap);
+}
+int tp_prove_inputs(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
+                    size_t n_public, uint8_t* proof_out, size_t proof_cap) {
+  return prove_from_host(ctx, c, advice, public_inputs, n_public, proof_out, proof_cap);
 }
 
 // ---- helpers -------------------------------------------------------------------------------------

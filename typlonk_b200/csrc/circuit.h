@@ -27,6 +27,10 @@ struct tp_circuit {
   tp::Fr* t = nullptr;       // 3n
   tp::Fr* q[6] = {0};        // opening quotients (a, b, c, z, z-omega, r), n each
   tp::Fr* r = nullptr;       // n
+  // true while pi_coef and buf4[4] (the public-input polynomial and its 4n evaluations) are known to hold zeros:
+  // a proof whose public inputs are all zero -- the only kind the reference can prove, SURVEY.md App. D.1 -- then
+  // skips that polynomial's six transforms
+  bool pi_buffers_zero = false;
   std::vector<void*> allocs;
   // verifier state (verify.cu): the eight commitments of the circuit itself, computed on first use and kept
   // (the reference recomputes the sigma commitments in every verify, permutation/src/lib.rs:180-194)

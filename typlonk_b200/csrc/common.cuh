@@ -197,8 +197,9 @@ int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* con
 int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out /* len, may be null */, tph::HFr* y);
 // up to 8 polynomials of the same length at once (own point each; q_out[b] may be null = evaluation only)
 int poly_open_batch_dev(tp_ctx* ctx, const Fr* const* p, size_t len, const Fr* z, Fr* const* q_out, int batch, tph::HFr* y);
+// *ok: the gate equation holds on every row; *pi_is_zero (may be null): every public input is zero
 int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
-                   bool* ok);
+                   bool* ok, bool* pi_is_zero);
 struct QuotientArgs {   // every 4n-sized array is coset-major: slot k * n + i <-> omega_4n^(4i + k)
   const Fr* sel4[5];   // 4n evaluations
   const Fr* sig4[3];

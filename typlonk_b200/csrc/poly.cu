@@ -317,11 +317,14 @@ __global__ void k_gate_check(GateArgs g) {
   acc = fr_sub(acc, fr_mul(fr_load(g.sel[2] + j), c));
   acc = fr_add(acc, fr_mul(fr_mul(fr_load(g.sel[3] + j), a), b));
   acc = fr_add(acc, fr_load(g.sel[4] + j));
-  acc = fr_add(acc, fr_load(g.pi + j));
-  if (!fr_is_zero(acc)) atomicOr(g.flag, 1u);
+  const Fr pi = fr_load(g.pi + j);
+  acc = fr_add(acc, pi);
+  // bit 0: the gate equation fails on some row; bit 1: some public input is non-zero
+  const unsigned f = (fr_is_zero(acc) ? 0u : 1u) | (fr_is_zero(pi) ? 0u : 2u);
+  if (f) atomicOr(g.flag, f);
 }
 int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const adv[3], const Fr* pi, size_t n,
-                   bool* ok) {
+                   bool* ok, bool* pi_is_zero) {
   TP_TRY(ensure(ctx, ctx->flag, sizeof(unsigned)));
   GateArgs g;
   for (int i = 0; i < 5; i++) g.sel[i] = sel_evals[i];
@@ -334,7 +337,9 @@ int gate_check_dev(tp_ctx* ctx, const Fr* const sel_evals[5], const Fr* const ad
   TP_LAUNCH(ctx, "k_gate_check");
   TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, g.flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  *ok = (*(unsigned*)ctx->pinned == 0);
+  const unsigned f = *(unsigned*)ctx->pinned;
+  *ok = (f & 1u) == 0;
+  if (pi_is_zero) *pi_is_zero = (f & 2u) == 0;
   return TP_OK;
 }
 

@@ -307,6 +307,7 @@ int tp_verify(tp_ctx* ctx, tp_circuit* c, const uint8_t* proof, size_t proof_len
     size_t take = n_public < n ? n_public : n;
     TP_CUDA_OK(ctx, cudaMemsetAsync(c->pi_eval, 0, n * sizeof(Fr), ctx->stream));
     if (take) TP_CUDA_OK(ctx, cudaMemcpyAsync(c->pi_eval, public_inputs, take * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    c->pi_buffers_zero = false;
     TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
     const Fr* polys[3] = {c->pi_coef, c->sig_coef[0], c->sig_coef[1]};
     Fr* quots[3] = {nullptr, nullptr, nullptr};

@@ -29,7 +29,7 @@ SYMBOLS = [
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
     "tp_circuit_load", "tp_circuit_compile", "tp_circuit_destroy", "tp_circuit_sigma_commitments",
-    "tp_prove", "tp_prove_dev", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option", "tp_ctx_get_stat",
+    "tp_prove", "tp_prove_dev", "tp_prove_inputs", "tp_measure_imad_peak", "tp_selftest", "tp_fr_rand_stream", "tp_ctx_set_option", "tp_ctx_get_stat",
     "tp_srs_g2", "tp_srs_set_g2", "tp_kzg_verify", "tp_pairing_check", "tp_verify", "tp_verify_prepared", "tp_proof_challenges",
     "tp_trace_create", "tp_trace_destroy", "tp_trace_gate", "tp_trace_gates", "tp_trace_assert_eq", "tp_trace_finish",
     "tp_trace_gate_kinds", "tp_trace_selectors", "tp_trace_permutation", "tp_trace_witness",
@@ -553,6 +553,16 @@ class CircuitHandle:
         out = (C.c_char * PROOF_FIXED_BYTES)()
         self.ctx._check(lib().tp_prove(self.ctx._h, self._h, adv, _buf(public_inputs_mont), out,
                                        C.c_size_t(PROOF_FIXED_BYTES)))
+        return bytes(out)
+
+    def prove_inputs(self, advice_mont, public_inputs_mont) -> bytes:
+        """tp_prove_inputs: the public-input vector as the caller of prove() gives it (any length <= n)."""
+        keep = [_buf(b) for b in advice_mont]
+        adv = (C.c_void_p * 3)(*[C.cast(x, C.c_void_p) for x in keep])
+        out = (C.c_char * PROOF_FIXED_BYTES)()
+        n_public = len(public_inputs_mont) // 32
+        self.ctx._check(lib().tp_prove_inputs(self.ctx._h, self._h, adv, _buf(public_inputs_mont) if n_public else None,
+                                              C.c_size_t(n_public), out, C.c_size_t(PROOF_FIXED_BYTES)))
         return bytes(out)
 
     def prove_dev(self, advice_dptrs, pi_dptr) -> bytes:

@@ -221,8 +221,9 @@ class CompiledCircuit:
             cols = self.witness_bytes(inputs, blinders)
         else:
             cols = [F.fr_vec_to_bytes(c) for c in self.witness(inputs, blinders)]
-        pis = ([v % F.R_MOD for v in public_inputs] + [0] * self.rows)[: self.rows]
-        fixed = self.handle.prove(cols, F.fr_vec_to_bytes(pis))
+        given = [v % F.R_MOD for v in public_inputs][: self.rows]
+        pis = (given + [0] * self.rows)[: self.rows]          # what Proof.public_inputs carries (proof.rs:52-53, 190)
+        fixed = self.handle.prove_inputs(cols, F.fr_vec_to_bytes(given))
         return Proof(fixed, pis)
 
     def verify(self, proof: Proof) -> bool:
