@@ -284,6 +284,18 @@ int tp_permutation_builder_add_row(tp_permutation_builder* b);
 int tp_permutation_builder_add_constrain(tp_permutation_builder* b, size_t left_i, size_t left_j, size_t right_i,
                                          size_t right_j);
 int tp_permutation_builder_build(tp_permutation_builder* b, size_t size, uint64_t* perm);
+/* Permutation::compile (permutation/src/lib.rs:101-154) on its own: from the flat permutation (index = j + i n, n a
+ * power of two) the device builds id[i][j] = k_i w^j and sigma[i][j] = k_i' w^j' for (i', j') = perm[i n + j], n
+ * Montgomery Fr per column, and the coset representatives k_i (the first three k >= 1 with k^n != 1; may be NULL).
+ * tp_circuit_compile does the same internally; this entry feeds tp_perm_prove / tp_circuit_load. */
+int tp_permutation_compile(tp_ctx* ctx, const uint64_t* perm, size_t n, uint64_t* const id[3], uint64_t* const sigma[3],
+                           uint64_t cosets[3][4]);
+
+/* Fr conversions for host languages without a big-integer type (host only): Fr::from(i64) with negatives as
+ * r - |v| (plonk/src/utils.rs:152-153); 32-byte LE canonical <-> Montgomery limbs (>= r -> TP_ERR_MALFORMED). */
+int tp_fr_from_i64(int64_t v, uint64_t out[4]);
+int tp_fr_from_canonical(const uint8_t in[32], uint64_t out[4]);
+int tp_fr_to_canonical(const uint64_t in[4], uint8_t out[32]);
 
 /* ---- wire formats --------------------------------------------
  * The reference derives no (de)serialisation for Proof or Srs, so the framing is ours; every

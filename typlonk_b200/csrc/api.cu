@@ -478,6 +478,41 @@ int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const sel
   return TP_OK;
 }
 
+// Permutation::compile on its own (permutation/src/lib.rs:101-154): the (id, sigma) columns and the coset
+// representatives of a flat permutation, computed by the kernel tp_circuit_compile uses.
+int tp_permutation_compile(tp_ctx* ctx, const uint64_t* perm, size_t n, uint64_t* const id[3], uint64_t* const sigma[3],
+                           uint64_t cosets[3][4]) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (!perm || !id || !sigma || n == 0 || (n & (n - 1))) return fail(ctx, TP_ERR_INVALID_ARG, "permutation_compile: n must be a power of two");
+  for (size_t i = 0; i < 3 * n; i++)
+    if (perm[i] >= 3 * n) return fail(ctx, TP_ERR_INVALID_ARG, "permutation_compile: index out of range");
+  const unsigned log_n = log2_exact(n);
+  HFr k[3];
+  uint64_t kv = 1;
+  for (int i = 0; i < 3; i++) {
+    while (HFr::from_u64(kv).pow_u64((uint64_t)n) == HFr::one()) kv++;
+    k[i] = HFr::from_u64(kv);
+    if (cosets) memcpy(cosets[i], k[i].v, 32);
+    kv++;
+  }
+  TP_TRY(ensure(ctx, ctx->misc[0], 3 * n * sizeof(uint64_t)));
+  TP_TRY(ensure(ctx, ctx->misc[1], 6 * n * sizeof(Fr)));
+  TP_TRY(h2d(ctx, ctx->misc[0].p, perm, 3 * n * sizeof(uint64_t)));
+  const Fr* tw;
+  TP_TRY(ntt_get_twiddles(ctx, log_n, &tw));
+  Fr kd[3] = {to_dev(k[0]), to_dev(k[1]), to_dev(k[2])};
+  Fr* base = (Fr*)ctx->misc[1].p;
+  Fr* idp[3] = {base, base + n, base + 2 * n};
+  Fr* sgp[3] = {base + 3 * n, base + 4 * n, base + 5 * n};
+  TP_TRY(sigma_tables_dev(ctx, (const uint64_t*)ctx->misc[0].p, n, tw, kd, idp, sgp));
+  for (int i = 0; i < 3; i++) {
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(id[i], idp[i], n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(sigma[i], sgp[i], n * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  return TP_OK;
+}
+
 int tp_circuit_sigma_commitments(tp_ctx* ctx, tp_circuit* c, uint8_t out[3 * TP_G1_BYTES]) {
   if (!c->have_sigma_com) {
     const Fr* sets[3] = {c->sig_coef[0], c->sig_coef[1], c->sig_coef[2]};

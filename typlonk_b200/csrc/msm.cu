@@ -478,6 +478,20 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
       cur = key;
     }
     const unsigned idx = ent.x;
+#ifdef TP_ACC_PREFETCH
+    // The next entry's point sits anywhere in a multi-GB table: ask for its line(s) now, one addition
+    // (thousands of cycles) ahead of the load, instead of stalling on an HBM miss with three warps per scheduler.
+    if (e + 1 < end) {
+      const char* nx = (const char*)msm_point(bases, scratch, split, sorted[e + 1].x & 0x7fffffffu);
+#if TP_ACC_PREFETCH == 2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 80));
+#else
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 80));
+#endif
+    }
+#endif
     G1Affine p = affine_load(msm_point(bases, scratch, split, idx & 0x7fffffffu));
     if (!affine_is_identity(p)) xyzz_madd(acc, p, (idx >> 31) != 0);
   }

@@ -152,6 +152,37 @@ struct tp_trace {
 
 extern "C" {
 
+// ---- Fr conversions for host languages without a big-integer type (the C++ mirror, include/typlonk_b200.hpp) -------
+
+// Fr::from(i64): negative values map to r - |v| (ark-ff `From<i32/i64>`, used by plonk/src/utils.rs:152-153)
+int tp_fr_from_i64(int64_t v, uint64_t out[4]) {
+  if (!out) return TP_ERR_INVALID_ARG;
+  const uint64_t mag = v < 0 ? (uint64_t)0 - (uint64_t)v : (uint64_t)v;
+  HFr x = HFr::from_u64(mag);
+  if (v < 0) x = x.neg();
+  memcpy(out, x.v, 32);
+  return TP_OK;
+}
+// 32-byte little-endian canonical integer (< r, else TP_ERR_MALFORMED) <-> Montgomery limbs
+int tp_fr_from_canonical(const uint8_t in[32], uint64_t out[4]) {
+  if (!in || !out) return TP_ERR_INVALID_ARG;
+  uint64_t v[4];
+  memcpy(v, in, 32);
+  if (tph::ge<4>(v, tph::FR_PARAMS.mod)) return TP_ERR_MALFORMED;
+  HFr m = HFr::to_mont(v);
+  memcpy(out, m.v, 32);
+  return TP_OK;
+}
+int tp_fr_to_canonical(const uint64_t in[4], uint8_t out[32]) {
+  if (!in || !out) return TP_ERR_INVALID_ARG;
+  HFr m;
+  memcpy(m.v, in, 32);
+  if (tph::ge<4>(m.v, tph::FR_PARAMS.mod)) return TP_ERR_INVALID_ARG;
+  HFr c = m.from_mont();
+  memcpy(out, c.v, 32);
+  return TP_OK;
+}
+
 // ---- the permutation crate's builder on its own ---------------------------------------------------------------
 
 int tp_permutation_builder_create(size_t rows, tp_permutation_builder** out) {

@@ -35,6 +35,7 @@ SYMBOLS = [
     "tp_trace_gate_kinds", "tp_trace_selectors", "tp_trace_permutation", "tp_trace_witness",
     "tp_permutation_builder_create", "tp_permutation_builder_destroy", "tp_permutation_builder_add_row",
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
+    "tp_permutation_compile", "tp_fr_from_i64", "tp_fr_from_canonical", "tp_fr_to_canonical",
     "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
     "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize",
 ]
