@@ -234,6 +234,25 @@ def test_perm_prove_matches_oracle(ctx, n):
     assert got == expect
 
 
+@pytest.mark.parametrize("n", [4, 64, 4096])
+def test_permutation_compile_matches_oracle(ctx, n):
+    """Permutation::compile (permutation/src/lib.rs:101-154): id / sigma columns and coset representatives."""
+    from typlonk_b200.permutation import Permutation
+    rnd = random.Random(7 * n)
+    perm = list(range(3 * n))
+    rnd.shuffle(perm)
+    want = operm.Permutation(perm).compile()
+    got = Permutation(perm).compile(ctx)
+    assert got.cosets == want.cosets == [2, 3, 4]
+    assert got.ids == [[c[0] for c in col] for col in want.cols]
+    assert got.sigmas == [[c[1] for c in col] for col in want.cols]
+    values = [rng.fr_rand_stream(20 + i, n) for i in range(3)]
+    beta, gamma = rng.fr_rand_stream(21, 2)
+    assert got.prove(values, beta, gamma) == want.prove(values, beta, gamma)
+    with pytest.raises(TyplonkError):
+        Permutation(list(range(3 * n - 1)) + [3 * n]).compile(ctx)     # index out of range
+
+
 def test_perm_prove_zero_denominator(ctx):
     from typlonk_b200.permutation import CompiledPermutation
     n = 8

@@ -208,19 +208,54 @@ __global__ void k_scan_add(T* out, const T* sums, size_t n) {
 }
 
 // ---- 3. scatter ----------------------------------------------------------------------------
-__global__ void k_msm_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
-                              const unsigned* __restrict__ offsets, size_t n, size_t total, unsigned nwin,
-                              unsigned levels, unsigned stride, uint2* __restrict__ sorted) {
-  size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  unsigned key = keys[e];
+// The 8-byte stores of the counting sort land at random positions of one MSM's bucket-sorted list (len * nwin * 8
+// bytes: 109 MB at 2^20, as large as the L2), and a store that misses L2 costs DRAM a 32-byte sector read and a
+// write-back.  The scatter therefore runs once per SLICE of the bucket range: the stores of a launch fall into a
+// region that stays in L2 until its sectors are complete, and the entry arrays being MSM-major keeps that region to
+// one MSM at a time.  A launch re-reads every key (4 bytes, four per thread) but touches ranks, offsets and the
+// output only for the keys of its slice.  B200, 2^20, 13 MSMs per proof, sort phase: 1 slice 5.8 ms, 2 slices 4.7 ms,
+// 4 slices 5.0 ms, 8 slices 7.0 ms (profiles/r1_summary.md Q).
+__device__ __forceinline__ void msm_scatter_one(unsigned key, size_t e, const unsigned* __restrict__ ranks,
+                                                const unsigned* __restrict__ offsets, size_t n, unsigned nwin,
+                                                unsigned levels, unsigned stride, uint2* __restrict__ sorted,
+                                                unsigned slice_mask, unsigned slice_shift, unsigned slice) {
   if ((key & MSM_NONE) == MSM_NONE) return;
-  unsigned k = key & MSM_NONE;
-  unsigned pos = offsets[k] + ranks[e];
-  unsigned i = (unsigned)(e % n);
-  unsigned w = (unsigned)(e / n) % nwin;
+  const unsigned k = key & MSM_NONE;
+  if (((k & slice_mask) >> slice_shift) != slice) return;
+  const unsigned pos = offsets[k] + ranks[e];
+  const unsigned i = (unsigned)(e % n);
+  const unsigned w = (unsigned)(e / n) % nwin;
   // index into the fixed-base table: level (w % levels) holds 2^(c (w % levels)) * P_i
   sorted[pos] = make_uint2(((w % levels) * stride + i) | (key & 0x80000000u), k);  // one 8-byte store
+}
+#define SCATTER_UNROLL 1
+__global__ void __launch_bounds__(256) k_msm_scatter(const unsigned* __restrict__ keys, const unsigned* __restrict__ ranks,
+                                                     const unsigned* __restrict__ offsets, size_t n, size_t total,
+                                                     unsigned nwin, unsigned levels, unsigned stride,
+                                                     uint2* __restrict__ sorted, unsigned slice_mask, unsigned slice_shift,
+                                                     unsigned slice) {
+  // SCATTER_UNROLL coalesced 16-byte key loads per thread, all issued before any of them is used
+  uint4 kk[SCATTER_UNROLL];
+  size_t e0[SCATTER_UNROLL];
+#pragma unroll
+  for (int j = 0; j < SCATTER_UNROLL; j++) {
+    e0[j] = (((size_t)blockIdx.x * SCATTER_UNROLL + j) * blockDim.x + threadIdx.x) * 4;
+    kk[j] = make_uint4(MSM_NONE, MSM_NONE, MSM_NONE, MSM_NONE);
+    if (e0[j] + 4 <= total) {   // the key array is 16-byte aligned: cudaMalloc'ed, e0 a multiple of 4
+      kk[j] = *reinterpret_cast<const uint4*>(keys + e0[j]);
+    } else if (e0[j] < total) {
+      kk[j].x = keys[e0[j]];
+      if (e0[j] + 1 < total) kk[j].y = keys[e0[j] + 1];
+      if (e0[j] + 2 < total) kk[j].z = keys[e0[j] + 2];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SCATTER_UNROLL; j++) {
+    msm_scatter_one(kk[j].x, e0[j], ranks, offsets, n, nwin, levels, stride, sorted, slice_mask, slice_shift, slice);
+    msm_scatter_one(kk[j].y, e0[j] + 1, ranks, offsets, n, nwin, levels, stride, sorted, slice_mask, slice_shift, slice);
+    msm_scatter_one(kk[j].z, e0[j] + 2, ranks, offsets, n, nwin, levels, stride, sorted, slice_mask, slice_shift, slice);
+    msm_scatter_one(kk[j].w, e0[j] + 3, ranks, offsets, n, nwin, levels, stride, sorted, slice_mask, slice_shift, slice);
+  }
 }
 
 // ---- 4a. batch-affine rounds --------------------------------------------------------------
@@ -918,9 +953,30 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
                                                 ranks);
     TP_LAUNCH(ctx, "k_msm_digits");
     TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
-    k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
-                                                                           pl.levels, (unsigned)srs->len, sorted);
-    TP_LAUNCH(ctx, "k_msm_scatter");
+    {
+      // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
+      // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
+      // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
+      // is several L2s long gains nothing from two.  TP_MSM_SCATTER_SLICES forces a count.
+      static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
+      static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
+      unsigned log_slices = 0;
+      if (env_slices) {
+        while ((2u << log_slices) <= env_slices) log_slices++;
+      } else {
+        const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
+        if (per_msm > window && per_msm / 2 <= window) log_slices = 1;
+      }
+      if (log_slices > pl.c - 1) log_slices = pl.c - 1;
+      const unsigned slice_shift = pl.c - 1 - log_slices;
+      const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
+      for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
+        k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
+                                                                                 pl.levels, (unsigned)srs->len, sorted,
+                                                                                 pl.nbuck - 1, slice_shift, sl);
+        TP_LAUNCH(ctx, "k_msm_scatter");
+      }
+    }
     TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     TP_CUDA_OK(ctx, cudaMemcpyAsync((unsigned*)ctx->pinned + 1, hist + nkeys + 1, sizeof(unsigned), cudaMemcpyDeviceToHost,
                                     ctx->stream));

@@ -458,6 +458,17 @@ class Context:
         cos = _buf(coset_mont) if coset_mont is not None else None
         self._check(lib().tp_ntt_dev(self._h, C.c_void_p(dptr), C.c_uint(log_n), C.c_int(1 if inverse else 0), cos))
 
+    def permutation_compile(self, perm_u64: bytes, n: int):
+        """tp_permutation_compile: (3 id columns, 3 sigma columns, 3 coset representatives), Montgomery bytes."""
+        ids = [bytearray(32 * n) for _ in range(3)]
+        sgs = [bytearray(32 * n) for _ in range(3)]
+        ip = (C.c_void_p * 3)(*[C.addressof((C.c_char * len(b)).from_buffer(b)) for b in ids])
+        sp = (C.c_void_p * 3)(*[C.addressof((C.c_char * len(b)).from_buffer(b)) for b in sgs])
+        ks = (C.c_uint64 * 12)()
+        self._check(lib().tp_permutation_compile(self._h, _buf(perm_u64), C.c_size_t(n), ip, sp, ks))
+        raw = bytes(ks)
+        return ids, sgs, [raw[32 * i:32 * i + 32] for i in range(3)]
+
     def perm_prove(self, values, ids, sigmas, beta_mont: bytes, gamma_mont: bytes) -> bytes:
         n = len(values[0]) // 32
         keep = [_buf(b) for b in list(values) + list(ids) + list(sigmas)]

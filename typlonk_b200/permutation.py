@@ -65,6 +65,14 @@ class Permutation:
     def __init__(self, perm):
         self.perm = perm
 
+    def compile(self, ctx: Context) -> "CompiledPermutation":
+        """Permutation::compile (permutation/src/lib.rs:101-128) on the device (tp_permutation_compile)."""
+        import struct
+        n = len(self.perm) // C
+        ids, sgs, ks = ctx.permutation_compile(struct.pack("<%dQ" % len(self.perm), *self.perm), n)
+        return CompiledPermutation(ctx, [F.fr_vec_from_bytes(bytes(b)) for b in ids],
+                                   [F.fr_vec_from_bytes(bytes(b)) for b in sgs], [F.fr_from_bytes(k) for k in ks])
+
 
 class CompiledPermutation:
     """permutation/src/lib.rs:156-195: `cols` (id, sigma) per column + cosets."""
