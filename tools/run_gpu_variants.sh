@@ -1,5 +1,9 @@
-mkdir -p gpurun_out
-for v in 1 2 4 8 0; do
+for lg in 22 24; do
+for v in 1 2 4 8 16; do
   export TP_MSM_SCATTER_SLICES=$v
-  timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('slices[$v]', round(d['value'],3), round(d['e2e']['value'],3), d['phases_ms_per_step'], d['proof_sha256'])"
+  timeout 300 python -m typlonk_b200.sweep --msm $lg --ntt "" --reps 3 2>&1 | python -c "import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('lg $lg slices[$v]', round(d['ms'],3), {k:round(x,3) for k,x in d['phases_ms'].items()})"
+done
 done

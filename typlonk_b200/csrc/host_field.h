@@ -89,34 +89,40 @@ struct Fp {
   Fp neg() const { return zero() - *this; }
   Fp dbl() const { return *this + *this; }
 
-  // CIOS Montgomery product.
+  // CIOS Montgomery product.  Both moduli leave the top bit of their highest limb clear, so the running value
+  // never needs a second overflow word (the "no-carry" form); the loops are unrolled because a single thread's
+  // latency is what the MSM tails and the verifier wait for.
   Fp operator*(const Fp& o) const {
-    uint64_t t[N + 2];
-    memset(t, 0, sizeof(t));
+    static_assert(N <= 8, "unroll pragmas below assume at most 8 limbs");
+    uint64_t t[N + 1];
+#pragma GCC unroll 8
+    for (int k = 0; k <= N; k++) t[k] = 0;
+#pragma GCC unroll 8
     for (int i = 0; i < N; i++) {
       uint64_t c = 0;
+#pragma GCC unroll 8
       for (int j = 0; j < N; j++) {
         u128 x = (u128)v[j] * o.v[i] + t[j] + c;
         t[j] = (uint64_t)x;
         c = (uint64_t)(x >> 64);
       }
-      u128 x = (u128)t[N] + c;
-      t[N] = (uint64_t)x;
-      t[N + 1] = (uint64_t)(x >> 64);
-      uint64_t m = t[0] * P.inv;
-      x = (u128)m * P.mod[0] + t[0];
+      const uint64_t tn = t[N] + c;
+      const uint64_t m = t[0] * P.inv;
+      u128 x = (u128)m * P.mod[0] + t[0];
       c = (uint64_t)(x >> 64);
+#pragma GCC unroll 8
       for (int j = 1; j < N; j++) {
         x = (u128)m * P.mod[j] + t[j] + c;
         t[j - 1] = (uint64_t)x;
         c = (uint64_t)(x >> 64);
       }
-      x = (u128)t[N] + c;
+      x = (u128)tn + c;
       t[N - 1] = (uint64_t)x;
-      t[N] = t[N + 1] + (uint64_t)(x >> 64);
+      t[N] = (uint64_t)(x >> 64);
     }
     Fp r;
-    memcpy(r.v, t, sizeof(r.v));
+#pragma GCC unroll 8
+    for (int k = 0; k < N; k++) r.v[k] = t[k];
     if (t[N] || ge<N>(r.v, P.mod)) sub_n<N>(r.v, r.v, P.mod);
     return r;
   }

@@ -32,6 +32,8 @@
 
 #include "common.cuh"
 
+#include <future>
+
 namespace tp {
 
 #define MSM_NONE 0x7fffffffu
@@ -896,6 +898,31 @@ void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]) {
   }
 }
 
+// Affine conversion of a whole batch with ONE field inversion (Montgomery's trick): the inversion is ~570 field
+// products on the host, a commitment batch has up to nine of them back to back.  Same bytes as encode_g1.
+static void encode_g1_batch(const tph::HG1* p, uint8_t (*out)[TP_G1_BYTES], int n) {
+  tph::HFq prefix[MSM_MAX_BATCH];
+  tph::HFq run = tph::HFq::one();
+  for (int i = 0; i < n; i++) {
+    prefix[i] = run;
+    if (!p[i].is_identity()) run = run * p[i].z;
+  }
+  tph::HFq inv = run.inv();
+  for (int i = n - 1; i >= 0; i--) {
+    if (p[i].is_identity()) {
+      encode_g1(p[i], out[i]);
+      continue;
+    }
+    const tph::HFq zi = inv * prefix[i];
+    inv = inv * p[i].z;
+    const tph::HFq zi2 = zi.sqr();
+    const tph::HFq x = p[i].x * zi2, y = p[i].y * zi2 * zi;
+    memcpy(out[i], x.v, 48);
+    memcpy(out[i] + 48, y.v, 48);
+    out[i][96] = 0;
+  }
+}
+
 template <typename T>
 static int exclusive_scan(tp_ctx* ctx, const T* in, T* out, size_t n, unsigned* max_out) {
   size_t nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
@@ -957,7 +984,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
       // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
       // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
       // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
-      // is several L2s long gains nothing from two.  TP_MSM_SCATTER_SLICES forces a count.
+      // is several L2s long gains little (2^24: 9.9 -> 9.4 ms with four).  TP_MSM_SCATTER_SLICES forces a count.
       static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
       static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
       unsigned log_slices = 0;
@@ -965,7 +992,8 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
         while ((2u << log_slices) <= env_slices) log_slices++;
       } else {
         const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
-        if (per_msm > window && per_msm / 2 <= window) log_slices = 1;
+        if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
+        else if (per_msm > window) log_slices = 1;
       }
       if (log_slices > pl.c - 1) log_slices = pl.c - 1;
       const unsigned slice_shift = pl.c - 1 - log_slices;
@@ -1254,7 +1282,9 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     memcpy(zzz.v, q + 144, 48);
     return tph::g1_from_xyzz(x, y, zz, zzz);
   };
-  for (int b = 0; b < batch; b++) {
+  // one bucket set's tail is ~40 dependent group operations of single-thread host arithmetic (~0.1 ms); the sets of a
+  // batch are independent, so every batch element beyond the first gets its own thread
+  auto tail = [&](int b) {
     tph::HG1 acc = tph::HG1::identity();
     for (int q = (int)pl.nsets - 1; q >= 0; q--) {
       if (q != (int)pl.nsets - 1)
@@ -1273,7 +1303,11 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
       acc = tph::g1_add(acc, f);
     }
     results[b] = acc;
-  }
+  };
+  std::vector<std::future<void>> others;
+  for (int b = 1; b < batch; b++) others.push_back(std::async(std::launch::async, tail, b));
+  tail(0);
+  for (auto& f : others) f.get();
   return TP_OK;
 }
 
@@ -1315,7 +1349,7 @@ int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, 
       }
     }
   }
-  for (int b = 0; b < batch; b++) encode_g1(res[b], out[b]);
+  encode_g1_batch(res, out, batch);
   return TP_OK;
 }
 
