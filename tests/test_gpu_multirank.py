@@ -47,7 +47,12 @@ def _worker(rank, world, port, log_n, q):
         n = 1 << log_n
         circuit = synthetic.mul_chain_direct(ctx, log_n)
         cols = synthetic.mul_chain_witness(n - 3, n)
-        proof = circuit.handle.prove([F.fr_vec_to_bytes(c) for c in cols], bytes(32 * n))
+        col_bytes = [F.fr_vec_to_bytes(c) for c in cols]
+        proof = circuit.handle.prove(col_bytes, bytes(32 * n))
+        # the short public-input vector of prove()'s caller: three sliced columns + one whole 32-byte vector
+        short = circuit.handle.prove_inputs(col_bytes, bytes(32))
+        if short != proof:
+            proof = "error: tp_prove_inputs and tp_prove disagree on rank %d" % rank
         q.put((rank, proof))
         dist.barrier()
         ctx.close()
