@@ -33,6 +33,7 @@
 #include "common.cuh"
 
 #include <future>
+#include <system_error>
 
 namespace tp {
 
@@ -1305,8 +1306,13 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     results[b] = acc;
   };
   std::vector<std::future<void>> others;
-  for (int b = 1; b < batch; b++) others.push_back(std::async(std::launch::async, tail, b));
+  int b_next = 1;
+  try {
+    for (; b_next < batch; b_next++) others.push_back(std::async(std::launch::async, tail, b_next));
+  } catch (const std::system_error&) {  // no more threads to be had: the rest runs here
+  }
   tail(0);
+  for (int b = b_next; b < batch; b++) tail(b);
   for (auto& f : others) f.get();
   return TP_OK;
 }

@@ -12,6 +12,7 @@
 #include "transcript.h"
 
 #include <future>
+#include <system_error>
 
 using namespace tp;
 using namespace tph;
@@ -126,9 +127,12 @@ bool verify_host(const SrsPairing& sp, const VerifierValues& v, const ParsedProo
   for (int i = 0; i < 5; i++) {
     const G1Aff* com = &p.com[i < 3 ? i : 3];
     const HFr* at = i == 4 ? &zeta_omega : &zeta;
-    openings[i] = std::async(std::launch::async, [&sp, &gen, &p, com, at, i] {
-      return kzg_check(sp, gen, *com, p.wit[i], p.ev[i], *at);
-    });
+    auto one = [&sp, &gen, &p, com, at, i] { return kzg_check(sp, gen, *com, p.wit[i], p.ev[i], *at); };
+    try {
+      openings[i] = std::async(std::launch::async, one);
+    } catch (const std::system_error&) {  // no thread to be had: deferred = evaluated by get() on this thread
+      openings[i] = std::async(std::launch::deferred, one);
+    }
   }
   auto openings_ok = [&openings] {
     bool ok = true;
