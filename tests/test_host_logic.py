@@ -169,3 +169,24 @@ def test_quotient_by_cosets_identity():
         t0 = [(a + b) % M for a, b in zip(Nj[1], t1)]
         q, _r = poly.divide_by_vanishing_poly(N, n)
         assert poly.strip(t0 + t1 + t2) == poly.strip(list(q))
+
+
+def test_fr_conversion_helpers_of_the_abi():
+    """tp_fr_from_i64 / tp_fr_from_canonical / tp_fr_to_canonical (host only) against the Python field helpers."""
+    import ctypes as C
+    L = ffi.lib()
+    L.tp_fr_from_i64.argtypes = [C.c_int64, C.c_void_p]
+    for v in (0, 1, 5, -1, -7, 2**63 - 1, -2**63):
+        out = (C.c_char * 32)()
+        assert L.tp_fr_from_i64(v, out) == 0
+        assert bytes(out) == F.fr_to_bytes(v % fields.R_MOD), v
+    for x in rng.fr_rand_stream(12, 8) + [0, fields.R_MOD - 1]:
+        mont = (C.c_char * 32)()
+        assert L.tp_fr_from_canonical(x.to_bytes(32, "little"), mont) == 0
+        assert bytes(mont) == F.fr_to_bytes(x)
+        back = (C.c_char * 32)()
+        assert L.tp_fr_to_canonical(bytes(mont), back) == 0
+        assert int.from_bytes(bytes(back), "little") == x
+    out = (C.c_char * 32)()
+    assert L.tp_fr_from_canonical(fields.R_MOD.to_bytes(32, "little"), out) == 12      # TP_ERR_MALFORMED
+    assert L.tp_fr_to_canonical(b"\xff" * 32, out) == 1                                  # not a field element
