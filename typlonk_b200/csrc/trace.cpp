@@ -17,7 +17,7 @@
 #include <string.h>
 
 #include <new>
-#include <unordered_map>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/typlonk_b200.h"
@@ -40,7 +40,7 @@ inline uint64_t tag_row(uint64_t t) { return t >> 2; }
 // first-insertion order and each class's members in push order.
 struct CopyConstraints {
   size_t rows = 0;
-  std::unordered_map<uint64_t, uint32_t> slot_of;  // key tag -> class number (first-insertion order)
+  std::vector<uint32_t> slot_of;                   // packed key tag -> class number + 1 (0 = none); tags are dense (4 per row)
   std::vector<uint64_t> keys;                      // class number -> key tag
   std::vector<uint32_t> pair_slot;                 // arrival order
   std::vector<uint64_t> pair_right;
@@ -51,14 +51,14 @@ struct CopyConstraints {
   bool add(uint64_t li, uint64_t lj, uint64_t ri, uint64_t rj) {
     if (!check(li, lj) || !check(ri, rj)) return false;
     uint64_t key = pack_tag(li, lj);
-    auto it = slot_of.find(key);
+    if (key >= slot_of.size()) slot_of.resize(std::max<size_t>(4 * rows, 2 * slot_of.size()), 0);
     uint32_t slot;
-    if (it == slot_of.end()) {
+    if (slot_of[key] == 0) {
       slot = (uint32_t)keys.size();
-      slot_of.emplace(key, slot);
+      slot_of[key] = slot + 1;
       keys.push_back(key);
     } else {
-      slot = it->second;
+      slot = slot_of[key] - 1;
     }
     pair_slot.push_back(slot);
     pair_right.push_back(pack_tag(ri, rj));
