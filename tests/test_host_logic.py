@@ -190,3 +190,14 @@ def test_fr_conversion_helpers_of_the_abi():
     out = (C.c_char * 32)()
     assert L.tp_fr_from_canonical(fields.R_MOD.to_bytes(32, "little"), out) == 12      # TP_ERR_MALFORMED
     assert L.tp_fr_to_canonical(b"\xff" * 32, out) == 1                                  # not a field element
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md is the binding guide: every symbol the header declares must appear in it."""
+    header = open(os.path.join(ROOT, "include", "typlonk_b200.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|const char\*)\s+(tp_[a-z0-9_]+)\(", header, flags=re.M)))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for short in ("add_row", "add_constrain", "build", "destroy"):
+        doc = doc.replace("…_" + short, "tp_permutation_builder_" + short)
+    missing = [n for n in declared if n not in doc]
+    assert not missing, missing

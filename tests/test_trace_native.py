@@ -150,6 +150,8 @@ def test_unplaced_variable_and_argument_errors():
         t.witness(bytes(64), bytes(288))
     with pytest.raises(ffi.TyplonkError):
         t.witness(b"\xff" * 32, bytes(288))   # input limbs >= r are not a field element
+    with pytest.raises(ffi.TyplonkError):
+        t.witness(bytes(32), bytes(256) + b"\xff" * 32)   # nor are such blinder limbs
 
 
 def test_fill_sizes():

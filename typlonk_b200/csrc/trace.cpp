@@ -346,6 +346,8 @@ int tp_trace_witness(const tp_trace* t, const uint64_t* inputs, size_t n_inputs,
   for (int k = 0; k < 3; k++)
     if (!advice[k]) return TP_ERR_INVALID_ARG;
   const size_t n = t->rows, g = t->kind.size();
+  for (int k = 0; k < 9; k++)
+    if (tph::ge<4>(blinders + 4 * k, tph::FR_PARAMS.mod)) return TP_ERR_INVALID_ARG;  // not a field element
   std::vector<HFr> val;
   TP_TRY_ALLOC(val.resize(n_inputs + g))
   for (size_t k = 0; k < n_inputs; k++) {
