@@ -173,3 +173,27 @@ def test_srs_wire_at_scale_subgroup_checked():
     back = Srs.from_bytes(ctx, raw, 2)
     assert back.handle.download() == srs.handle.download()
     ctx.close()
+
+
+def test_proof_codec_is_canonical_under_random_corruption():
+    """Property: whatever bytes come in, tp_proof_decode either rejects them or accepts an encoding that re-encodes to
+    exactly the same bytes (one canonical encoding per proof)."""
+    import random
+    rnd = random.Random(2024)
+    accepted = rejected = 0
+    for name in sorted(PROOFS):
+        raw = bytes.fromhex(PROOFS[name]["proof_hex"])
+        for _ in range(60):
+            bad = bytearray(raw)
+            for _ in range(rnd.choice([1, 1, 2, 5])):
+                pos = rnd.randrange(len(bad))
+                bad[pos] ^= 1 << rnd.randrange(8)
+            try:
+                fixed, pis = ffi.proof_decode(bytes(bad))
+            except ffi.Malformed:
+                rejected += 1
+                continue
+            accepted += 1
+            assert ffi.proof_encode(fixed, pis) == bytes(bad)
+    # flips in a scalar's low bits are still canonical scalars (accepted); flips in a point leave the curve (rejected)
+    assert accepted > 0 and rejected > 0
