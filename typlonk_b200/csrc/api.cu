@@ -73,6 +73,12 @@ int tp_ctx_destroy(tp_ctx* ctx) {
   if (!ctx) return TP_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) {
+    cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamDestroy(ctx->copy_stream);
+    for (auto& e : ctx->copy_ev)
+      if (e) cudaEventDestroy(e);
+  }
   for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.tw);
   for (auto& c : ctx->coset_tables) {
     cudaFree(c.lo);
@@ -534,9 +540,18 @@ static void put_fr(uint8_t*& w, const HFr& x) {
   w += 32;
 }
 
-static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
+// `col_ready` (may be null): three events on another stream, one per witness column, recorded when that column's
+// upload has landed.  The prover then interpolates column k as soon as it is there -- while the next one is still
+// crossing PCIe -- instead of waiting for all three and running the batched transform.
+static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const cudaEvent_t* col_ready = nullptr) {
   const size_t n = c->n;
   const tp_srs* srs = c->srs;
+  if (col_ready) {
+    for (int k = 0; k < 3; k++) {
+      TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, col_ready[k], 0));
+      TP_TRY(ntt_dev(ctx, c->adv_eval[k], c->adv_coef[k], c->log_n, true, nullptr));
+    }
+  }
   // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321) -- first, because it
   // needs nothing but the uploaded columns and also tells whether the public inputs are all zero.
   bool pi_zero = false;
@@ -557,7 +572,9 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out) {
     c->pi_buffers_zero = false;
   }
   // witness + public-input polynomials (proof.rs:50, 105-106)
-  {
+  if (col_ready) {
+    if (!pi_zero) TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
+  } else {
     const Fr* ins[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
     Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
     TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, pi_zero ? 3 : 4, c->log_n, true));
@@ -765,7 +782,20 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
       TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, ncols * slice, slice, world,
                                         cudaMemcpyDeviceToDevice, ctx->stream));
   } else {
-    for (int j = 0; j < ncols; j++) TP_TRY(h2d(ctx, dst[j], cols[j], bytes));
+    // single GPU: columns on the copy stream, one event each; the compute stream picks them up one by one
+    if (!ctx->copy_stream) {
+      TP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+      for (auto& e : ctx->copy_ev) TP_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // the buffers may still be read by work queued earlier on the compute stream (the previous proof)
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->copy_ev[3], ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[3], 0));
+    for (int j = 0; j < 3; j++) {
+      TP_CUDA_OK(ctx, cudaMemcpyAsync(dst[j], cols[j], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+      TP_CUDA_OK(ctx, cudaEventRecord(ctx->copy_ev[j], ctx->copy_stream));
+    }
+    if (ncols == 4) TP_TRY(h2d(ctx, dst[3], cols[3], bytes));   // the full-length public-input column, compute stream
+    return prove_resident(ctx, c, proof_out, ctx->copy_ev);
   }
   return prove_resident(ctx, c, proof_out);
 }

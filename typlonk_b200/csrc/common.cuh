@@ -75,6 +75,10 @@ struct tp_ctx {
   void* pinned = nullptr;  // small pinned staging area
   size_t pinned_cap = 0;
   void* fixed_base = nullptr;  // 32 x 255 affine multiples of G for SRS generation
+  // tp_prove / tp_prove_inputs: the witness columns cross PCIe on their own stream, one event per column, so that
+  // column k is interpolated while column k + 1 is still in flight (created on first use)
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0..2] column landed, [3] compute stream reached the upload
 };
 
 struct tp_srs {
