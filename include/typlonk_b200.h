@@ -331,6 +331,8 @@ int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_
  * `StdRng::seed_from_u64(seed)` (ChaCha12), written as Montgomery limbs -- the same stream the
  * reference's Fiat-Shamir uses (plonk/src/proof/challenges.rs:38-45).  Host only. */
 int tp_fr_rand_stream(uint64_t seed, size_t count, uint64_t* out);
+/* "tp-build-stamp:<sha256 of the sources and flags this binary was compiled from>" (host only). */
+const char* tp_build_stamp(void);
 /* Self-test of the device field/curve arithmetic against host arithmetic; 0 failures expected. */
 int tp_selftest(tp_ctx* ctx, int* failures);
 

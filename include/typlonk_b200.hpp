@@ -29,18 +29,22 @@
 //
 // Where the reference panics, this throws typlonk::Error (code = the C ABI status).  Where the reference draws from
 // thread_rng (tau in Srs::random, the nine blinders in prove) there is an overload that takes the values explicitly
-// -- the parity tests need them fixed -- and one that draws them from std::random_device.
+// -- the parity tests need them fixed -- and one that draws them from the operating system's CSPRNG (getrandom).
 #pragma once
 
 #include <array>
 #include <cstdint>
 #include <cstring>
 #include <memory>
-#include <random>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <utility>
 #include <vector>
+
+#if defined(__linux__)
+#include <sys/random.h>
+#endif
 
 #include "typlonk_b200.h"
 
@@ -70,6 +74,27 @@ inline void check(int rc, const char* what, tp_ctx* ctx = nullptr) {
   if (rc == TP_ERR_GATE_UNSATISFIED) throw GateUnsatisfied(rc, msg);
   if (rc == TP_ERR_MALFORMED) throw Malformed(rc, msg);
   throw Error(rc, msg);
+}
+/// 64 bits from the operating system's CSPRNG: getrandom(2) where it exists, else /dev/urandom.
+inline uint64_t os_random_u64() {
+  uint64_t v = 0;
+  size_t got = 0;
+#if defined(__linux__)
+  while (got < sizeof(v)) {
+    ssize_t k = getrandom(reinterpret_cast<unsigned char*>(&v) + got, sizeof(v) - got, 0);
+    if (k <= 0) break;
+    got += (size_t)k;
+  }
+#endif
+  if (got < sizeof(v)) {
+    std::FILE* f = std::fopen("/dev/urandom", "rb");
+    if (f) {
+      got += std::fread(reinterpret_cast<unsigned char*>(&v) + got, 1, sizeof(v) - got, f);
+      std::fclose(f);
+    }
+  }
+  if (got < sizeof(v)) throw Error(TP_ERR_INVALID_ARG, "no operating-system entropy source (getrandom, /dev/urandom)");
+  return v;
 }
 }  // namespace detail
 
@@ -108,10 +133,11 @@ struct Fr {
       }
     }
   }
-  /// `Fr::rand(&mut thread_rng())`
+  /// `Fr::rand(&mut thread_rng())`: every 64-bit word comes straight from the operating system's CSPRNG
+  /// (getrandom(2), /dev/urandom as the fallback) -- tau and the blinders are secrets, so no seeded
+  /// non-cryptographic generator sits in between.  Throws if the system has no entropy source.
   static Fr random() {
-    static thread_local std::mt19937_64 gen{std::random_device{}()};
-    return rand([] { return gen(); });
+    return rand([] { return detail::os_random_u64(); });
   }
   /// `count` draws of `StdRng::seed_from_u64(seed)` (the generator of plonk/src/proof/challenges.rs:38-45).
   static std::vector<Fr> rand_stream(uint64_t seed, size_t count) {

@@ -5,6 +5,7 @@ import pytest
 
 from oracle.pyoracle import builder as obuilder, plonk as oplonk, rng
 from typlonk_b200.ffi import GateUnsatisfied
+import py_tracer
 from typlonk_b200.plonk import CircuitDescription
 
 pytestmark = pytest.mark.gpu
@@ -155,7 +156,7 @@ def test_nonzero_public_inputs_general_path_alternating_with_the_zero_fast_path(
     circuit = mul_chain(gates).build(ctx, TAU)
     oc = _oracle_circuit(obuilder.make_mul_chain(gates), 2)
     n = circuit.rows
-    cols = circuit.witness([3, 5], BLINDERS)
+    cols = py_tracer.witness(circuit.desc, circuit.rows, [3, 5], BLINDERS)
     zero_pis = [0] * n
     want_zero = oplonk.prove_columns(oc, [list(c) for c in cols], list(zero_pis)).to_bytes()[:1472]
     pis = list(zero_pis)

@@ -9,6 +9,7 @@ import pytest
 from oracle.pyoracle import builder as obuilder, fields, permutation as operm, rng
 from typlonk_b200 import field as F, ffi, synthetic
 from typlonk_b200.permutation import PermutationBuilder
+import py_tracer
 from typlonk_b200.plonk import CircuitDescription, Proof
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -28,11 +29,11 @@ class Pythagoras(CircuitDescription):
 
 
 def test_tracer_matches_oracle_tracer():
-    gates, perm = Pythagoras.trace()
+    gates, perm = py_tracer.trace(Pythagoras)
     ogates, operm_ = obuilder.trace(obuilder.circuit_pythagoras, 3)
     assert gates == ogates and perm.perm == operm_.perm
     for g in (1, 2, 5, 13, 29):
-        gates, perm = synthetic.mul_chain_description(g).trace()
+        gates, perm = py_tracer.trace(synthetic.mul_chain_description(g))
         ogates, operm_ = obuilder.trace(obuilder.make_mul_chain(g), 2)
         assert gates == ogates and perm.perm == operm_.perm
 
@@ -40,7 +41,7 @@ def test_tracer_matches_oracle_tracer():
 def test_direct_mul_chain_structure_equals_traced():
     for g in (1, 5, 13, 61, 125):
         gates, perm = synthetic.mul_chain_structure(g)
-        tgates, tperm = synthetic.mul_chain_description(g).trace()
+        tgates, tperm = py_tracer.trace(synthetic.mul_chain_description(g))
         assert gates == tgates and perm.perm == tperm.perm
     n = 64
     cols = synthetic.mul_chain_witness(61, n, blind=list(range(1, 10)))

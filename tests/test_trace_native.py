@@ -9,6 +9,7 @@ import pytest
 
 from oracle.pyoracle import builder as obuilder, fields, permutation as operm
 from typlonk_b200 import field as F, ffi, synthetic
+import py_tracer
 from typlonk_b200.plonk import GATE_ROWS, KIND_NAMES, CircuitDescription, TraceVar
 
 
@@ -108,7 +109,7 @@ def test_random_circuits_native_vs_oracle_and_mirror(seed):
     class D(CircuitDescription):
         INPUTS = n_inputs
     D.run = staticmethod(run)
-    mgates, mperm = D.trace()
+    mgates, mperm = py_tracer.trace(D)
     assert mgates == ogates and mperm.perm == operm_.perm
     inputs = [random.Random(seed + 100).randrange(fields.R_MOD) for _ in range(n_inputs)]
     blind = [random.Random(seed + 200 + k).randrange(fields.R_MOD) for k in range(9)]

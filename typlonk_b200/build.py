@@ -46,9 +46,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     time with TYPLONK_B200_LIB); the default build takes neither."""
     LIBDIR.mkdir(exist_ok=True)
     lib = LIBDIR / ("libtyplonk_b200_%s.so" % tag) if tag else LIB
-    stamp_file = LIBDIR / ("build%s.stamp" % ("_" + tag if tag else ""))
-    stamp = _stamp() + "|" + " ".join(defines)
-    if not force and lib.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
+    # The hash of every source + flag is compiled INTO the library (tp_build_stamp, api.cu) and compared with the
+    # sources on disk: a stale .so left behind by a checkout can never pass for a current one (no side file).
+    stamp = hashlib.sha256((_stamp() + "|" + " ".join(defines)).encode()).hexdigest()
+    if not force and lib.exists() and ("tp-build-stamp:" + stamp).encode() in lib.read_bytes():
         return lib
     nvcc = _nvcc()
     objdir = LIBDIR / ("obj" + ("_" + tag if tag else ""))
@@ -57,6 +58,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     def compile_one(src):
         obj = objdir / (src.rsplit(".", 1)[0] + ".o")
         cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
+        if src == "api.cu":
+            cmd.insert(1, '-DTP_BUILD_STAMP="%s"' % stamp)
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,7 +75,6 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))
-    stamp_file.write_text(stamp)
     return lib
 
 

@@ -228,6 +228,7 @@ int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
 }  // extern "C++"
 
 int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
   if (!out || !tau) return fail(ctx, TP_ERR_INVALID_ARG, "srs_from_secret: null argument");
   size_t len = gates + 3;
   tp_srs* s = nullptr;
@@ -446,6 +447,10 @@ int tp_circuit_load(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const select
 
 int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selector_evals[5], const uint64_t* perm,
                        size_t n, tp_circuit** out, uint8_t fixed_commitments[5 * TP_G1_BYTES]) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (!selector_evals || !perm || !out) return fail(ctx, TP_ERR_INVALID_ARG, "circuit_compile: null argument");
+  for (size_t i = 0; i < 3 * n; i++)   // k_sigma_tables splits an entry by / n and % n: out of range = a wrong sigma, silently
+    if (perm[i] >= 3 * n) return fail(ctx, TP_ERR_INVALID_ARG, "circuit_compile: permutation index out of range");
   tp_circuit* c = nullptr;
   TP_TRY(circuit_new(ctx, srs, n, &c));
   int rc = TP_OK;
@@ -744,6 +749,9 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
 
 int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
                  uint8_t* proof_out, size_t proof_cap) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (!c || !proof_out || !advice_dev || !advice_dev[0] || !advice_dev[1] || !advice_dev[2] || !public_inputs_dev)
+    return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
   size_t bytes = c->n * sizeof(Fr);
   for (int i = 0; i < 3; i++)
@@ -755,6 +763,8 @@ int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], co
 // column are zero-filled on the device, which is the `public_inputs.resize(self.rows, Fr::zero())` of proof.rs:52-53.
 static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
                            size_t n_public, uint8_t* proof_out, size_t proof_cap) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (!c || !proof_out) return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
   if (n_public > c->n) return fail(ctx, TP_ERR_INVALID_ARG, "prove: more public inputs than rows");
   if (!advice || !advice[0] || !advice[1] || !advice[2] || (n_public && !public_inputs))
@@ -813,6 +823,12 @@ int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_
   return measure_imad_dev(ctx, imad_per_s, imad_wide_per_s);
 }
 int tp_selftest(tp_ctx* ctx, int* failures) { return selftest_dev(ctx, failures); }
+#ifndef TP_BUILD_STAMP
+#define TP_BUILD_STAMP "unstamped"
+#endif
+/* sha256 over every source file and compiler flag this library was built from (typlonk_b200/build.py compares it with
+ * the sources on disk, so a stale binary is rebuilt instead of being loaded against newer headers) */
+const char* tp_build_stamp(void) { return "tp-build-stamp:" TP_BUILD_STAMP; }
 int tp_fr_rand_stream(uint64_t seed, size_t count, uint64_t* out) {
   if (!out && count) return TP_ERR_INVALID_ARG;
   tph::StdRng rng = tph::StdRng::seed_from_u64(seed);

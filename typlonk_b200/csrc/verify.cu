@@ -26,13 +26,17 @@ struct SrsPairing {
 
 // ark-serialize 0.3 uncompressed, unchecked G1 (x | y canonical LE, infinity = bit 6 of the last byte)
 bool read_g1(const uint8_t in[96], G1Aff* out) {
-  if (in[95] & 0x40) {
-    *out = {HFq::zero(), HFq::one(), true};
-    return true;
-  }
   uint64_t x[6], y[6];
   memcpy(x, in, 48);
   memcpy(y, in + 48, 48);
+  if (in[95] & 0x80) return false;  // the compressed form's sign flag has no place in an uncompressed record
+  if (in[95] & 0x40) {              // infinity: canonical only as (x, y) = (0, 1) | flag
+    y[5] &= ~((uint64_t)0x40 << 56);
+    for (int i = 0; i < 6; i++)
+      if (x[i] != 0 || y[i] != (i == 0 ? 1u : 0u)) return false;
+    *out = {HFq::zero(), HFq::one(), true};
+    return true;
+  }
   if (ge<6>(x, FQ_PARAMS.mod) || ge<6>(y, FQ_PARAMS.mod)) return false;
   *out = {HFq::to_mont(x), HFq::to_mont(y), false};
   return true;
@@ -275,6 +279,11 @@ int tp_verify_prepared(const tp_verifier_inputs* in, const uint8_t* proof, size_
   for (int i = 0; i < 3; i++) on &= g1aff_on_curve(v.sigma[i] = g1aff_decode(in->sigma_commitments[i]));
   on &= g1aff_on_curve(v.identity = g1aff_decode(in->identity));
   if (!on) return TP_OK;
+  for (int i = 0; i < 3; i++)
+    if (ge<4>(in->cosets[i], FR_PARAMS.mod)) return TP_ERR_INVALID_ARG;
+  for (int i = 0; i < 2; i++)
+    if (ge<4>(in->sigma_evals[i], FR_PARAMS.mod)) return TP_ERR_INVALID_ARG;
+  if (ge<4>(in->public_eval, FR_PARAMS.mod)) return TP_ERR_INVALID_ARG;
   for (int i = 0; i < 3; i++) memcpy(v.k[i].v, in->cosets[i], 32);
   for (int i = 0; i < 2; i++) memcpy(v.sigma_bar[i].v, in->sigma_evals[i], 32);
   memcpy(v.public_eval.v, in->public_eval, 32);
@@ -290,6 +299,10 @@ int tp_verify(tp_ctx* ctx, tp_circuit* c, const uint8_t* proof, size_t proof_len
   if (proof_len < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_INVALID_ARG, "verify: proof shorter than the fixed block");
   if (!c->srs->pairing) return fail(ctx, TP_ERR_INVALID_ARG, "verify: the SRS has no G2 points (tp_srs_set_g2)");
   *ok = 0;
+  // the same bound the prover enforces (prove_from_host); Montgomery limbs must be reduced
+  if (n_public > c->n) return fail(ctx, TP_ERR_INVALID_ARG, "verify: more public inputs than rows");
+  for (size_t i = 0; i < n_public; i++)
+    if (ge<4>(public_inputs + 4 * i, FR_PARAMS.mod)) return fail(ctx, TP_ERR_INVALID_ARG, "verify: public input not reduced modulo r");
   ParsedProof p;
   if (!parse_proof(proof, &p)) return fail(ctx, TP_ERR_INVALID_ARG, "verify: non-canonical field element in the proof");
   if (!points_on_curve(p)) return TP_OK;

@@ -99,7 +99,11 @@ __global__ void __launch_bounds__(128) k_g1_from_wire(const uint4* __restrict__ 
     y.v[11] &= 0x3fffffffu;
     bool ok = !(flags & 2) && fq_lt_mod(x) && fq_lt_mod(y);
     G1Affine p;
-    if (flags & 1) {  // infinity: the device SRS keeps it as the all-zero record
+    if (flags & 1) {  // infinity: canonical only as (x, y) = (0, 1); the device SRS keeps it as the all-zero record
+      bool canon = x.v[0] == 0 && y.v[0] == 1;
+#pragma unroll
+      for (int k = 1; k < 12; k++) canon = canon && x.v[k] == 0 && y.v[k] == 0;
+      ok = ok && canon;
       p.x = fq_zero();
       p.y = fq_zero();
     } else {
@@ -185,7 +189,8 @@ bool g2_from_wire(const uint8_t in[TP_WIRE_G2_BYTES], int check, G2Aff* out) {
   bool ok = fq_from_wire(in, 0, &p.x.a, nullptr) && fq_from_wire(in + 48, 0, &p.x.b, nullptr) &&
             fq_from_wire(in + 96, 0, &p.y.a, nullptr) && fq_from_wire(in + 144, 0xc0, &p.y.b, &flags);
   if (!ok || (flags & 0x80)) return false;
-  if (flags & 0x40) {
+  if (flags & 0x40) {  // infinity is canonical only as (x, y) = (0, 1)
+    if (!(p.x == Fq2::zero()) || !(p.y == Fq2::one())) return false;
     *out = {Fq2::zero(), Fq2::one(), true};
     return true;
   }
@@ -201,7 +206,7 @@ static bool g1_wire_valid(const uint8_t in[TP_WIRE_G1_BYTES]) {
   p.inf = false;
   if (!fq_from_wire(in, 0, &p.x, nullptr) || !fq_from_wire(in + 48, 0xc0, &p.y, &flags)) return false;
   if (flags & 0x80) return false;
-  if (flags & 0x40) return true;
+  if (flags & 0x40) return p.x == HFq::zero() && p.y == HFq::one();  // infinity is canonical only as (0, 1)
   return g1aff_on_curve(p);
 }
 

@@ -37,7 +37,7 @@ SYMBOLS = [
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
     "tp_permutation_compile", "tp_fr_from_i64", "tp_fr_from_canonical", "tp_fr_to_canonical",
     "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
-    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize",
+    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp",
 ]
 
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)

@@ -17,9 +17,8 @@ CircuitDescription / Var (plonk/src/description.rs:4-16), CircuitBuilder::compil
 The circuit closure is run ONCE over `TraceVar`, which records every `+` / `*` / `assert_eq` into the
 library's native tracer (csrc/trace.cpp); padding, selector columns, the copy-constraint
 permutation and every proof's witness columns come from that recording in C++ (the reference re-runs
-the closure over ComputeVar for every proof, builder.rs:380-397).  `BuildVar` / `ComputeVar` /
-`_Context` below restate the reference's two-pass scheme in Python and are what the CPU tests
-compare the native tracer with.  Everything numeric -- SRS, selector interpolation and commitments,
+the closure over ComputeVar for every proof, builder.rs:380-397); a Python restatement of that two-pass scheme,
+which the CPU tests compare the native tracer with, lives in tests/py_tracer.py.  Everything numeric -- SRS, selector interpolation and commitments,
 sigma tables, the whole prover -- runs on the device in libtyplonk_b200.  tau and the nine blinders are explicit inputs where the
 reference draws them from thread_rng (builder.rs:71, proof.rs:42-48).  `verify` (proof.rs:59-63) runs
 its circuit-sized parts on the device and the pairings on the host inside the library (csrc/verify.cu).
@@ -32,48 +31,9 @@ from . import field as F
 from .ffi import (Context, GateUnsatisfied, PROOF_FIXED_BYTES, GATE_ADD, GATE_MUL, Trace,  # noqa: F401
                   proof_decode, proof_encode)
 from .kzg import Srs
-from .permutation import Permutation, PermutationBuilder
+from .permutation import Permutation
 
 GATE_ROWS = {"Mul": (0, 0, 1, 1, 0), "Add": (1, 1, 1, 0, 0), "Dummy": (0, 0, 0, 0, 0)}  # builder.rs:318-324
-
-
-class _Context:
-    """builder.rs:119-188."""
-
-    def __init__(self):
-        self.gates = []
-        self.permutation = PermutationBuilder()
-        self.next_var_id = 0
-        self.pending_eq = []
-        self.var_map = {}
-
-    def new_id(self):
-        self.next_var_id += 1
-        return self.next_var_id - 1
-
-    def add_gate(self, gate):
-        self.gates.append(gate)
-        self.permutation.add_row()
-        return len(self.gates) - 1
-
-    def add_eq(self, left, right):
-        a, b = self.var_map.get(left), self.var_map.get(right)
-        if a is not None and b is not None:
-            if not self.permutation.add_constrain(a, b):
-                raise ValueError("invalid tag")
-        else:
-            self.pending_eq.append((left, right))
-
-    def finish(self):
-        pending, self.pending_eq = self.pending_eq, []
-        for left, right in pending:
-            self.add_eq(left, right)
-        assert not self.pending_eq
-        size = 2
-        while size < len(self.gates) + 3:  # fill(), builder.rs:47-58
-            size *= 2
-        self.gates += ["Dummy"] * (size - len(self.gates))
-        return self.gates, self.permutation
 
 
 class Var:
@@ -84,66 +44,6 @@ class Var:
 
     def assert_eq(self, other):
         raise NotImplementedError
-
-
-class BuildVar(Var):
-    """builder.rs:327-378."""
-
-    def __init__(self, context, vid):
-        self.context, self.id = context, vid
-
-    def clone(self):
-        return BuildVar(self.context, self.id)
-
-    def _binary(self, rhs, gate):
-        ctx = self.context
-        j = ctx.add_gate(gate)
-        out = ctx.new_id()
-        ctx.var_map[out] = (2, j)
-        for vid, i in ((self.id, 0), (rhs.id, 1)):
-            if vid in ctx.var_map:
-                new_id = ctx.new_id()
-                ctx.var_map[new_id] = (i, j)
-                ctx.add_eq(vid, new_id)
-            else:
-                ctx.var_map[vid] = (i, j)
-        return BuildVar(ctx, out)
-
-    def __add__(self, rhs):
-        return self._binary(rhs, "Add")
-
-    def __mul__(self, rhs):
-        return self._binary(rhs, "Mul")
-
-    def assert_eq(self, other):
-        self.context.add_eq(self.id, other.id)
-
-
-class ComputeVar(Var):
-    """builder.rs:332-336, 380-397; assert_eq is a no-op as in the reference (:435-441)."""
-
-    def __init__(self, value, advice):
-        self.value, self.advice = value % F.R_MOD, advice
-
-    def clone(self):
-        return ComputeVar(self.value, self.advice)
-
-    def _binary(self, rhs, mul):
-        l, r = self.value, rhs.value
-        v = (l * r if mul else l + r) % F.R_MOD
-        self.advice[0].append(l)
-        self.advice[1].append(r)
-        self.advice[2].append(v)
-        return ComputeVar(v, self.advice)
-
-    def __add__(self, rhs):
-        return self._binary(rhs, False)
-
-    def __mul__(self, rhs):
-        return self._binary(rhs, True)
-
-    def assert_eq(self, other):
-        pass
 
 
 class TraceVar(Var):
@@ -190,7 +90,7 @@ class Proof:
 class CompiledCircuit:
     """plonk/src/lib.rs:18-26."""
 
-    def __init__(self, desc, ctx, srs, handle, rows, fixed_commitments, gates, perm, native_trace=None):
+    def __init__(self, desc, ctx, srs, handle, rows, fixed_commitments, gates, perm, native_trace):
         self.desc, self.ctx, self.srs, self.handle = desc, ctx, srs, handle
         self.rows = rows
         self.fixed_commitments = fixed_commitments
@@ -203,24 +103,10 @@ class CompiledCircuit:
         assert len(blinders) == 9
         return self.native_trace.witness(F.fr_vec_to_bytes(inputs), F.fr_vec_to_bytes(blinders))
 
-    def witness(self, inputs, blinders):
-        """proof.rs:33-49 by re-running the closure over ComputeVar, as the reference does (canonical ints)."""
-        advice = [[], [], []]
-        self.desc.run([ComputeVar(v, advice) for v in inputs])
-        assert len(blinders) == 9
-        cols = []
-        for k, col in enumerate(advice):
-            col = col[: self.rows - 3] + [0] * max(0, self.rows - 3 - len(col))
-            cols.append(col + [b % F.R_MOD for b in blinders[3 * k: 3 * k + 3]])
-        return cols
-
     def prove(self, inputs, public_inputs, blinders) -> Proof:
         """CompiledCircuit::prove (proof.rs:26-57).  Raises GateUnsatisfied where the reference
         panics in `vanishes`."""
-        if self.native_trace is not None:
-            cols = self.witness_bytes(inputs, blinders)
-        else:
-            cols = [F.fr_vec_to_bytes(c) for c in self.witness(inputs, blinders)]
+        cols = self.witness_bytes(inputs, blinders)
         given = [v % F.R_MOD for v in public_inputs][: self.rows]
         pis = (given + [0] * self.rows)[: self.rows]          # what Proof.public_inputs carries (proof.rs:52-53, 190)
         fixed = self.handle.prove_inputs(cols, F.fr_vec_to_bytes(given))
@@ -238,13 +124,6 @@ class CircuitDescription:
     @staticmethod
     def run(inputs):
         raise NotImplementedError
-
-    @classmethod
-    def trace(cls):
-        ctx = _Context()
-        cls.run([BuildVar(ctx, ctx.new_id()) for _ in range(cls.INPUTS)])
-        gates, permutation = ctx.finish()
-        return gates, permutation.build(len(gates))
 
     @classmethod
     def trace_native(cls) -> Trace:
