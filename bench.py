@@ -1,17 +1,27 @@
 #!/usr/bin/env python3
-"""Headline benchmark: full PLONK prove of the synthetic mul-chain circuit (BASELINE.json
-configs[2]: 2^20 rows) through the reference-facing C ABI (tp_prove_dev / tp_prove).
+"""Headline benchmark: full PLONK prove of the synthetic mul-chain circuit (BASELINE.json configs[2]: 2^20 rows)
+through the reference-facing C ABI (tp_prove_dev / tp_prove_inputs).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n L] [--impl reference] [--sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n L] [--impl reference] [--no-sweep] [--no-north-star]
 
-One JSON line on stdout (rank 0).  A "step" is one complete proof (13 G1 MSMs, 12 iNTT + 5
-4n-NTTs, grand product, quotient, 6 openings).  `value` = prove ms with the witness resident
-in HBM; `e2e` = the same through tp_prove with pinned HOST buffers (H2D of the 3 witness columns
-+ public inputs and D2H of the proof inside the timed region).  N > 1: one process per GPU, every
-MSM sharded by point range, partial points all-gathered with NCCL, and the quotient sharded by
-coset of the 4n domain with one NCCL broadcast per coset (strong scaling).
+One JSON line on stdout (rank 0).  A "step" is one complete proof (13 G1 MSMs, 5 iNTT + 20 coset NTT + 4 inverse coset
+NTT, grand product, quotient, 6 openings).  `value` = prove ms with the witness resident in HBM; `e2e` = the same
+through tp_prove_inputs with pinned HOST buffers (H2D of the 3 witness columns + public inputs and D2H of the proof
+inside the timed region).  The proof bytes of every run are compared with the CPU oracle's golden proof of the same
+workload (tests/golden/mulchain_big.json, made by tools/make_golden_big.py) -> `parity`.
 
-`--impl reference` times the CPU oracle port (oracle/c, all host threads) on a bounded sample.
+N > 1 (torchrun, one process per GPU): the library owns the NCCL communicator (tp_ctx_comm_init_rank; the 128-byte id
+travels once over torch.distributed before anything is timed).  Every MSM is sharded by bucket with the per-rank
+reduction outputs all-gathered and combined on the device, the quotient by coset of the 4n domain, the witness upload
+by rows; no Python runs inside a proof.  Strong scaling.
+
+Also in the line: `north_star` -- the 2^22-gate prove of BASELINE.json configs[4] on the same N GPUs, digest-checked;
+`standalone` -- G1 MSM Mpts/s and NTT GB/s at the prover's size on these N GPUs; `sweeps` (N = 1) -- MSM 2^16..2^26
+incl. the skewed and all-equal cases, NTT / iNTT / coset NTT 2^16..2^24; `cpu_baseline` (N = 1) -- ONE real 2^20 prove
+of the oracle's C++ port on all host threads, no extrapolation.
+
+`--impl reference` times the CPU oracle port (oracle/c, all host threads) on the SAME 2^20 workload: full proves, as
+many of the K requested as fit in ~150 s (at least one); `steps` in its line is the number actually timed.
 """
 import argparse
 import json
@@ -128,29 +138,60 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvidia-smi"}
 
 
+def _golden(log_n):
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "mulchain_big.json")) as f:
+            return json.load(f).get("2^%d" % log_n)
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def _parity(proof: bytes, log_n: int):
+    import hashlib
+    digest = hashlib.sha256(proof).hexdigest()
+    g = _golden(log_n)
+    if g is None:
+        return {"digest_ok": None, "vs": "no golden proof committed for n=2^%d" % log_n, "sha256": digest}
+    return {"digest_ok": digest == g["sha256"] and proof.hex() == g["proof_hex"], "sha256": digest,
+            "vs": "c-oracle golden (tests/golden/mulchain_big.json, all 1472 proof bytes)"}
+
+
+def _cpu_prove(log_n, budget_s, max_steps):
+    """Full proves of the oracle's C++ port on all host threads: (ms per prove, proves timed, threads, proof)."""
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1
+    from oracle import coracle  # the only product-side place allowed to execute oracle/
+    tau, sel, perm, cols, pi = coracle.mul_chain_inputs(log_n)
+    c = coracle.Circuit(tau, sel, perm, 1 << log_n)
+    times, proof = [], None
+    t_start = time.perf_counter()
+    while len(times) < max(max_steps, 1):
+        t0 = time.perf_counter()
+        proof = c.prove(cols, pi)
+        times.append((time.perf_counter() - t0) * 1e3)
+        spent = time.perf_counter() - t_start
+        if spent + times[-1] / 1e3 > budget_s:   # the next one would not fit
+            break
+    c.close()
+    return sum(times) / len(times), len(times), coracle.threads(), proof
+
+
 def run_reference(args):
-    """CPU arm: the oracle's C++ port of the reference prover on the host cores."""
+    """CPU arm: the oracle's C++ port of the reference prover on the host cores, on the bench's own workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core it can
-    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    from oracle import coracle  # the only product-side place allowed to execute oracle/
-    log_n = min(args.log_n, args.ref_log_n)
-    res = coracle.bench_prove(log_n, steps=args.steps, warmup=min(args.warmup, 1))
-    scale = (1 << args.log_n) / float(1 << log_n)
-    # extrapolate the bounded sample LINEARLY in n (conservative for the CPU: ignores the log n factor
-    # of its NTTs; Pippenger's per-point cost falls slightly with n)
-    ms = res["ms_per_step"] * scale
-    sample = "full prove at n=2^%d (%d steps, %.0f ms each), scaled linearly x%.0f to n=2^%d" % (
-        log_n, args.steps, res["ms_per_step"], scale, args.log_n)
+    ms, done, threads, proof = _cpu_prove(args.log_n, args.ref_budget_s, args.steps)
+    sample = "%d full prove(s) at n=2^%d, %.0f ms each, %d host threads (requested %d steps; bounded to ~%d s)" % (
+        done, args.log_n, ms, threads, args.steps, args.ref_budget_s)
     line = {
-        "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
+        "warmup": 0, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64-limb Montgomery Fr/Fq (integer)", "data": "synthetic",
         "config": {"workload": "mulchain_prove_n=2^%d" % args.log_n, "gates": (1 << args.log_n) - 3},
-        "cpu_baseline": {"value": ms, "unit": UNIT, "cores": res["threads"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": ms, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ms, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "parity": _parity(proof, args.log_n),
+        "timed_region_s": round(ms * done / 1e3, 1),
     }
     print(json.dumps(line))
 
@@ -162,9 +203,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-n", type=int, default=20)
     ap.add_argument("--impl", default="typlonk_b200")
-    ap.add_argument("--ref-log-n", type=int, default=16, help="size of the bounded CPU sample")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop starting proves after this long")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also run the MSM / NTT sweeps (extra lines on stderr)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the MSM / NTT size sweeps (N = 1)")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the 2^22-gate prove")
+    ap.add_argument("--north-star-log-n", type=int, default=22)
     ap.add_argument("--dump-proof", default=None, help="write the proof bytes of the last timed step to this file (rank 0)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -192,59 +235,15 @@ def main():
     ctx = Context(local_rank, tstream.cuda_stream)
 
     if world > 1:
-        # 144 bytes per MSM of the batch and rank: persistent pinned staging and device buffers per message size, so a
-        # call is two small async copies around ncclAllGather and one stream synchronisation
-        gather_bufs = {}
-
-        def allgather(data: bytes) -> bytes:
-            nb = len(data)
-            if nb not in gather_bufs:
-                gather_bufs[nb] = (torch.empty(nb, dtype=torch.uint8).pin_memory(),
-                                   torch.empty(nb, dtype=torch.uint8, device=dev),
-                                   torch.empty(world * nb, dtype=torch.uint8, device=dev),
-                                   torch.empty(world * nb, dtype=torch.uint8).pin_memory())
-            hs, ds, dr, hr = gather_bufs[nb]
-            hs.numpy()[:] = np.frombuffer(data, dtype=np.uint8)
-            ds.copy_(hs, non_blocking=True)
-            dist.all_gather_into_tensor(dr, ds)
-            hr.copy_(dr, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            return hr.numpy().tobytes()
-        ctx.set_shard(rank, world, allgather)
-
-        from typlonk_b200.ffi import DeviceView
-
-        def bcast(ptr: int, nbytes: int, root: int):
-            # aliases the library's device buffer; NCCL orders itself after the current (= ctx) stream
-            dist.broadcast(torch.as_tensor(DeviceView(ptr, nbytes), device=dev), src=root)
-        if os.environ.get("TP_NO_COSET_SHARD", "0") != "1":
-            ctx.set_broadcast(bcast)
-
-    log_n = args.log_n
-    n = 1 << log_n
-    t0 = time.time()
-    circuit = synthetic.mul_chain_direct(ctx, log_n)
-    cols = synthetic.mul_chain_witness(n - 3, n)
-    col_bytes = [F.fr_vec_to_bytes(c) for c in cols]
-    pi_bytes = bytes(32 * n)
-    setup_s = time.time() - t0
-
-    # device-resident inputs (torch owns the memory) and pinned host copies for the e2e leg
-    def to_tensor(b):
-        return torch.frombuffer(bytearray(b), dtype=torch.uint8)
-    host = [to_tensor(b).pin_memory() for b in col_bytes] + [to_tensor(pi_bytes).pin_memory()]
-    devt = [h.to(dev) for h in host]
-    torch.cuda.synchronize()
-
-    def step_resident():
-        return circuit.handle.prove_dev([t.data_ptr() for t in devt[:3]], devt[3].data_ptr())
-
-    # the public-input vector as the reference's caller passes it: `circuit.prove(inputs, vec![0])` (README.md:29,
-    # builder/test.rs:28) -- one element; the library zero-fills the other n - 1 rows on the device (proof.rs:52-53)
-    host_pi = torch.zeros(32, dtype=torch.uint8).pin_memory()
-
-    def step_e2e():
-        return circuit.handle.prove_inputs([h.data_ptr() for h in host[:3]], host_pi.numpy())
+        # The library owns its NCCL communicator.  The one thing it needs from the host language is rank 0's 128-byte id,
+        # handed over here, once, before anything is timed; no Python runs inside a proof afterwards.
+        from typlonk_b200 import ffi as _ffi
+        idt = torch.zeros(_ffi.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(_ffi.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, src=0)
+        torch.cuda.synchronize()
+        ctx.comm_init_rank(rank, world, bytes(idt.cpu().numpy().tobytes()))
 
     def barrier():
         if world > 1:
@@ -267,6 +266,34 @@ def main():
             ms = float(t.item())
         return ms, out
 
+    def to_tensor(b):
+        return torch.frombuffer(bytearray(b), dtype=torch.uint8)
+
+    def workload(log_n):
+        """Circuit + device-resident witness + pinned host witness of the 2^log_n mul chain."""
+        n = 1 << log_n
+        t0 = time.time()
+        circuit = synthetic.mul_chain_direct(ctx, log_n)
+        cols = synthetic.mul_chain_witness(n - 3, n)
+        host = [to_tensor(F.fr_vec_to_bytes(c)).pin_memory() for c in cols] + [torch.zeros(32 * n, dtype=torch.uint8).pin_memory()]
+        devt = [h.to(dev) for h in host]
+        torch.cuda.synchronize()
+        return circuit, host, devt, time.time() - t0
+
+    log_n = args.log_n
+    n = 1 << log_n
+    circuit, host, devt, setup_s = workload(log_n)
+
+    def step_resident():
+        return circuit.handle.prove_dev([t.data_ptr() for t in devt[:3]], devt[3].data_ptr())
+
+    # the public-input vector as the reference's caller passes it: `circuit.prove(inputs, vec![0])` (README.md:29,
+    # builder/test.rs:28) -- one element; the library zero-fills the other n - 1 rows on the device (proof.rs:52-53)
+    host_pi = torch.zeros(32, dtype=torch.uint8).pin_memory()
+
+    def step_e2e():
+        return circuit.handle.prove_inputs([h.data_ptr() for h in host[:3]], host_pi.numpy())
+
     for _ in range(args.warmup):
         proof = step_resident()
     l2_flush = "inputs+tables (%.1f GiB working set) exceed the 126 MB L2" % ((13 * 4 + 30) * n * 32 / 2**30) \
@@ -287,47 +314,52 @@ def main():
     ms_e2e, proof_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop()
     assert proof == proof_e2e, "resident and host-buffer proofs differ"
+    parity = _parity(proof, log_n)
+    if world > 1:   # every rank must hold the same bytes
+        import hashlib
+        dg = torch.frombuffer(bytearray(hashlib.sha256(proof).digest()), dtype=torch.uint8).to(dev)
+        alld = [torch.empty_like(dg) for _ in range(world)]
+        dist.all_gather(alld, dg)
+        parity["ranks_agree"] = all(bool((x == dg).all().item()) for x in alld)
     # the proof just timed goes through the product verifier (device: PI / sigma evaluations, circuit commitments on the
     # first call; host: pairings).  Outside the timed region; wall clock because the pairing half is host work.
-    verify = None
-    if world == 1:
-        tv = []
-        for _ in range(3):
-            t1 = time.perf_counter()
-            ok = circuit.handle.verify(proof, bytes(32))
-            tv.append((time.perf_counter() - t1) * 1e3)
-            assert ok, "tp_verify rejects the proof the bench just produced"
-        bad = bytearray(proof)
-        bad[192] ^= 1
-        assert not circuit.handle.verify(bytes(bad), bytes(32)), "tp_verify accepts a corrupted proof"
-        verify = {"first_call_ms": round(tv[0], 2), "ms": round(min(tv[1:]), 2), "accepted": True,
-                  "note": "first call includes the 8 circuit-commitment MSMs, cached afterwards"}
+    tv = []
+    for _ in range(3):
+        t1 = time.perf_counter()
+        ok = circuit.handle.verify(proof, bytes(32))
+        tv.append((time.perf_counter() - t1) * 1e3)
+        assert ok, "tp_verify rejects the proof the bench just produced"
+    bad = bytearray(proof)
+    bad[192] ^= 1
+    assert not circuit.handle.verify(bytes(bad), bytes(32)), "tp_verify accepts a corrupted proof"
+    verify = {"first_call_ms": round(tv[0], 2), "ms": round(min(tv[1:]), 2), "accepted": True,
+              "note": "first call includes the 8 circuit-commitment MSMs, cached afterwards"}
 
     # BASELINE.json's metric names two more numbers next to the prove time: G1 MSM Mpts/s and NTT GB/s (algorithmic
-    # 64 * N bytes per transform).  Measured here on the prover's own SRS and a witness column, device
-    # resident, after the timed region; the full size sweeps are `--sweep` / typlonk_b200/sweep.py.
-    standalone = None
-    if world == 1:
-        def per_call(fn, reps=5):
-            fn()
-            ms, _ = timed(fn, reps)
-            return ms / reps
-        scal = devt[2].clone()
-        msm_ms = per_call(lambda: ctx.commit_dev(circuit.srs.handle, scal.data_ptr(), n))
-        ntt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n))
-        intt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, inverse=True))
-        cos_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, coset_mont=F.fr_to_bytes(7)))
-        standalone = {"log_n": log_n,
-                      "msm_ms": round(msm_ms, 4), "msm_mpts_per_s": round(n / msm_ms / 1e3, 1),
-                      "ntt_ms": round(ntt_ms, 4), "ntt_gb_per_s": round(64.0 * n / ntt_ms / 1e6, 1),
-                      "intt_ms": round(intt_ms, 4), "coset_ntt_ms": round(cos_ms, 4),
-                      "ntt_hbm_frac": round(64.0 * n / ntt_ms / 1e6 / _peaks()[0], 4)}
-        del scal
+    # 64 * N bytes per transform), "at 1/2/4/8 B200".  Measured here on the prover's own SRS and a witness
+    # column, device resident, after the timed region: the MSM sharded over the N GPUs like the prover's (every rank
+    # calls it), the NTT on one GPU (a single transform is not split; the prover shards NTTs by coset).
+    def per_call(fn, reps=5):
+        fn()
+        ms, _ = timed(fn, reps)
+        return ms / reps
+    scal = devt[2].clone()
+    msm_ms = per_call(lambda: ctx.commit_dev(circuit.srs.handle, scal.data_ptr(), n))
+    ntt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n))
+    intt_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, inverse=True))
+    cos_ms = per_call(lambda: ctx.ntt_dev(scal.data_ptr(), log_n, coset_mont=F.fr_to_bytes(7)))
+    standalone = {"log_n": log_n, "n_gpus": world,
+                  "msm_ms": round(msm_ms, 4), "msm_mpts_per_s": round(n / msm_ms / 1e3, 1),
+                  "ntt_ms": round(ntt_ms, 4), "ntt_gb_per_s": round(64.0 * n / ntt_ms / 1e6, 1),
+                  "intt_ms": round(intt_ms, 4), "coset_ntt_ms": round(cos_ms, 4),
+                  "ntt_hbm_frac": round(64.0 * n / ntt_ms / 1e6 / _peaks()[0], 4),
+                  "note": "msm: one commitment sharded over n_gpus; ntt: one transform on one GPU"}
+    del scal
 
     ms_step = ms_total / args.steps
     hbm_peak, peak_kind = _peaks()
     # dominant kernel: MSM bucket accumulation.  Algorithmic bytes per MSM = 128 B / point
-    # (96 B base + 32 B scalar); a launch processes this rank's shard of every
+    # (96 B base + 32 B scalar); a launch processes this rank's share of every
     # MSM in its batch (13 MSMs per proof go out as batches of 3 + 1 + 9 = 3 launches).
     acc_ms, acc_launches = prof["msm_accum"]
     acc_launch_ms = acc_ms / max(acc_launches, 1)
@@ -359,38 +391,80 @@ def main():
                     "peak": imad_wide, "unit": "wide multiply-adds/s", "frac": (prod_rate / imad_wide) if prod_rate else None,
                     "additions_per_step": entries / args.steps, "wide_products_per_addition": per_add,
                     "window_bits": ctx.get_stat("msm_window_bits"), "windows": ctx.get_stat("msm_windows"),
-                    "table_levels": ctx.get_stat("msm_table_levels")}
+                    "table_levels": ctx.get_stat("msm_table_levels"),
+                    "note": "per rank: additions_per_step counts the bucket additions THIS rank issued"}
+    phases = {p: round(prof[p][0] / args.steps, 3) for p in PHASES}
     line = {
         "metric": METRIC, "value": ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "u32-limb Montgomery Fr/Fq (integer)", "data": "synthetic",
         "config": {"workload": "mulchain_prove_n=2^%d" % log_n, "gates": n - 3, "srs_points": n + 3,
-                   "parallelism": "msm point-range shard + quotient coset shard x%d" % world if world > 1 else "single GPU", "l2": l2_flush, "setup_s": round(setup_s, 1)},
-        "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 32,
-                "inputs": "3 witness columns of n Fr + the 1-element public-input vector, pinned host memory",
+                   "parallelism": ("msm bucket shard + quotient coset shard + row-sharded upload x%d, library-owned NCCL" % world)
+                   if world > 1 else "single GPU", "l2": l2_flush, "setup_s": round(setup_s, 1)},
+        "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 32 * world,
+                "inputs": "3 witness columns of n Fr + the 1-element public-input vector, pinned host memory"
+                          + (" (each rank uploads its 1/%d row slice; slices exchanged over NVLink)" % world if world > 1 else ""),
                 "d2h_bytes_per_step": 1472},
         "gpu_launches": launches,
         "clocks": clocks,
+        "parity": parity,
         "roofline": roofline,
         "roofline_int": roofline_int,
-        "phases_ms_per_step": {p: round(prof[p][0] / args.steps, 3) for p in PHASES},
+        "phases_ms_per_step": phases,
         "imad_peak_per_s": imad_wide,
-        "proof_sha256": __import__("hashlib").sha256(proof).hexdigest()[:16],
+        "proof_sha256": parity["sha256"][:16],
         "verify": verify,
         "standalone": standalone,
+        "north_star": None,
+        "sweeps": None,
         "cpu_baseline": None,
     }
+
+    # ---- BASELINE.json configs[4] / the north-star target: the 2^22-gate circuit on these N GPUs, bytes checked -------
+    if not args.no_north_star and args.north_star_log_n != log_n:
+        try:
+            circuit.handle.destroy()
+            circuit.srs.handle.destroy()
+            del devt, host
+            torch.cuda.empty_cache()
+            lg = args.north_star_log_n
+            big, bhost, bdev, bsetup = workload(lg)
+            f_res = lambda: big.handle.prove_dev([t.data_ptr() for t in bdev[:3]], bdev[3].data_ptr())  # noqa: E731
+            f_e2e = lambda: big.handle.prove_inputs([h.data_ptr() for h in bhost[:3]], host_pi.numpy())  # noqa: E731
+            f_res()
+            f_res()
+            ctx.prof_reset()
+            ctx.prof_enable(True)
+            ns_steps = 3
+            ms_ns, pr = timed(f_res, ns_steps)
+            ns_prof = ctx.prof_get()
+            ctx.prof_enable(False)
+            f_e2e()
+            ms_ns_e2e, pr2 = timed(f_e2e, ns_steps)
+            line["north_star"] = {"workload": "mulchain_prove_n=2^%d" % lg, "gates": (1 << lg) - 3, "n_gpus": world,
+                                  "prove_ms": round(ms_ns / ns_steps, 3), "e2e_ms": round(ms_ns_e2e / ns_steps, 3),
+                                  "steps": ns_steps, "warmup": 2, "parity": _parity(pr, lg), "e2e_same_bytes": pr == pr2,
+                                  "phases_ms_per_step": {p: round(ns_prof[p][0] / ns_steps, 3) for p in PHASES},
+                                  "setup_s": round(bsetup, 1)}
+            big.handle.destroy()
+            big.srs.handle.destroy()
+            del bdev, bhost
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            line["north_star"] = {"error": repr(e)}
+            if world > 1:
+                raise
+    if world == 1 and not args.no_sweep:
+        from typlonk_b200 import sweep
+        line["sweeps"] = sweep.run(ctx, torch)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         try:
-            os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-            from oracle import coracle
-            res = coracle.bench_prove(min(log_n, args.ref_log_n), steps=1, warmup=0)
-            rl = min(log_n, args.ref_log_n)
-            scale = n / float(1 << rl)
+            ms_cpu, done, threads, cproof = _cpu_prove(log_n, 1.0, 1)
             line["cpu_baseline"] = {
-                "value": res["ms_per_step"] * scale, "unit": UNIT, "cores": res["threads"], "kind": "port",
-                "sample": "full prove at n=2^%d measured %.0f ms on %d threads, scaled linearly x%.0f to n=2^%d" % (
-                    rl, res["ms_per_step"], res["threads"], scale, log_n)}
+                "value": ms_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": "ONE full prove of the same 2^%d workload by oracle/c (C++ port of the reference prover with "
+                          "Pippenger + NTTs), %d host threads; no extrapolation" % (log_n, threads),
+                "same_bytes_as_gpu": cproof == proof}
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if rank == 0 and args.dump_proof:
@@ -398,9 +472,6 @@ def main():
             f.write(proof)
     if rank == 0:
         print(json.dumps(line))
-    if args.sweep and rank == 0 and world == 1:
-        from typlonk_b200 import sweep
-        sweep.run(ctx, torch, sys.stderr)
     if world > 1:
         dist.destroy_process_group()
 

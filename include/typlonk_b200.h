@@ -67,22 +67,34 @@ int tp_ctx_destroy(tp_ctx* ctx);
 const char* tp_last_error(tp_ctx* ctx);
 int tp_sync(tp_ctx* ctx);
 
-/* Multi-GPU (one process per GPU).  Every MSM is sharded by contiguous point range over
- * `world` ranks; each rank produces a partial Jacobian point (3 x 48 B Montgomery) and calls
- * `allgather(user, send[144 B], recv[world x 144 B], 144)` -- the host language wires this to
- * NCCL (torch.distributed.all_gather over NVLink).  rank/world = 0/1 disables sharding. */
-typedef int (*tp_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
-int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user);
-/* Optional second collective: broadcast `bytes` of DEVICE memory at `dev_ptr` from rank `root` to every
- * rank, ordered with respect to the ctx stream (the host language wires it to ncclBroadcast, e.g.
- * torch.distributed.broadcast on a tensor aliasing dev_ptr).  With it, tp_prove shards the quotient
- * (plonk/src/proof.rs:292-375) over ranks by coset of the 4n evaluation domain: a rank evaluates the
- * numerator on its cosets only and the four n-coefficient interpolants (n x 32 B each) are exchanged.
- * Without it every rank evaluates all four cosets itself.  tp_prove (host buffers) also uses it to upload the
- * witness in row slices: each rank copies 1/world of every column over PCIe and the slices travel over
- * NVLink.  Call after tp_ctx_set_shard. */
-typedef int (*tp_bcast_dev_fn)(void* user, void* dev_ptr, size_t bytes, int root);
-int tp_ctx_set_broadcast(tp_ctx* ctx, tp_bcast_dev_fn bcast, void* user);
+/* ---- multi-GPU ---------------------------------------------------------------------------
+ * The prover is SPMD over `world` ranks, one GPU each; every rank ends up with the same proof bytes.  What is split:
+ *  - every MSM (kzg/src/lib.rs:41-54) by BUCKET: all ranks extract the signed window digits of all scalars, rank r
+ *    sorts / accumulates / reduces only the buckets b with b mod world == r (the window size stays the one planned for
+ *    the whole length, so additions and bucket reduction both shrink 1/world).  The per-rank reduction outputs
+ *    (a few KB) are all-gathered device-to-device and combined by one small kernel; the host reads back one buffer.
+ *  - the quotient (plonk/src/proof.rs:292-375) by coset of the 4n domain, one device broadcast per coset;
+ *  - tp_prove's witness upload: each rank copies 1/world of every column over PCIe, the slices travel over NVLink.
+ * The communicator lives INSIDE the library (NCCL, loaded with dlopen("libnccl.so.2"); in a torch process that is the
+ * copy torch already loaded): no host-language callback runs during a proof.
+ *
+ * (a) One process per GPU (torchrun, MPI): rank 0 calls tp_comm_unique_id, the host language hands the 128 bytes to
+ *     every rank once (any channel), every rank calls tp_ctx_comm_init_rank on its own tp_ctx_create'd context BEFORE
+ *     creating the SRS (the MSM plan depends on `world`).  All ranks then make the same calls with the same inputs. */
+#define TP_COMM_ID_BYTES 128
+int tp_comm_unique_id(uint8_t out[TP_COMM_ID_BYTES]);
+int tp_ctx_comm_init_rank(tp_ctx* ctx, int rank, int world, const uint8_t id[TP_COMM_ID_BYTES]);
+/* (b) One process, `ndev` GPUs -- the shape of the reference, where CompiledCircuit::prove (plonk/src/proof.rs:26-57)
+ *     is one call on one thread.  The returned context is a front for ndev per-device contexts, each with its own
+ *     stream and worker thread, joined by ncclCommInitAll.  tp_srs_* , tp_circuit_*, tp_commit, tp_open, tp_prove,
+ *     tp_prove_inputs, tp_verify, tp_sync and the tp_prof_* / stat calls accept it unchanged and return one result
+ *     (host-pointer arguments are read by every worker; `_dev` entry points are per device and are refused).
+ *     A device may be listed more than once: those ranks then exchange through peer copies and a host barrier
+ *     instead of NCCL -- slower, but it runs the complete sharded path on a single GPU (used by the tests). */
+#define TP_MAX_GROUP 16
+int tp_ctx_create_multi(const int* devices, int ndev, tp_ctx** out);
+/* ranks behind `ctx` (1 for a plain context) and whether they exchange through NCCL */
+int tp_ctx_group_size(const tp_ctx* ctx, int* ndev, int* uses_nccl);
 
 /* Tunables of the MSM behind tp_commit / tp_open / tp_prove.  Results are identical for every
  * setting (the affine sum of a bucket is unique).

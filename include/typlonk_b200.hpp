@@ -173,6 +173,21 @@ class Context {
     detail::check(tp_ctx_create(device, cuda_stream, &h), "tp_ctx_create (no CUDA device? there is no CPU fallback)");
     h_ = std::shared_ptr<tp_ctx>(h, [](tp_ctx* p) { tp_ctx_destroy(p); });
   }
+  /// One context over several GPUs of this process (tp_ctx_create_multi): CompiledCircuit::prove stays ONE call
+  /// (plonk/src/proof.rs:26-57) while every MSM, the quotient and the witness upload are sharded over the devices.
+  /// A device listed twice = two ranks on it (peer copies instead of NCCL; for tests on one GPU).
+  static Context multi(const std::vector<int>& devices) {
+    tp_ctx* h = nullptr;
+    detail::check(tp_ctx_create_multi(devices.data(), (int)devices.size(), &h), "tp_ctx_create_multi");
+    Context c{std::shared_ptr<tp_ctx>(h, [](tp_ctx* p) { tp_ctx_destroy(p); })};
+    return c;
+  }
+  /// ranks behind this context (1 for a single device)
+  int ranks() const {
+    int n = 1;
+    tp_ctx_group_size(get(), &n, nullptr);
+    return n;
+  }
   tp_ctx* get() const { return h_.get(); }
   void sync() const { detail::check(tp_sync(get()), "tp_sync", get()); }
   uint64_t launch_count() const {
@@ -182,6 +197,7 @@ class Context {
   }
 
  private:
+  explicit Context(std::shared_ptr<tp_ctx> h) : h_(std::move(h)) {}
   std::shared_ptr<tp_ctx> h_;
 };
 

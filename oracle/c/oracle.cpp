@@ -31,6 +31,9 @@
 #include <algorithm>
 #include <chrono>
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
+extern "C" double oracle_now_ms();
 
 typedef unsigned __int128 u128;
 
@@ -83,20 +86,33 @@ struct Fp {
   }
   Fp neg() const { return zero() - *this; }
   Fp dbl() const { return *this + *this; }
-  Fp operator*(const Fp& o) const {  // coarsely integrated operand scanning
-    uint64_t t[N + 2];
-    memset(t, 0, sizeof t);
+  // Montgomery product, CIOS with the "no-carry" shortcut ark-ff 0.3 uses for moduli whose top bit is clear
+  // (both r and q here): the two inner chains never overflow a limb pair, so no extra carry words are kept.
+  Fp operator*(const Fp& o) const {
+    uint64_t t[N];
+#pragma GCC unroll 8
+    for (int j = 0; j < N; j++) t[j] = 0;
+#pragma GCC unroll 8
     for (int i = 0; i < N; i++) {
-      uint64_t c = 0;
-      for (int j = 0; j < N; j++) { u128 x = (u128)l[j] * o.l[i] + t[j] + c; t[j] = (uint64_t)x; c = (uint64_t)(x >> 64); }
-      u128 x = (u128)t[N] + c; t[N] = (uint64_t)x; t[N + 1] = (uint64_t)(x >> 64);
-      uint64_t m = t[0] * P.inv;
-      x = (u128)m * P.p[0] + t[0]; c = (uint64_t)(x >> 64);
-      for (int j = 1; j < N; j++) { x = (u128)m * P.p[j] + t[j] + c; t[j - 1] = (uint64_t)x; c = (uint64_t)(x >> 64); }
-      x = (u128)t[N] + c; t[N - 1] = (uint64_t)x; t[N] = t[N + 1] + (uint64_t)(x >> 64);
+      u128 x = (u128)l[0] * o.l[i] + t[0];
+      uint64_t c = (uint64_t)(x >> 64);
+      const uint64_t m = (uint64_t)x * P.inv;
+      u128 y = (u128)m * P.p[0] + (uint64_t)x;
+      uint64_t c2 = (uint64_t)(y >> 64);
+#pragma GCC unroll 8
+      for (int j = 1; j < N; j++) {
+        x = (u128)l[j] * o.l[i] + t[j] + c;
+        c = (uint64_t)(x >> 64);
+        y = (u128)m * P.p[j] + (uint64_t)x + c2;
+        c2 = (uint64_t)(y >> 64);
+        t[j - 1] = (uint64_t)y;
+      }
+      t[N - 1] = c + c2;
     }
-    Fp r; memcpy(r.l, t, sizeof r.l);
-    if (t[N] || geq_p(r.l)) sub_p(r.l);
+    Fp r;
+#pragma GCC unroll 8
+    for (int j = 0; j < N; j++) r.l[j] = t[j];
+    if (geq_p(r.l)) sub_p(r.l);
     return r;
   }
   Fp sqr() const { return *this * *this; }
@@ -479,11 +495,16 @@ void oracle_circuit_fixed_commitments(void* cv, uint8_t out[5 * 97]) {
 int oracle_prove(void* cv, const uint64_t* const advice[3], const uint64_t* public_inputs, uint8_t* out) {
   Circuit& c = *(Circuit*)cv;
   const size_t n = c.n;
+  const bool timing = getenv("ORACLE_TIMING") != nullptr;
+  double t_last = oracle_now_ms();
+  auto lap = [&](const char* what) { if (timing) { double t = oracle_now_ms(); fprintf(stderr, "[oracle] %-12s %9.1f ms\n", what, t - t_last); t_last = t; } };
   std::vector<Fr> ev[3], co[3], pi((const Fr*)public_inputs, (const Fr*)public_inputs + n), pic;
   for (int i = 0; i < 3; i++) { ev[i].assign((const Fr*)advice[i], (const Fr*)advice[i] + n); co[i] = ev[i]; ntt(co[i].data(), c.log_n, true); }
   pic = pi; ntt(pic.data(), c.log_n, true);
+  lap("intt x4");
   std::vector<Aff> com(4);
   for (int i = 0; i < 3; i++) com[i] = commit(c, co[i]);
+  lap("commit abc");
   Fr beta, gamma;
   challenges2({com[0], com[1], com[2]}, &beta, &gamma);
   for (size_t j = 0; j < n; j++) {  // vanishes(line1), proof.rs:317-321
@@ -512,9 +533,11 @@ int oracle_prove(void* cv, const uint64_t* const advice[3], const uint64_t* publ
     z[0] = Fr::one();
     for (size_t j = 0; j < n; j++) z[j + 1] = z[j] * num[j];
   }
+  lap("grand prod");
   std::vector<Fr> zc(z.begin(), z.begin() + n);
   ntt(zc.data(), c.log_n, true);
   com[3] = commit(c, zc);
+  lap("commit z");
   Fr alpha, zeta;
   challenges2(com, &alpha, &zeta);
 
@@ -545,6 +568,7 @@ int oracle_prove(void* cv, const uint64_t* const advice[3], const uint64_t* publ
   std::vector<Fr> t(3 * n);
   for (size_t k = 0; k < n; k++) { Fr t2 = num4[k + 3 * n], t1 = num4[k + 2 * n] + t2, t0 = num4[k + n] + t1; t[k + 2 * n] = t2; t[k + n] = t1; t[k] = t0; }
 
+  lap("quotient");
   // openings
   Fr omega = root_of_unity(c.log_n);
   Fr y[5], pts5[5] = {zeta, zeta, zeta, zeta, zeta * omega};
@@ -571,6 +595,7 @@ int oracle_prove(void* cv, const uint64_t* const advice[3], const uint64_t* publ
   Aff tcom[3];
   for (int i = 0; i < 3; i++) { std::vector<Fr> s(t.begin() + i * n, t.begin() + (i + 1) * n); tcom[i] = commit(c, s); }
 
+  lap("open+commit");
   uint8_t* w = out;
   auto pg = [&](const Aff& p) { ser_g1(p, w); w += 96; };
   auto pf = [&](const Fr& x) { Fr cn = x.canonical(); memcpy(w, cn.l, 32); w += 32; };

@@ -18,7 +18,7 @@ def build(force=False) -> Path:
     OUT.parent.mkdir(exist_ok=True)
     if not force and OUT.exists() and OUT.stat().st_mtime >= SRC.stat().st_mtime:
         return OUT
-    cmd = ["g++", "-O3", "-fopenmp", "-shared", "-fPIC", "-std=c++17", str(SRC), "-o", str(OUT)]
+    cmd = ["g++", "-O3", "-mbmi2", "-madx", "-fopenmp", "-shared", "-fPIC", "-std=c++17", str(SRC), "-o", str(OUT)]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + res.stderr)

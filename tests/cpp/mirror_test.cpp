@@ -118,8 +118,7 @@ static void prove_and_print(const Context& ctx, const char* name, const Fr& tau,
   CHECK((std::string(name) + ": tampered proof rejected").c_str(), !circuit.verify(bad));
 }
 
-static int device() {
-  Context ctx;
+static int device(const Context& ctx) {
   const Fr tau = Fr::rand_stream(1, 1)[0];
   std::array<Fr, 9> blinders;
   {
@@ -195,7 +194,24 @@ static int device() {
 
 int main(int argc, char** argv) {
   std::string mode = argc > 1 ? argv[1] : "host";
-  int f = mode == "device" ? device() : host_only();
+  int f;
+  if (mode == "device") {
+    f = device(Context());
+  } else if (mode == "multi") {   // `multi 0,0,0`: the same program on a device group (three ranks on device 0)
+    std::vector<int> devices;
+    std::string list = argc > 2 ? argv[2] : "0,0";
+    for (size_t pos = 0; pos <= list.size();) {
+      size_t comma = list.find(',', pos);
+      if (comma == std::string::npos) comma = list.size();
+      devices.push_back(std::stoi(list.substr(pos, comma - pos)));
+      pos = comma + 1;
+    }
+    Context ctx = Context::multi(devices);
+    std::printf("ranks %d\n", ctx.ranks());
+    f = device(ctx);
+  } else {
+    f = host_only();
+  }
   std::printf("%d failures\n", f);
   return f ? 1 : 0;
 }

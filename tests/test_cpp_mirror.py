@@ -39,9 +39,12 @@ def test_cpp_mirror_compiles_and_host_side_works(tmp_path):
 
 
 @pytest.mark.gpu
-def test_cpp_mirror_reproduces_golden_proofs_on_device(tmp_path):
+@pytest.mark.parametrize("mode", [["device"], ["multi", "0,0"], ["multi", "0,0,0"]])
+def test_cpp_mirror_reproduces_golden_proofs_on_device(tmp_path, mode):
+    """`multi`: the same single-process program on a device group (tp_ctx_create_multi) -- ranks sharing device 0, so
+    every MSM / quotient / upload runs sharded with the library's own exchange and must give the same bytes."""
     exe = _build(tmp_path)
-    res = subprocess.run([exe, "device"], capture_output=True, text=True, timeout=600)
+    res = subprocess.run([exe] + mode, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0 and "FAIL" not in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
     seen = {}
     for line in res.stdout.splitlines():

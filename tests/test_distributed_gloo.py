@@ -1,7 +1,10 @@
-"""CPU, world_size 2 over gloo: the multi-GPU plan of SURVEY.md 8(e) -- every rank computes the MSM
-of its contiguous point range, partial points are all-gathered (144 B each) and summed -- checked
-with the oracle standing in for the per-rank device MSM.  Exercises the same allgather callback
-shape the C ABI uses (bytes in, world x bytes out) and the shard arithmetic of msm_dev."""
+"""CPU, world_size 2 over gloo: the multi-GPU plan of SURVEY.md 8(e) as csrc/msm.cu runs it -- every rank extracts the
+signed window digits of ALL scalars, keeps the buckets it owns (bucket b belongs to rank b % world as local bucket
+b // world), reduces them to P = sum_j B_j and F = sum_j j B_j, the ranks' (P, F) are all-gathered, and every rank
+finishes with  sum_r [ world * F_r + (r + 1) * P_r ]  -- checked with the oracle's curve arithmetic standing in for the
+device kernels, and the quotient's coset split with its one broadcast per coset.  The arithmetic identities the CUDA
+path relies on are what is under test here; the kernels themselves are compared with these results on the GPU
+(tests/test_gpu_multirank.py)."""
 import os
 import sys
 
@@ -13,14 +16,51 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _shard(length, rank, world):
-    per = (length + world - 1) // world          # typlonk_b200/csrc/msm.cu: msm_dev
-    first = per * rank
-    cnt = 0 if first >= length else min(per, length - first)
-    return first, cnt
+def _signed_digits(s, c, nwin):
+    """typlonk_b200/csrc/msm.cu k_msm_digits: window digits in [-2^(c-1), 2^(c-1)] with carry."""
+    out, carry = [], 0
+    for w in range(nwin):
+        raw = ((s >> (w * c)) & ((1 << c) - 1)) + carry
+        carry = 0
+        if raw > (1 << (c - 1)):
+            raw -= 1 << c
+            carry = 1
+        out.append(raw)
+    assert carry == 0
+    return out
 
 
-def _worker(rank, world, port, n, q):
+def _windows_for(c):
+    nwin = (255 + c - 1) // c
+    if 255 - (nwin - 1) * c == c:
+        nwin += 1
+    return nwin
+
+
+def _rank_partial(pts, scalars, c, rank, world):
+    """(P, F) of the buckets rank `rank` owns; the fixed-base table level 2^(c w) P_i is a scalar multiple here."""
+    from oracle.pyoracle import curve
+    nwin = _windows_for(c)
+    buckets = {}
+    for p, s in zip(pts, scalars):
+        for w, d in enumerate(_signed_digits(s, c, nwin)):
+            if d == 0:
+                continue
+            b = abs(d) - 1
+            if b % world != rank:
+                continue
+            t = curve.g1_mul(p, 1 << (c * w))          # reduced modulo r inside (the points have order r)
+            if d < 0:
+                t = curve.g1_neg(t)
+            buckets[b // world] = curve.g1_add(buckets.get(b // world), t)
+    P = F = None
+    for j, pt in buckets.items():
+        P = curve.g1_add(P, pt)
+        F = curve.g1_add(F, curve.g1_mul(pt, j) if j else None)
+    return P, F
+
+
+def _worker(rank, world, port, n, c, q):
     sys.path.insert(0, ROOT)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,61 +73,73 @@ def _worker(rank, world, port, n, q):
         pts.append(acc)
         acc = curve.g1_mul(acc, tau)
     scalars = rng.fr_rand_stream(3, n)
-    first, cnt = _shard(n, rank, world)
-    part = curve.g1_msm(pts[first:first + cnt], scalars[first:first + cnt])
+    scalars[0] = fields.R_MOD - 1                     # top window + carries
+    if n > 3:
+        scalars[1], scalars[2], scalars[3] = 0, 5, 5  # zero digit rows, a repeated bucket
+    P, F = _rank_partial(pts, scalars, c, rank, world)
 
-    def allgather(data: bytes) -> bytes:            # the callback shape of Context.set_shard
-        send = torch.frombuffer(bytearray(data), dtype=torch.uint8)
-        recv = torch.empty(world * len(data), dtype=torch.uint8)
-        dist.all_gather_into_tensor(recv, send)
-        return recv.numpy().tobytes()
+    def enc(pt):   # 144-byte Jacobian (x, y, z) Montgomery, z = 0 for the identity
+        if pt is None:
+            return fields.fq_mont_bytes(1) * 2 + bytes(48)
+        return fields.fq_mont_bytes(pt[0]) + fields.fq_mont_bytes(pt[1]) + fields.fq_mont_bytes(1)
 
-    # partial point as 144-byte Jacobian (x, y, z) Montgomery, z = 0 for the identity
-    if part is None:
-        send = fields.fq_mont_bytes(1) * 2 + bytes(48)
-    else:
-        send = fields.fq_mont_bytes(part[0]) + fields.fq_mont_bytes(part[1]) + fields.fq_mont_bytes(1)
-    recv = allgather(send)
-    total = None
-    for r in range(world):
-        blob = recv[144 * r:144 * (r + 1)]
+    def dec(blob):
         if blob[96:] == bytes(48):
-            continue
-        total = curve.g1_add(total, (fields.fq_from_mont_bytes(blob[:48]), fields.fq_from_mont_bytes(blob[48:96])))
-    full = curve.g1_msm(pts, scalars)
-    q.put((rank, total == full))
+            return None
+        return (fields.fq_from_mont_bytes(blob[:48]), fields.fq_from_mont_bytes(blob[48:96]))
+
+    send = torch.frombuffer(bytearray(enc(P) + enc(F)), dtype=torch.uint8)
+    recv = torch.empty(world * 288, dtype=torch.uint8)
+    dist.all_gather_into_tensor(recv, send)
+    raw = recv.numpy().tobytes()
+    # the host tail of msm_local: F slots summed over ranks, the P points weighted by running sums
+    fsum = None
+    for r in range(world):
+        fsum = curve.g1_add(fsum, dec(raw[288 * r + 144:288 * r + 288]))
+    run = pw = None
+    for r in reversed(range(world)):
+        run = curve.g1_add(run, dec(raw[288 * r:288 * r + 144]))
+        pw = curve.g1_add(pw, run)
+    total = curve.g1_add(curve.g1_mul(fsum, world) if fsum else None, pw)
+    q.put((rank, total == curve.g1_msm(pts, scalars)))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n", [5, 64])
-def test_sharded_msm_combines_to_full_msm(n):
+@pytest.mark.parametrize("n,c", [(5, 4), (24, 7)])
+def test_bucket_sharded_msm_combines_to_full_msm(n, c):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + (os.getpid() % 1000) + n
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, c, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=240) for _ in range(world)]
+    results = [q.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
 
 
-def test_shard_ranges_cover_exactly():
-    for length in (0, 1, 7, 8, 9, 1 << 20, (1 << 20) - 1):
-        for world in (1, 2, 4, 8):
-            spans = [_shard(length, r, world) for r in range(world)]
-            covered = sum(c for _, c in spans)
-            assert covered == length
-            pos = 0
-            for first, cnt in spans:
-                if cnt:
-                    assert first == pos
-                    pos += cnt
+def test_bucket_ownership_covers_every_digit_once():
+    import random
+    rnd = random.Random(3)
+    for c in (3, 8, 20):
+        nwin = _windows_for(c)
+        for world in (1, 2, 3, 8):
+            for _ in range(50):
+                s = rnd.randrange(0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001)
+                digits = _signed_digits(s, c, nwin)
+                assert sum(d << (c * w) for w, d in enumerate(digits)) == s
+                owners = [(abs(d) - 1) % world for d in digits if d]
+                assert all(0 <= o < world for o in owners)
+                # local index and weight: global bucket b counts b + 1 = world * (b // world) + (b % world) + 1
+                for d in digits:
+                    if d:
+                        b = abs(d) - 1
+                        assert world * (b // world) + (b % world) + 1 == abs(d)
 
 
-# ---- quotient sharded by coset (api.cu prove_resident, tp_ctx_set_broadcast) ------------------------------
+# ---- quotient sharded by coset (api.cu prove_resident, comm_bcast) ------------------------------
 def _coset_owner(k, world):
     return k % world if world < 4 else k * (world // 4)   # typlonk_b200/csrc/api.cu: owner(k)
 

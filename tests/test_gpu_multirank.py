@@ -1,88 +1,84 @@
-"""GPU, several ranks on ONE device (gloo carries the collectives through host memory): the
-multi-GPU plan of SURVEY.md 8(e) exactly as bench.py runs it under torchrun -- every MSM sharded
-by contiguous point range with the 144-byte partial points all-gathered, the quotient sharded by
-coset of the 4n domain with one device broadcast per coset -- must produce the proof bytes of the
-single-rank prover (and of the C++ oracle).  world = 2, 3 and 4 cover 2 / uneven / 1 coset per rank."""
+"""GPU, several ranks on ONE device: the multi-GPU plan of SURVEY.md 8(e) exactly as the library runs it on a box of
+B200s -- every MSM sharded by bucket (rank r owns the buckets b with b mod world == r) with the per-rank reduction
+outputs all-gathered and combined on the device, the quotient sharded by coset of the 4n domain with one device
+broadcast per coset, the witness upload sharded by rows -- must produce the bytes of the single-rank prover and of the
+C++ oracle.  `Context.multi([0] * world)` is the single-process device group of tp_ctx_create_multi with every rank
+on device 0; the ranks then exchange through peer copies instead of NCCL, everything else is the code the 8-GPU run
+executes.  world = 2, 3, 4, 8 cover 2 / uneven / 1 / 0-or-1 cosets per rank and a non-power-of-two bucket split."""
 import os
-import sys
+import random
 
 import pytest
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, log_n, q):
-    try:
-        sys.path.insert(0, ROOT)
-        os.environ["MASTER_ADDR"] = "127.0.0.1"
-        os.environ["MASTER_PORT"] = str(port)
-        dist.init_process_group("gloo", rank=rank, world_size=world)
-        from typlonk_b200 import field as F, synthetic
-        from typlonk_b200.ffi import Context, DeviceView
-        dev = torch.device("cuda", 0)
-        st = torch.cuda.Stream(device=dev)
-        torch.cuda.set_stream(st)
-        ctx = Context(0, st.cuda_stream)
-
-        def allgather(data: bytes) -> bytes:
-            send = torch.frombuffer(bytearray(data), dtype=torch.uint8)
-            recv = torch.empty(world * len(data), dtype=torch.uint8)
-            dist.all_gather_into_tensor(recv, send)
-            return recv.numpy().tobytes()
-
-        def bcast(ptr: int, nbytes: int, root: int):
-            t = torch.as_tensor(DeviceView(ptr, nbytes), device=dev)
-            host = t.cpu()                      # synchronises with the ctx stream (current stream)
-            dist.broadcast(host, src=root)
-            if rank != root:
-                t.copy_(host)
-                torch.cuda.current_stream().synchronize()
-
-        ctx.set_shard(rank, world, allgather)
-        ctx.set_broadcast(bcast)
-        n = 1 << log_n
-        circuit = synthetic.mul_chain_direct(ctx, log_n)
-        cols = synthetic.mul_chain_witness(n - 3, n)
-        col_bytes = [F.fr_vec_to_bytes(c) for c in cols]
-        proof = circuit.handle.prove(col_bytes, bytes(32 * n))
-        # the short public-input vector of prove()'s caller: three sliced columns + one whole 32-byte vector
-        short = circuit.handle.prove_inputs(col_bytes, bytes(32))
-        if short != proof:
-            proof = "error: tp_prove_inputs and tp_prove disagree on rank %d" % rank
-        q.put((rank, proof))
-        dist.barrier()
-        ctx.close()
-        dist.destroy_process_group()
-    except Exception as e:  # noqa: BLE001
-        import traceback
-        q.put((rank, "error: %r\n%s" % (e, traceback.format_exc())))
-
-
-@pytest.mark.parametrize("world,log_n", [(2, 10), (3, 8), (4, 12)])
+@pytest.mark.parametrize("world,log_n", [(2, 10), (3, 8), (4, 12), (8, 11), (5, 3)])
 def test_sharded_prover_matches_single_rank_and_oracle(ctx, world, log_n):
     from oracle import coracle
     from typlonk_b200 import field as F, synthetic
+    from typlonk_b200.ffi import Context
     n = 1 << log_n
     circuit = synthetic.mul_chain_direct(ctx, log_n)
-    cols = synthetic.mul_chain_witness(n - 3, n)
-    single = circuit.handle.prove([F.fr_vec_to_bytes(c) for c in cols], bytes(32 * n))
+    cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
+    single = circuit.handle.prove(cols, bytes(32 * n))
     tau_b, sel, perm, ocols, pi = coracle.mul_chain_inputs(log_n)
     oc = coracle.Circuit(tau_b, sel, perm, n)
     assert oc.prove(ocols, pi) == single
     oc.close()
 
-    mpc = mp.get_context("spawn")
-    q = mpc.Queue()
-    port = 29700 + (os.getpid() % 1000) + world
-    procs = [mpc.Process(target=_worker, args=(r, world, port, log_n, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    results = dict(q.get(timeout=600) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
-    for r in range(world):
-        assert results[r] == single, "rank %d: %s" % (r, results[r] if isinstance(results[r], str) else "proof differs")
+    group = Context.multi([0] * world)
+    assert group.group_size() == (world, False)
+    gc = synthetic.mul_chain_direct(group, log_n)
+    assert gc.handle.prove(cols, bytes(32 * n)) == single
+    # the short public-input vector of prove()'s caller: three sliced columns + one whole 32-byte vector
+    assert gc.handle.prove_inputs(cols, bytes(32)) == single
+    assert gc.handle.verify(single, bytes(32))
+    bad = bytearray(single)
+    bad[192] ^= 1
+    assert not gc.handle.verify(bytes(bad), bytes(32))
+    assert group.launch_count() > 0
+    group.close()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_commit_edge_scalars(ctx, world):
+    """tp_commit / tp_open on a device group against the single-device result: uniform scalars, scalars below 2^16
+    (every digit in the lowest window: with contiguous bucket ranges one rank would get all of them), one repeated
+    scalar (a single bucket: all the work of a window on one rank), zeros, and r - 1 (top digit + signed carries)."""
+    from typlonk_b200 import field as F
+    from typlonk_b200.ffi import Context
+    from oracle.pyoracle import rng
+    n = 3000
+    tau = F.fr_to_bytes(rng.fr_rand_stream(1, 1)[0])
+    srs = ctx.srs_from_secret(tau, n - 3)
+    group = Context.multi([0] * world)
+    gsrs = group.srs_from_secret(tau, n - 3)
+    assert gsrs.download(0, 5) == srs.download(0, 5) and len(gsrs) == len(srs)
+    rnd = random.Random(7)
+    cases = {
+        "uniform": [rnd.randrange(F.R_MOD) for _ in range(n)],
+        "below_2^16": [rnd.randrange(1 << 16) for _ in range(n)],
+        "all_equal": [5] * n,
+        "zeros": [0] * n,
+        "r_minus_1_and_sparse": [F.R_MOD - 1 if i % 7 == 0 else 0 for i in range(n)],
+        "short": [rnd.randrange(F.R_MOD) for _ in range(3)],
+    }
+    for name, sc in cases.items():
+        raw = F.fr_vec_to_bytes(sc)
+        assert group.commit(gsrs, raw) == ctx.commit(srs, raw), name
+    z = F.fr_to_bytes(12345)
+    assert group.open(gsrs, F.fr_vec_to_bytes(cases["uniform"]), z) == ctx.open(srs, F.fr_vec_to_bytes(cases["uniform"]), z)
+    assert group.commit(gsrs, b"") == ctx.commit(srs, b"")
+    gsrs.destroy()
+    group.close()
+    srs.destroy()
+
+
+def test_group_refuses_device_pointer_entry_points(ctx):
+    from typlonk_b200.ffi import Context, TyplonkError
+    group = Context.multi([0, 0])
+    with pytest.raises(TyplonkError):
+        group.ntt_dev(0x1000, 4)
+    group.close()

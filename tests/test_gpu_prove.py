@@ -1,6 +1,8 @@
 """GPU parity tests of the full prover (tp_circuit_compile + tp_prove through the Python mirror of
 the reference API) against the CPU oracle: every proof byte equal under fixed tau / blinders, and
 verify() (oracle, pairings) accepts."""
+import os
+
 import pytest
 
 from oracle.pyoracle import builder as obuilder, plonk as oplonk, rng
@@ -123,6 +125,46 @@ def test_mul_chain_2_16_bytes_vs_c_oracle(ctx):
     assert [F.g1_from_abi(c) for c in oc.fixed_commitments()] == circuit.fixed_commitments
     assert oc.prove(ocols, pi) == proof
     oc.close()
+
+
+def test_mul_chain_2_20_bytes_vs_c_oracle_live_and_golden(ctx):
+    """BASELINE.json configs[2]: the 2^20-gate proof, ALL bytes, against (a) the C++ oracle run here on the same inputs
+    (about a minute of host time) and (b) the committed golden proof (tools/make_golden_big.py); both through tp_prove
+    (host buffers) and on a 2-rank device group (sharded MSM / quotient / upload)."""
+    import json
+    from oracle import coracle
+    from typlonk_b200 import field as F, synthetic
+    from typlonk_b200.ffi import Context
+    log_n = 20
+    n = 1 << log_n
+    circuit = synthetic.mul_chain_direct(ctx, log_n)
+    cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
+    proof = circuit.handle.prove(cols, bytes(32 * n))
+    circuit.handle.destroy()
+    circuit.srs.handle.destroy()
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mulchain_big.json")))["2^20"]
+    assert proof.hex() == gold["proof_hex"]
+    tau_b, sel, perm, ocols, pi = coracle.mul_chain_inputs(log_n)
+    oc = coracle.Circuit(tau_b, sel, perm, n)
+    assert oc.prove(ocols, pi) == proof
+    oc.close()
+    group = Context.multi([0, 0])
+    gc = synthetic.mul_chain_direct(group, log_n)
+    assert gc.handle.prove_inputs(cols, bytes(32)) == proof
+    group.close()
+
+
+def test_golden_big_proofs_2_16_and_2_18(ctx):
+    import json
+    from typlonk_b200 import field as F, synthetic
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "mulchain_big.json")))
+    for log_n in (16, 18):
+        n = 1 << log_n
+        circuit = synthetic.mul_chain_direct(ctx, log_n)
+        cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
+        assert circuit.handle.prove_inputs(cols, bytes(32)).hex() == gold["2^%d" % log_n]["proof_hex"]
+        circuit.handle.destroy()
+        circuit.srs.handle.destroy()
 
 
 @pytest.mark.parametrize("log_n", [10, 20])

@@ -67,6 +67,17 @@ def test_proof_decode_rejects_malformed():
     ok[0:96] = F.g1_serialize_unchecked(None)
     fixed, _ = ffi.proof_decode(bytes(ok))
     assert fixed[:96] == F.g1_serialize_unchecked(None)
+    # ... and ONLY in that encoding: the flag over any other (x, y) is a second spelling of the same point
+    for x, y in ((5, 7), (0, 0), (0, 2), (1, 1)):
+        bad = _golden()
+        rec = bytearray(x.to_bytes(48, "little") + y.to_bytes(48, "little"))
+        rec[95] |= 0x40
+        bad[0:96] = rec
+        with pytest.raises(ffi.Malformed):
+            ffi.proof_decode(bytes(bad))
+        # the verifier's own parser treats it as malformed too (no device needed: rejected while parsing)
+        with pytest.raises(ffi.TyplonkError):
+            ffi.proof_challenges(bytes(bad[:1472]))
 
 
 def test_proof_encode_checks_its_arguments():

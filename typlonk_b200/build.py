@@ -15,7 +15,7 @@ ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
 LIBDIR = ROOT / "lib"
 LIB = LIBDIR / "libtyplonk_b200.so"
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu", "wire.cu", "trace.cpp"]
+SOURCES = ["api.cu", "comm.cu", "ntt.cu", "msm.cu", "poly.cu", "srs.cu", "selftest.cu", "verify.cu", "wire.cu", "trace.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
@@ -71,7 +71,8 @@ def build(force: bool = False, verbose: bool = False, defines=(), tag: str = "")
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs)]
+    # NCCL is loaded with dlopen at run time (comm.cu): only libdl is linked
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs), "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (res.stdout, res.stderr))

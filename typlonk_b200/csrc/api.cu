@@ -33,6 +33,19 @@ static unsigned log2_exact(size_t n) {
   return l;
 }
 
+// ---- device groups (tp_ctx_create_multi, comm.cu) ----------------------------------------------------------------
+// A group front holds no device state: every entry point below starts with a branch that runs the same entry point on
+// every rank's own context from that rank's worker thread, and hands back rank 0's outputs (all ranks compute the same
+// bytes).  Entry points without a collective inside run on rank 0 alone.
+static inline bool is_group(const tp_ctx* ctx) { return ctx && !ctx->children.empty(); }
+static int on_rank0(tp_ctx* g, const std::function<int(tp_ctx*)>& fn) {
+  return group_run(g, [&](tp_ctx* c, int r) { return r == 0 ? fn(c) : TP_OK; });
+}
+#define TP_NO_GROUP(ctx, what)                                                                                          \
+  do {                                                                                                                \
+    if (is_group(ctx)) return fail(ctx, TP_ERR_INVALID_ARG, what ": device pointers belong to one device -- not available on a device group"); \
+  } while (0)
+
 extern "C" {
 
 // ---- context ------------------------------------------------------------------------------
@@ -71,7 +84,13 @@ int tp_ctx_create(int device, void* stream, tp_ctx** out) {
 
 int tp_ctx_destroy(tp_ctx* ctx) {
   if (!ctx) return TP_OK;
+  if (is_group(ctx)) {
+    group_destroy(ctx);
+    delete ctx;
+    return TP_OK;
+  }
   cudaSetDevice(ctx->device);
+  comm_release(ctx);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
@@ -86,7 +105,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
   }
   DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_sorted,
                     &ctx->msm_sorted_keys, &ctx->msm_hist, &ctx->msm_offsets, &ctx->msm_blocksums, &ctx->msm_buckets,
-                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_aff_pts,
+                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_gather, &ctx->msm_aff_pts,
                     &ctx->msm_sorted2, &ctx->msm_aff_cnt, &ctx->msm_aff_plan, &ctx->msm_aff_rec, &ctx->flag};
   for (auto* b : bufs) release(*b);
   for (auto& b : ctx->scan_tmp) release(b);
@@ -106,29 +125,15 @@ int tp_ctx_destroy(tp_ctx* ctx) {
 const char* tp_last_error(tp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 int tp_sync(tp_ctx* ctx) {
-  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  return TP_OK;
-}
-
-int tp_ctx_set_shard(tp_ctx* ctx, int rank, int world, tp_allgather_fn allgather, void* user) {
-  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, TP_ERR_INVALID_ARG, "set_shard: bad rank/world");
-  if (world > 1 && !allgather) return fail(ctx, TP_ERR_INVALID_ARG, "set_shard: world > 1 needs an all-gather");
-  ctx->rank = rank;
-  ctx->world = world;
-  ctx->allgather = allgather;
-  ctx->allgather_user = user;
-  return TP_OK;
-}
-
-int tp_ctx_set_broadcast(tp_ctx* ctx, tp_bcast_dev_fn bcast, void* user) {
   if (!ctx) return TP_ERR_INVALID_ARG;
-  ctx->bcast = bcast;
-  ctx->bcast_user = user;
+  if (is_group(ctx)) return group_run(ctx, [](tp_ctx* c, int) { return tp_sync(c); });
+  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return TP_OK;
 }
 
 int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
   if (!ctx || !name) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return group_run(ctx, [&](tp_ctx* c, int) { return tp_ctx_set_option(c, name, value); });
   if (strcmp(name, "msm_affine_rounds") == 0) {
     if (value < 0 || value > 8) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_affine_rounds must be 0..8");
     ctx->msm_aff_rounds = (unsigned)value;
@@ -144,6 +149,7 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
 
 int tp_ctx_get_stat(tp_ctx* ctx, const char* name, double* out) {
   if (!ctx || !name || !out) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_ctx_get_stat(c, name, out); });
   const struct { const char* n; double v; } stats[] = {
       {"msm_entries", ctx->stat_msm_entries}, {"msm_calls", ctx->stat_msm_calls}, {"msm_window_bits", ctx->stat_msm_c},
       {"msm_windows", ctx->stat_msm_nwin},    {"msm_table_levels", ctx->stat_msm_levels}, {"msm_chunk", ctx->stat_msm_chunk}};
@@ -170,11 +176,13 @@ static int prof_collect(tp_ctx* ctx) {
   return TP_OK;
 }
 int tp_prof_enable(tp_ctx* ctx, int on) {
+  if (is_group(ctx)) return group_run(ctx, [&](tp_ctx* c, int) { return tp_prof_enable(c, on); });
   TP_TRY(prof_collect(ctx));
   ctx->prof = on != 0;
   return TP_OK;
 }
 int tp_prof_reset(tp_ctx* ctx) {
+  if (is_group(ctx)) return group_run(ctx, [](tp_ctx* c, int) { return tp_prof_reset(c); });
   TP_TRY(prof_collect(ctx));
   for (int i = 0; i < TP_PHASE_COUNT; i++) {
     ctx->prof_ms[i] = 0;
@@ -185,6 +193,7 @@ int tp_prof_reset(tp_ctx* ctx) {
   return TP_OK;
 }
 int tp_prof_get(tp_ctx* ctx, double* ms, uint64_t* launches) {
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_prof_get(c, ms, launches); });   // rank 0's timers
   TP_TRY(prof_collect(ctx));
   for (int i = 0; i < TP_PHASE_COUNT; i++) {
     if (ms) ms[i] = ctx->prof_ms[i];
@@ -193,7 +202,9 @@ int tp_prof_get(tp_ctx* ctx, double* ms, uint64_t* launches) {
   return TP_OK;
 }
 int tp_launch_count(tp_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return TP_ERR_INVALID_ARG;
   *out = ctx->launches;
+  for (tp_ctx* c : ctx->children) *out += c->launches;   // a group: kernels launched on all its devices
   return TP_OK;
 }
 
@@ -208,11 +219,10 @@ int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
   size_t budget = (size_t)(0.45 * (double)free_b);
-  // the window size is planned for the point range ONE rank accumulates (set the shard before
-  // creating the SRS): a shard of n / world points wants a smaller window than n points
-  size_t per_rank = (len + (size_t)ctx->world - 1) / (size_t)ctx->world;
+  // sharded by bucket, accumulation and reduction both shrink 1 / world: the window is the one a single GPU would pick
+  // for the whole length (the rank count only enters through the fixed per-set overhead)
   for (int attempt = 0; attempt < 2; attempt++) {
-    msm_choose_tables(per_rank, len, attempt == 0 ? budget : 0, &s->c, &s->levels);
+    msm_choose_tables(len, len, attempt == 0 ? budget : 0, (unsigned)ctx->world, &s->c, &s->levels);
     cudaError_t e = cudaMalloc(&s->g1, (len ? len : 1) * (size_t)s->levels * sizeof(G1Affine));
     if (e == cudaSuccess) {
       *out = s;
@@ -227,9 +237,27 @@ int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out) {
 }  // namespace tp
 }  // extern "C++"
 
+// group front of an SRS: `make(rank context, &part)` on every rank
+static int srs_group_new(tp_ctx* g, tp_srs** out, const std::function<int(tp_ctx*, tp_srs**)>& make) {
+  tp_srs* front = new tp_srs();
+  front->parts.assign(g->children.size(), nullptr);
+  int rc = group_run(g, [&](tp_ctx* c, int r) { return make(c, &front->parts[r]); });
+  if (rc != TP_OK) {
+    group_run(g, [&](tp_ctx* c, int r) { return tp_srs_destroy(c, front->parts[r]); });
+    delete front;
+    return rc;
+  }
+  front->len = front->parts[0]->len;
+  front->c = front->parts[0]->c;
+  front->levels = front->parts[0]->levels;
+  *out = front;
+  return TP_OK;
+}
+
 int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs** out) {
   if (!ctx) return TP_ERR_INVALID_ARG;
   if (!out || !tau) return fail(ctx, TP_ERR_INVALID_ARG, "srs_from_secret: null argument");
+  if (is_group(ctx)) return srs_group_new(ctx, out, [&](tp_ctx* c, tp_srs** part) { return tp_srs_from_secret(c, tau, gates, part); });
   size_t len = gates + 3;
   tp_srs* s = nullptr;
   TP_TRY(srs_alloc(ctx, len, &s));
@@ -249,7 +277,9 @@ int tp_srs_from_secret(tp_ctx* ctx, const uint64_t tau[4], size_t gates, tp_srs*
   return TP_OK;
 }
 int tp_srs_upload(tp_ctx* ctx, const uint8_t* g1_xy, size_t len, tp_srs** out) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
   if (!out || (!g1_xy && len)) return fail(ctx, TP_ERR_INVALID_ARG, "srs_upload: null argument");
+  if (is_group(ctx)) return srs_group_new(ctx, out, [&](tp_ctx* c, tp_srs** part) { return tp_srs_upload(c, g1_xy, len, part); });
   tp_srs* s = nullptr;
   TP_TRY(srs_alloc(ctx, len, &s));
   int rc = h2d(ctx, s->g1, g1_xy, len * 96);
@@ -269,11 +299,18 @@ int tp_srs_len(const tp_srs* srs, size_t* len) {
   return TP_OK;
 }
 int tp_srs_g1_download(tp_ctx* ctx, const tp_srs* srs, size_t offset, size_t count, uint8_t* out_xy) {
+  if (!ctx || !srs) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_srs_g1_download(c, srs->parts[0], offset, count, out_xy); });
   if (offset + count > srs->len) return fail(ctx, TP_ERR_INVALID_ARG, "srs_download: range out of bounds");
   return d2h_sync(ctx, out_xy, srs->g1 + offset, count * 96);
 }
 int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs) {
   if (!srs) return TP_OK;
+  if (is_group(ctx)) {
+    group_run(ctx, [&](tp_ctx* c, int r) { return tp_srs_destroy(c, (size_t)r < srs->parts.size() ? srs->parts[r] : nullptr); });
+    delete srs;
+    return TP_OK;
+  }
   cudaStreamSynchronize(ctx->stream);
   cudaFree(srs->g1);
   srs_pairing_free(srs);
@@ -283,9 +320,18 @@ int tp_srs_destroy(tp_ctx* ctx, tp_srs* srs) {
 
 // ---- KZG ------------------------------------------------------------------------------------
 int tp_commit_dev(tp_ctx* ctx, const tp_srs* srs, const void* coeffs_dev, size_t len, uint8_t out[TP_G1_BYTES]) {
+  if (!ctx || !srs || !out) return TP_ERR_INVALID_ARG;
+  TP_NO_GROUP(ctx, "commit_dev");
   return msm_dev(ctx, srs, (const Fr*)coeffs_dev, len, out);
 }
 int tp_commit(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, uint8_t out[TP_G1_BYTES]) {
+  if (!ctx || !srs || !out || (len && !coeffs)) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) {
+    std::vector<uint8_t> outs(ctx->children.size() * TP_G1_BYTES);
+    TP_TRY(group_run(ctx, [&](tp_ctx* c, int r) { return tp_commit(c, srs->parts[r], coeffs, len, &outs[(size_t)r * TP_G1_BYTES]); }));
+    memcpy(out, outs.data(), TP_G1_BYTES);
+    return TP_OK;
+  }
   if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
   TP_TRY(ensure(ctx, ctx->msm_scalars, (len ? len : 1) * sizeof(Fr)));
   TP_TRY(h2d(ctx, ctx->msm_scalars.p, coeffs, len * sizeof(Fr)));
@@ -293,6 +339,18 @@ int tp_commit(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len
 }
 int tp_open(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, const uint64_t z[4],
             uint8_t w_out[TP_G1_BYTES], uint64_t y_out[4]) {
+  if (!ctx || !srs || !z || !w_out || !y_out) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) {
+    const size_t nr = ctx->children.size();
+    std::vector<uint8_t> ws(nr * TP_G1_BYTES);
+    std::vector<uint64_t> ys(nr * 4);
+    TP_TRY(group_run(ctx, [&](tp_ctx* c, int r) {
+      return tp_open(c, srs->parts[r], coeffs, len, z, &ws[(size_t)r * TP_G1_BYTES], &ys[(size_t)r * 4]);
+    }));
+    memcpy(w_out, ws.data(), TP_G1_BYTES);
+    memcpy(y_out, ys.data(), 32);
+    return TP_OK;
+  }
   if (len == 0) return fail(ctx, TP_ERR_EMPTY_POLY, "open: empty polynomial");
   if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "open: polynomial longer than the SRS");
   TP_TRY(ensure(ctx, ctx->msm_scalars, len * sizeof(Fr)));
@@ -308,9 +366,13 @@ int tp_open(tp_ctx* ctx, const tp_srs* srs, const uint64_t* coeffs, size_t len, 
 
 // ---- NTT ------------------------------------------------------------------------------------
 int tp_ntt_dev(tp_ctx* ctx, void* data_dev, unsigned log_n, int inverse, const uint64_t* coset) {
+  if (!ctx || !data_dev) return TP_ERR_INVALID_ARG;
+  TP_NO_GROUP(ctx, "ntt_dev");
   return ntt_dev(ctx, (const Fr*)data_dev, (Fr*)data_dev, log_n, inverse != 0, coset);
 }
 int tp_ntt(tp_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, const uint64_t* coset) {
+  if (!ctx || !data) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_ntt(c, data, log_n, inverse, coset); });   // one transform: one device
   if (log_n > 28) return fail(ctx, TP_ERR_INVALID_ARG, "ntt: log_n > 28");
   size_t n = (size_t)1 << log_n;
   TP_TRY(ensure(ctx, ctx->misc[3], n * sizeof(Fr)));
@@ -323,6 +385,8 @@ int tp_ntt(tp_ctx* ctx, uint64_t* data, unsigned log_n, int inverse, const uint6
 int tp_perm_prove(tp_ctx* ctx, const uint64_t* const values[3], const uint64_t* const id[3],
                   const uint64_t* const sigma[3], size_t n, const uint64_t beta[4], const uint64_t gamma[4],
                   uint64_t* out) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_perm_prove(c, values, id, sigma, n, beta, gamma, out); });
   if (n == 0) return fail(ctx, TP_ERR_INVALID_ARG, "perm_prove: n == 0");
   TP_TRY(ensure(ctx, ctx->misc[4], 9 * n * sizeof(Fr)));
   TP_TRY(ensure(ctx, ctx->misc[5], (n + 1) * sizeof(Fr)));
@@ -417,8 +481,33 @@ static int circuit_new(tp_ctx* ctx, const tp_srs* srs, size_t n, tp_circuit** ou
   return TP_OK;
 }
 
+// group front of a circuit: `make(rank context, rank, &part)` on every rank
+static int circuit_group_new(tp_ctx* g, const tp_srs* srs, size_t n, tp_circuit** out,
+                             const std::function<int(tp_ctx*, int, tp_circuit**)>& make) {
+  if (!out || !srs) return fail(g, TP_ERR_INVALID_ARG, "circuit: null argument");
+  if (srs->parts.size() != g->children.size()) return fail(g, TP_ERR_INVALID_ARG, "circuit: the SRS does not belong to this device group");
+  tp_circuit* front = new tp_circuit();
+  front->n = n;
+  front->log_n = log2_exact(n);
+  front->srs = srs;
+  front->parts.assign(g->children.size(), nullptr);
+  int rc = group_run(g, [&](tp_ctx* c, int r) { return make(c, r, &front->parts[r]); });
+  if (rc != TP_OK) {
+    group_run(g, [&](tp_ctx* c, int r) { return tp_circuit_destroy(c, front->parts[r]); });
+    delete front;
+    return rc;
+  }
+  *out = front;
+  return TP_OK;
+}
+
 int tp_circuit_destroy(tp_ctx* ctx, tp_circuit* c) {
   if (!c) return TP_OK;
+  if (is_group(ctx)) {
+    group_run(ctx, [&](tp_ctx* cc, int r) { return tp_circuit_destroy(cc, (size_t)r < c->parts.size() ? c->parts[r] : nullptr); });
+    delete c;
+    return TP_OK;
+  }
   cudaStreamSynchronize(ctx->stream);
   for (void* p : c->allocs) cudaFree(p);
   delete c;
@@ -427,6 +516,11 @@ int tp_circuit_destroy(tp_ctx* ctx, tp_circuit* c) {
 
 int tp_circuit_load(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const selectors[5], const uint64_t* const id[3],
                     const uint64_t* const sigma[3], const uint64_t cosets[3][4], size_t n, tp_circuit** out) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx))
+    return circuit_group_new(ctx, srs, n, out, [&](tp_ctx* c, int r, tp_circuit** part) {
+      return tp_circuit_load(c, srs->parts[r], selectors, id, sigma, cosets, n, part);
+    });
   tp_circuit* c = nullptr;
   TP_TRY(circuit_new(ctx, srs, n, &c));
   int rc = TP_OK;
@@ -449,6 +543,14 @@ int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const sel
                        size_t n, tp_circuit** out, uint8_t fixed_commitments[5 * TP_G1_BYTES]) {
   if (!ctx) return TP_ERR_INVALID_ARG;
   if (!selector_evals || !perm || !out) return fail(ctx, TP_ERR_INVALID_ARG, "circuit_compile: null argument");
+  if (is_group(ctx)) {
+    std::vector<uint8_t> fixed(ctx->children.size() * 5 * TP_G1_BYTES);
+    TP_TRY(circuit_group_new(ctx, srs, n, out, [&](tp_ctx* c, int r, tp_circuit** part) {
+      return tp_circuit_compile(c, srs->parts[r], selector_evals, perm, n, part, &fixed[(size_t)r * 5 * TP_G1_BYTES]);
+    }));
+    if (fixed_commitments) memcpy(fixed_commitments, fixed.data(), 5 * TP_G1_BYTES);
+    return TP_OK;
+  }
   for (size_t i = 0; i < 3 * n; i++)   // k_sigma_tables splits an entry by / n and % n: out of range = a wrong sigma, silently
     if (perm[i] >= 3 * n) return fail(ctx, TP_ERR_INVALID_ARG, "circuit_compile: permutation index out of range");
   tp_circuit* c = nullptr;
@@ -494,6 +596,7 @@ int tp_circuit_compile(tp_ctx* ctx, const tp_srs* srs, const uint64_t* const sel
 int tp_permutation_compile(tp_ctx* ctx, const uint64_t* perm, size_t n, uint64_t* const id[3], uint64_t* const sigma[3],
                            uint64_t cosets[3][4]) {
   if (!ctx) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_permutation_compile(c, perm, n, id, sigma, cosets); });
   if (!perm || !id || !sigma || n == 0 || (n & (n - 1))) return fail(ctx, TP_ERR_INVALID_ARG, "permutation_compile: n must be a power of two");
   for (size_t i = 0; i < 3 * n; i++)
     if (perm[i] >= 3 * n) return fail(ctx, TP_ERR_INVALID_ARG, "permutation_compile: index out of range");
@@ -525,6 +628,13 @@ int tp_permutation_compile(tp_ctx* ctx, const uint64_t* perm, size_t n, uint64_t
 }
 
 int tp_circuit_sigma_commitments(tp_ctx* ctx, tp_circuit* c, uint8_t out[3 * TP_G1_BYTES]) {
+  if (!ctx || !c || !out) return TP_ERR_INVALID_ARG;
+  if (is_group(ctx)) {
+    std::vector<uint8_t> outs(ctx->children.size() * 3 * TP_G1_BYTES);
+    TP_TRY(group_run(ctx, [&](tp_ctx* cc, int r) { return tp_circuit_sigma_commitments(cc, c->parts[r], &outs[(size_t)r * 3 * TP_G1_BYTES]); }));
+    memcpy(out, outs.data(), 3 * TP_G1_BYTES);
+    return TP_OK;
+  }
   if (!c->have_sigma_com) {
     const Fr* sets[3] = {c->sig_coef[0], c->sig_coef[1], c->sig_coef[2]};
     TP_TRY(msm_batch_dev(ctx, c->srs, sets, 3, c->n, c->sigma_com));
@@ -606,10 +716,11 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
 
   // quotient (proof.rs:292-375) on the 4n domain, coset by coset: five coset NTTs, the pointwise
   // numerator, one inverse coset NTT each.  Sharded over ranks by coset when the caller wired a
-  // device broadcast (tp_ctx_set_broadcast); every rank then rebuilds t from the four interpolants.
+  // context is sharded (comm.cu); every rank then rebuilds t from the four interpolants.
   {
     const Fr* src[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->pi_coef};
-    const bool shard = ctx->world > 1 && ctx->bcast != nullptr;
+    static const bool no_coset_shard = getenv("TP_NO_COSET_SHARD") && *getenv("TP_NO_COSET_SHARD") == '1';
+    const bool shard = comm_ready(ctx) && !no_coset_shard;
     auto owner = [&](unsigned k) { return !shard ? ctx->rank : (ctx->world < 4 ? (int)(k % ctx->world) : (int)(k * (ctx->world / 4))); };
     unsigned mine[4];
     int nmine = 0;
@@ -662,8 +773,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     }
     if (shard) {
       for (unsigned k = 0; k < 4; k++)
-        if (ctx->bcast(ctx->bcast_user, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)) != 0)
-          return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a quotient coset failed");
+        TP_TRY(comm_bcast(ctx, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)));
     }
     TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, qa.tw4, c->t));
   }
@@ -750,6 +860,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
 int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], const void* public_inputs_dev,
                  uint8_t* proof_out, size_t proof_cap) {
   if (!ctx) return TP_ERR_INVALID_ARG;
+  TP_NO_GROUP(ctx, "prove_dev");
   if (!c || !proof_out || !advice_dev || !advice_dev[0] || !advice_dev[1] || !advice_dev[2] || !public_inputs_dev)
     return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
@@ -766,6 +877,14 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
   if (!ctx) return TP_ERR_INVALID_ARG;
   if (!c || !proof_out) return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
   if (proof_cap < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "prove: proof buffer too small");
+  if (is_group(ctx)) {   // CompiledCircuit::prove as ONE call (proof.rs:26-57): every rank proves, rank 0's bytes go out
+    std::vector<uint8_t> proofs(ctx->children.size() * TP_PROOF_FIXED_BYTES);
+    TP_TRY(group_run(ctx, [&](tp_ctx* cc, int r) {
+      return prove_from_host(cc, c->parts[r], advice, public_inputs, n_public, &proofs[(size_t)r * TP_PROOF_FIXED_BYTES], TP_PROOF_FIXED_BYTES);
+    }));
+    memcpy(proof_out, proofs.data(), TP_PROOF_FIXED_BYTES);
+    return TP_OK;
+  }
   if (n_public > c->n) return fail(ctx, TP_ERR_INVALID_ARG, "prove: more public inputs than rows");
   if (!advice || !advice[0] || !advice[1] || !advice[2] || (n_public && !public_inputs))
     return fail(ctx, TP_ERR_INVALID_ARG, "prove: null argument");
@@ -778,7 +897,7 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
     TP_CUDA_OK(ctx, cudaMemsetAsync(c->pi_eval + n_public, 0, (c->n - n_public) * sizeof(Fr), ctx->stream));
   }
   const size_t world = (size_t)ctx->world;
-  if (ctx->world > 1 && ctx->bcast && c->n % world == 0 && c->n / world >= 64) {
+  if (comm_ready(ctx) && c->n % world == 0 && c->n / world >= 64) {
     // Sharded upload: every rank holds the same host columns, so each one sends only its row slice over PCIe
     // and the slices are exchanged over NVLink (one device broadcast per rank), then scattered into the columns.
     const size_t rows = c->n / world, slice = rows * sizeof(Fr);
@@ -786,8 +905,7 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
     for (int j = 0; j < ncols; j++)
       TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * ncols + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
     for (int r = 0; r < ctx->world; r++)
-      if (ctx->bcast(ctx->bcast_user, stage + (size_t)r * ncols * slice, ncols * slice, r) != 0)
-        return fail(ctx, TP_ERR_COLLECTIVE, "prove: broadcast of a witness slice failed");
+      TP_TRY(comm_bcast(ctx, stage + (size_t)r * ncols * slice, ncols * slice, r));
     for (int j = 0; j < ncols; j++)
       TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, ncols * slice, slice, world,
                                         cudaMemcpyDeviceToDevice, ctx->stream));
@@ -820,9 +938,13 @@ int tp_prove_inputs(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3],
 
 // ---- helpers -------------------------------------------------------------------------------------
 int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s) {
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_measure_imad_peak(c, imad_per_s, imad_wide_per_s); });
   return measure_imad_dev(ctx, imad_per_s, imad_wide_per_s);
 }
-int tp_selftest(tp_ctx* ctx, int* failures) { return selftest_dev(ctx, failures); }
+int tp_selftest(tp_ctx* ctx, int* failures) {
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_selftest(c, failures); });
+  return selftest_dev(ctx, failures);
+}
 #ifndef TP_BUILD_STAMP
 #define TP_BUILD_STAMP "unstamped"
 #endif

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@ struct DevBuf {
   size_t cap = 0;
 };
 
+struct LocalGroup;
 struct NttTables {
   Fr* tw = nullptr;  // omega_N^i, i in [0, N/2]
 };
@@ -40,12 +42,14 @@ struct tp_ctx {
   std::string err;
   int sm_count = 148;
   uint64_t launches = 0;
-  // sharding
+  // sharding (comm.cu): this context is rank `rank` of `world`; for world > 1 exactly one transport is set
   int rank = 0, world = 1;
-  tp_allgather_fn allgather = nullptr;
-  void* allgather_user = nullptr;
-  tp_bcast_dev_fn bcast = nullptr;   // device-buffer broadcast (quotient cosets); null = every rank computes all four
-  void* bcast_user = nullptr;
+  void* nccl = nullptr;                   // ncclComm_t owned by the library (tp_ctx_comm_init_rank / tp_ctx_create_multi)
+  tp::LocalGroup* local = nullptr;        // ranks of one process without NCCL (several ranks on one device: tests)
+  // device group (tp_ctx_create_multi): this context is only a front -- every entry point fans out to children[r]
+  // (rank r, own device / stream / worker thread) and returns one result
+  std::vector<tp_ctx*> children;
+  void* workers = nullptr;
   // tunables (tp_ctx_set_option)
   unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
@@ -68,7 +72,7 @@ struct tp_ctx {
   // scratch
   tp::DevBuf ntt_scratch;
   tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_sorted, msm_sorted_keys, msm_hist, msm_offsets, msm_blocksums,
-      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
+      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_gather, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
   tp::DevBuf scan_tmp[8];
   tp::DevBuf misc[16];
   tp::DevBuf flag;
@@ -90,6 +94,7 @@ struct tp_srs {
   unsigned c = 0;       // MSM window bits the tables were built for
   unsigned levels = 1;
   void* pairing = nullptr;  // verify.cu: (G2, tau G2) with their Miller-loop line tables, and srs[0]
+  std::vector<tp_srs*> parts;  // SRS of a device group: one full copy (with its table levels) per rank; nothing else is set
 };
 
 namespace tp {
@@ -178,6 +183,16 @@ struct ProfScope {
   }
 };
 
+// ---- comm.cu: the two exchange steps of the sharded prover and the device-group plumbing ---------------
+// every rank calls with the same sizes; ordered after the work already queued on ctx->stream
+int comm_allgather(tp_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
+int comm_bcast(tp_ctx* ctx, void* dev_ptr, size_t bytes, int root);
+inline bool comm_ready(const tp_ctx* ctx) { return ctx->world > 1 && (ctx->nccl || ctx->local); }
+void comm_release(tp_ctx* ctx);
+// fn(children[r], r) on every worker thread of a group front at once; first non-zero status, error text copied up
+int group_run(tp_ctx* group, const std::function<int(tp_ctx*, int)>& fn);
+void group_destroy(tp_ctx* group);
+
 // ---- device-level entry points (each implemented in its own .cu) -----------------------
 // verify.cu
 int srs_pairing_from_secret(tp_srs* srs, const tph::HFr& tau);
@@ -230,7 +245,7 @@ int sigma_tables_dev(tp_ctx* ctx, const uint64_t* perm_dev, size_t n, const Fr* 
                      Fr* sigma[3]);
 int pad_copy_dev(tp_ctx* ctx, const Fr* in, size_t len, Fr* out, size_t out_len);
 int rotate_copy_dev(tp_ctx* ctx, const Fr* in, size_t n, size_t shift, Fr* out);
-void msm_choose_tables(size_t len, size_t table_len, size_t budget_bytes, unsigned* c_out, unsigned* levels_out);
+void msm_choose_tables(size_t len, size_t table_len, size_t budget_bytes, unsigned world, unsigned* c_out, unsigned* levels_out);
 // api.cu: device allocation of an SRS with the fixed-base table levels the MSM plan wants
 int srs_alloc(tp_ctx* ctx, size_t len, tp_srs** out);
 // wire.cu: Montgomery SRS records <-> ark-serialize 0.3 uncompressed records, on the device

@@ -53,7 +53,8 @@ static unsigned msm_chunk() { static unsigned v = env_uint("TP_MSM_CHUNK", 64); 
 struct MsmPlan {
   unsigned c;        // window bits
   unsigned nwin;     // number of windows
-  unsigned nbuck;    // buckets per set = 2^(c-1)
+  unsigned nbuck;    // buckets per set THIS RANK owns: 2^(c-1) on one GPU; sharded, rank r of `world` owns the global
+                     // buckets b with b % world == r as local bucket b / world (count rounded up to a power of two)
   unsigned levels;   // fixed-base table levels held by the SRS
   unsigned nsets;    // bucket sets per MSM = ceil(nwin / levels)
 };
@@ -65,10 +66,10 @@ static unsigned windows_for(unsigned c) {
   return nwin;
 }
 
-// Window size and table depth for an SRS of `table_len` points of which one MSM call on this rank
-// touches `len` (the shard when the MSM is split over GPUs), when `budget` bytes may go to tables.
-// Cost in Fq multiplications: 10 per bucket addition (XYZZ mixed), ~30 per bucket in the reduction.
-void msm_choose_tables(size_t len, size_t table_len, size_t budget, unsigned* c_out, unsigned* levels_out) {
+// Window size and table depth for an SRS of `table_len` points of which one MSM call touches `len`, when `budget`
+// bytes may go to tables.  Cost in Fq multiplications: 10 per bucket addition (XYZZ mixed), ~30 per bucket in the
+// reduction; sharded over `world` ranks by bucket, both terms shrink 1/world, so the plan is that of one GPU.
+void msm_choose_tables(size_t len, size_t table_len, size_t budget, unsigned world, unsigned* c_out, unsigned* levels_out) {
   static unsigned force_c = env_uint("TP_MSM_C", 0);
   static unsigned max_levels = env_uint("TP_MSM_LEVELS", 1u << 30);
   double best_cost = 1e300;
@@ -88,7 +89,8 @@ void msm_choose_tables(size_t len, size_t table_len, size_t budget, unsigned* c_
     unsigned nsets = (nwin + levels - 1) / levels;
     levels = (nwin + nsets - 1) / nsets;  // no deeper than the set count needs
     double nb = (double)(1u << (c - 1));
-    double cost = (double)n * nwin * 10.0 + nsets * nb * 30.0 + nsets * 3000.0;
+    const double w = world ? (double)world : 1.0;
+    double cost = (double)n * nwin * 10.0 / w + nsets * nb * 30.0 / w + nsets * 3000.0;
     unsigned top_bits = 255 - (nwin - 1) * c;
     if (levels == 1 && top_bits + 6 < c && n > 4096) cost += 25e6;  // a lone top window funnels ~n points into few buckets
     if (cost < best_cost) {
@@ -101,11 +103,17 @@ void msm_choose_tables(size_t len, size_t table_len, size_t budget, unsigned* c_
   *levels_out = best_l;
 }
 
-static MsmPlan msm_plan(const tp_srs* srs) {
+static MsmPlan msm_plan(const tp_srs* srs, unsigned world) {
   MsmPlan pl;
   pl.c = srs->c;
   pl.nwin = windows_for(pl.c);
   pl.nbuck = 1u << (pl.c - 1);
+  if (world > 1) {
+    const unsigned need = (pl.nbuck + world - 1) / world;
+    unsigned p2 = 1;
+    while (p2 < need) p2 <<= 1;
+    pl.nbuck = p2;
+  }
   pl.levels = srs->levels;
   pl.nsets = (pl.nwin + pl.levels - 1) / pl.levels;
   return pl;
@@ -118,9 +126,11 @@ struct MsmScalarSets {
 };
 // blockIdx.y = batch element b.  Window w goes to bucket set b * nsets + w / levels; the entry
 // arrays stay window-major ((b * nwin + w) * n + i) so the scatter can recover (w, i).
+// Sharded (world > 1): every rank walks all scalars, but only the digits whose bucket it owns
+// (bucket % world == my_rank) take a histogram slot; the others leave MSM_NONE in the key array and cost one coalesced 4-byte store.
 __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck, unsigned levels,
-                             unsigned nsets, unsigned* __restrict__ hist, unsigned* __restrict__ keys,
-                             unsigned* __restrict__ ranks) {
+                             unsigned nsets, unsigned world, unsigned my_rank, unsigned* __restrict__ hist,
+                             unsigned* __restrict__ keys, unsigned* __restrict__ ranks) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const unsigned wbase = blockIdx.y * nwin;
@@ -137,7 +147,7 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
       raw = (unsigned)(two >> off) & ((1u << c) - 1);
     }
     raw += carry;
-    unsigned key = MSM_NONE, rank = 0;
+    unsigned key = MSM_NONE, rank = 0;   // rank = position of the entry inside its bucket
     carry = 0;
     if (raw != 0) {
       unsigned mag = raw, neg = 0;
@@ -147,9 +157,17 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
         carry = 1;
       }
       if (mag != 0) {
-        unsigned k = (sbase + w / levels) * nbuck + (mag - 1);
-        rank = atomicAdd(&hist[k], 1u);
-        key = k | (neg << 31);
+        unsigned b = mag - 1;
+        bool mine = true;
+        if (world > 1) {
+          mine = (b % world) == my_rank;
+          b /= world;
+        }
+        if (mine) {
+          unsigned k = (sbase + w / levels) * nbuck + b;
+          rank = atomicAdd(&hist[k], 1u);
+          key = k | (neg << 31);
+        }
       }
     }
     keys[(size_t)(wbase + w) * n + i] = key;
@@ -884,6 +902,38 @@ __global__ void __launch_bounds__(SUM_THREADS) k_msm_masked_sum(MsmSumTasks task
   if (threadIdx.x == 0) xyzz_store(dst, sh[0]);
 }
 
+// ---- 7. cross-rank combination (sharded MSM) --------------------------------------------------------
+// `gathered` holds every rank's reduction output, [world][sets][slots] (the all-gather of msm_winsums).  The tail the
+// host runs per bucket set is linear in the slots and, except for slot 0 (P = sum of the rank's buckets, which enters
+// with the rank-dependent factor rank + 1), the same on every rank: slots >= 1 are therefore summed over ranks here --
+// one warp per (set, slot), lane r holding rank r's point, a shared-memory tree -- and the `world` P points pass
+// through.  out: [sets][(slots - 1) sums | world P points].
+__global__ void __launch_bounds__(32) k_msm_combine(const G1Xyzz* __restrict__ gathered, unsigned world, unsigned sets,
+                                                    unsigned slots, G1Xyzz* __restrict__ out) {
+  __shared__ G1Xyzz sh[32];
+  const unsigned set = blockIdx.x / slots, slot = blockIdx.x % slots;
+  const unsigned width = slots - 1 + world;
+  const unsigned r = threadIdx.x;
+  G1Xyzz p = xyzz_identity();
+  if (r < world) p = xyzz_load(gathered + ((size_t)r * sets + set) * slots + slot);
+  if (slot == 0) {
+    if (r < world) xyzz_store(out + (size_t)set * width + (slots - 1) + r, p);
+    return;
+  }
+  sh[r] = p;
+  __syncwarp();
+  for (unsigned d = 16; d > 0; d >>= 1) {
+    if (r < d && r + d < world) {
+      G1Xyzz a = sh[r];
+      G1Xyzz b = sh[r + d];
+      xyzz_add(a, b);
+      sh[r] = a;
+    }
+    __syncwarp();
+  }
+  if (r == 0) xyzz_store(out + (size_t)set * width + (slot - 1), sh[0]);
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]) {
   tph::HFq x, y;
@@ -938,23 +988,25 @@ static int exclusive_scan(tp_ctx* ctx, const T* in, T* out, size_t n, unsigned* 
   return TP_OK;
 }
 
-// This rank's partial sums over the `len` bases starting at SRS index `first`, for `batch` scalar
-// vectors at once: all vectors share one sort / accumulate / merge / reduce pipeline (bucket set
-// index = b * nsets + q), which amortises the latency-bound reduction tail and the launch overhead.
-static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* const* scalars, int batch, size_t len,
+// `batch` MSMs over the first `len` bases at once: all scalar vectors share one sort / accumulate / merge / reduce
+// pipeline (bucket set index = b * nsets + q), which amortises the latency-bound reduction tail and the launch
+// overhead.  On a sharded context (world > 1) this rank handles the buckets it owns, the ranks' reduction outputs are
+// all-gathered and combined on the device (comm.cu, k_msm_combine) and every rank returns the complete sums.
+static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, int batch, size_t len,
                      tph::HG1* results) {
   for (int b = 0; b < batch; b++) results[b] = tph::HG1::identity();
   if (len == 0 || batch == 0) return TP_OK;
   if (batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: batch too large");
   if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
-  const MsmPlan pl = msm_plan(srs);
+  const unsigned world = ctx->world > 1 ? (unsigned)ctx->world : 1u;
+  const MsmPlan pl = msm_plan(srs, world);
   if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nsets * pl.nbuck * batch >= ((size_t)1 << 30)) {
     if (batch == 1) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
     int half = batch / 2;  // split the batch until the entry count fits 31 bits
-    TP_TRY(msm_local(ctx, srs, first, scalars, half, len, results));
-    return msm_local(ctx, srs, first, scalars + half, batch - half, len, results + half);
+    TP_TRY(msm_local(ctx, srs, scalars, half, len, results));
+    return msm_local(ctx, srs, scalars + half, batch - half, len, results + half);
   }
-  const G1Affine* bases = srs->g1 + first;      // level k of point i lives at bases[k * srs->len + i]
+  const G1Affine* bases = srs->g1;              // level k of point i lives at bases[k * srs->len + i]
   const unsigned nsets_total = pl.nsets * batch;
   size_t nkeys = (size_t)nsets_total * pl.nbuck;
   size_t total = (size_t)pl.nwin * batch * len;
@@ -977,8 +1029,8 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     MsmScalarSets sets;
     for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < batch ? b : 0];
     dim3 grid((unsigned)((len + 255) / 256), (unsigned)batch);
-    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, hist, keys,
-                                                ranks);
+    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, world,
+                                                (unsigned)ctx->rank, hist, keys, ranks);
     TP_LAUNCH(ctx, "k_msm_digits");
     TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
     {
@@ -996,8 +1048,15 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
         if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
         else if (per_msm > window) log_slices = 1;
       }
-      if (log_slices > pl.c - 1) log_slices = pl.c - 1;
-      const unsigned slice_shift = pl.c - 1 - log_slices;
+      unsigned log_nbuck = 0;
+      while ((1u << log_nbuck) < pl.nbuck) log_nbuck++;
+      if (world > 1) {   // a rank scatters 1 / world of the list: fewer slices bring it inside the L2
+        unsigned lw = 0;
+        while ((2u << lw) <= world) lw++;
+        log_slices = log_slices > lw ? log_slices - lw : 0;
+      }
+      if (log_slices > log_nbuck) log_slices = log_nbuck;
+      const unsigned slice_shift = log_nbuck - log_slices;
       const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
       for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
         k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
@@ -1013,7 +1072,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     m_total = ((unsigned*)ctx->pinned)[0];
     max_bucket = ((unsigned*)ctx->pinned)[1];
   }
-  if (m_total == 0) return TP_OK;  // all scalars zero
+  if (m_total == 0 && world == 1) return TP_OK;  // all scalars zero (a sharded rank still takes part in the exchange)
   // ---- batch-affine rounds (4a): plan on the host from upper bounds, sizes stay on the device ----
   // bound[r] >= entries before round r + 1: every round leaves ceil(cnt / 2) per bucket.
   // Off by default: on sm_100a the rounds do not beat the XYZZ accumulation they replace (profiles/r1_summary.md K);
@@ -1024,7 +1083,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
   bound[0] = m_total;
   int rounds = 0;
   unsigned max_b = max_bucket;
-  const size_t split = (size_t)pl.levels * srs->len - first;  // table indices are < split (relative to `bases`)
+  const size_t split = (size_t)pl.levels * srs->len;  // table indices are < split
   if (!aff_disable) {
     const int want = (int)(aff_rounds_env < AFF_MAX_ROUNDS ? aff_rounds_env : AFF_MAX_ROUNDS);
     while (rounds < want) {
@@ -1147,7 +1206,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
   ctx->stat_msm_nwin = pl.nwin;
   ctx->stat_msm_levels = pl.levels;
   ctx->stat_msm_chunk = chunk;
-  {
+  if (m_total > 0) {
     ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
     if (chains) {
       TP_TRY(ensure(ctx, ctx->msm_aff_pts, (size_t)nchunks * sizeof(G1Affine)));
@@ -1200,7 +1259,9 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
   {
     ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
-    if (pair_path) {
+    if (m_total == 0) {
+      // a sharded rank that owns none of the digits: its buckets are all empty (the histogram says so)
+    } else if (pair_path) {
       k_msm_pair_fixup<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>((const unsigned*)ctx->msm_part_keys.p,
                                                                        (const G1Xyzz*)ctx->msm_part_pts.p, nchunks, buckets);
       TP_LAUNCH(ctx, "k_msm_pair_fixup");
@@ -1269,13 +1330,29 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
       TP_LAUNCH(ctx, "k_msm_masked_sum");
     }
   }
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, ctx->msm_winsums.p, (size_t)nsets_total * total_masks * sizeof(G1Xyzz),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+  // Sharded: the ranks' reduction outputs meet on the device -- all-gather on the stream, one combine kernel -- and the
+  // host reads back one buffer, as on a single GPU.  Row of a set: [slots 1.. summed over ranks | P of every rank].
+  const unsigned width = world > 1 ? total_masks - 1 + world : total_masks;
+  const G1Xyzz* final_dev = (const G1Xyzz*)ctx->msm_winsums.p;
+  if (world > 1) {
+    ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
+    const size_t per_rank = (size_t)nsets_total * total_masks * sizeof(G1Xyzz);
+    TP_TRY(ensure(ctx, ctx->msm_gather, per_rank * world + (size_t)nsets_total * width * sizeof(G1Xyzz)));
+    G1Xyzz* gathered = (G1Xyzz*)ctx->msm_gather.p;
+    G1Xyzz* combined = gathered + (size_t)world * nsets_total * total_masks;
+    TP_TRY(comm_allgather(ctx, ctx->msm_winsums.p, gathered, per_rank));
+    k_msm_combine<<<nsets_total * total_masks, 32, 0, ctx->stream>>>(gathered, world, nsets_total, total_masks, combined);
+    TP_LAUNCH(ctx, "k_msm_combine");
+    final_dev = combined;
+  }
+  if ((size_t)nsets_total * width * sizeof(G1Xyzz) > ctx->pinned_cap) return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, final_dev, (size_t)nsets_total * width * sizeof(G1Xyzz), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   // serial tail on the host
   const uint8_t* ws = (const uint8_t*)ctx->pinned;
-  auto point = [&](unsigned set, unsigned slot) {
-    const uint8_t* q = ws + ((size_t)set * total_masks + slot) * 192;
+  auto raw_point = [&](size_t index) {
+    const uint8_t* q = ws + index * 192;
     tph::HFq x, y, zz, zzz;
     memcpy(x.v, q, 48);
     memcpy(y.v, q + 48, 48);
@@ -1283,6 +1360,8 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
     memcpy(zzz.v, q + 144, 48);
     return tph::g1_from_xyzz(x, y, zz, zzz);
   };
+  // slot >= 1 of a set (summed over ranks when sharded)
+  auto point = [&](unsigned set, unsigned slot) { return raw_point((size_t)set * width + (world > 1 ? slot - 1 : slot)); };
   // one bucket set's tail is ~40 dependent group operations of single-thread host arithmetic (~0.1 ms); the sets of a
   // batch are independent, so every batch element beyond the first gets its own thread
   auto tail = [&](int b) {
@@ -1300,7 +1379,23 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, size_t first, const Fr* con
         for (unsigned d = 1; d < seg_level[l]; d <<= 1) f = tph::g1_dbl(f);
         f = tph::g1_add(f, point(set, 1 + nbits + (unsigned)(l - 1)));
       }
-      f = tph::g1_add(f, point(set, 0));
+      if (world == 1) {
+        f = tph::g1_add(f, raw_point((size_t)set * width));   // V = F + P
+      } else {
+        // local bucket j of rank r is global bucket world * j + r, which counts (world * j + r + 1) times:
+        // V = world * F(summed over ranks) + sum_r (r + 1) P_r, the latter by running sums
+        tph::HG1 wf = tph::HG1::identity();
+        for (int bit = 31 - __builtin_clz(world); bit >= 0; bit--) {
+          wf = tph::g1_dbl(wf);
+          if ((world >> bit) & 1) wf = tph::g1_add(wf, f);
+        }
+        tph::HG1 run = tph::HG1::identity(), pw = tph::HG1::identity();
+        for (int r = (int)world - 1; r >= 0; r--) {
+          run = tph::g1_add(run, raw_point((size_t)set * width + (total_masks - 1) + (unsigned)r));
+          pw = tph::g1_add(pw, run);
+        }
+        f = tph::g1_add(wf, pw);
+      }
       acc = tph::g1_add(acc, f);
     }
     results[b] = acc;
@@ -1322,39 +1417,9 @@ int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, 
   if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
   if (batch <= 0 || batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: bad batch size");
   ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
+  if (ctx->world > 1 && !comm_ready(ctx)) return fail(ctx, TP_ERR_COLLECTIVE, "msm: sharded context without a communicator");
   tph::HG1 res[MSM_MAX_BATCH];
-  if (ctx->world <= 1) {
-    TP_TRY(msm_local(ctx, srs, 0, scalars_dev, batch, len, res));
-  } else {
-    // contiguous point-range shard; every rank holds the full SRS and scalar vectors
-    size_t per = (len + ctx->world - 1) / ctx->world;
-    size_t first = per * ctx->rank;
-    size_t cnt = first >= len ? 0 : (len - first < per ? len - first : per);
-    const Fr* shifted[MSM_MAX_BATCH];
-    for (int b = 0; b < batch; b++) shifted[b] = scalars_dev[b] + first;
-    tph::HG1 part[MSM_MAX_BATCH];
-    TP_TRY(msm_local(ctx, srs, first, shifted, batch, cnt, part));
-    const size_t per_rank = (size_t)144 * batch;
-    std::vector<uint8_t> send(per_rank), recv(per_rank * ctx->world);
-    for (int b = 0; b < batch; b++) {
-      memcpy(&send[(size_t)b * 144], part[b].x.v, 48);
-      memcpy(&send[(size_t)b * 144 + 48], part[b].y.v, 48);
-      memcpy(&send[(size_t)b * 144 + 96], part[b].z.v, 48);
-    }
-    if (!ctx->allgather || ctx->allgather(ctx->allgather_user, send.data(), recv.data(), per_rank) != 0)
-      return fail(ctx, TP_ERR_COLLECTIVE, "msm: all-gather of partial points failed");
-    for (int b = 0; b < batch; b++) {
-      res[b] = tph::HG1::identity();
-      for (int r = 0; r < ctx->world; r++) {
-        const uint8_t* q = recv.data() + (size_t)r * per_rank + (size_t)b * 144;
-        tph::HG1 p;
-        memcpy(p.x.v, q, 48);
-        memcpy(p.y.v, q + 48, 48);
-        memcpy(p.z.v, q + 96, 48);
-        res[b] = tph::g1_add(res[b], p);
-      }
-    }
-  }
+  TP_TRY(msm_local(ctx, srs, scalars_dev, batch, len, res));
   encode_g1_batch(res, out, batch);
   return TP_OK;
 }

@@ -199,6 +199,7 @@ void srs_pairing_free(tp_srs* srs) {
 extern "C" {
 
 int tp_srs_g2(const tp_srs* srs, uint8_t g2[TP_G2_BYTES], uint8_t g2s[TP_G2_BYTES]) {
+  if (srs && !srs->parts.empty()) return tp_srs_g2(srs->parts[0], g2, g2s);   // SRS of a device group: every rank holds the same
   if (!srs || !srs->pairing || !g2 || !g2s) return TP_ERR_INVALID_ARG;
   const SrsPairing* sp = (const SrsPairing*)srs->pairing;
   g2_encode(sp->g2, g2);
@@ -207,6 +208,10 @@ int tp_srs_g2(const tp_srs* srs, uint8_t g2[TP_G2_BYTES], uint8_t g2s[TP_G2_BYTE
 }
 int tp_srs_set_g2(tp_srs* srs, const uint8_t g2[TP_G2_BYTES], const uint8_t g2s[TP_G2_BYTES]) {
   if (!srs || !g2 || !g2s) return TP_ERR_INVALID_ARG;
+  if (!srs->parts.empty()) {
+    for (tp_srs* part : srs->parts) TP_TRY(tp_srs_set_g2(part, g2, g2s));
+    return TP_OK;
+  }
   SrsPairing* sp = new SrsPairing();
   int rc = prepare_pairing(g2, g2s, sp);
   if (rc != TP_OK) {
@@ -296,6 +301,12 @@ int tp_verify(tp_ctx* ctx, tp_circuit* c, const uint8_t* proof, size_t proof_len
               size_t n_public, int* ok) {
   if (!ctx) return TP_ERR_INVALID_ARG;
   if (!c || !proof || !ok || (n_public && !public_inputs)) return fail(ctx, TP_ERR_INVALID_ARG, "verify: null argument");
+  if (!ctx->children.empty()) {   // device group: the first call's commitment MSMs are sharded, so every rank takes part
+    std::vector<int> oks(ctx->children.size(), 0);
+    TP_TRY(group_run(ctx, [&](tp_ctx* cc, int r) { return tp_verify(cc, c->parts[r], proof, proof_len, public_inputs, n_public, &oks[r]); }));
+    *ok = oks[0];
+    return TP_OK;
+  }
   if (proof_len < TP_PROOF_FIXED_BYTES) return fail(ctx, TP_ERR_INVALID_ARG, "verify: proof shorter than the fixed block");
   if (!c->srs->pairing) return fail(ctx, TP_ERR_INVALID_ARG, "verify: the SRS has no G2 points (tp_srs_set_g2)");
   *ok = 0;

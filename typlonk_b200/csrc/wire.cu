@@ -297,6 +297,8 @@ int tp_srs_serialized_size(const tp_srs* srs, size_t* bytes) {
 
 int tp_srs_serialize(tp_ctx* ctx, const tp_srs* srs, uint8_t* out, size_t cap, size_t* written) {
   if (!ctx || !srs || !out) return TP_ERR_INVALID_ARG;
+  if (!ctx->children.empty())   // device group: rank 0's copy
+    return group_run(ctx, [&](tp_ctx* c, int r) { return r == 0 ? tp_srs_serialize(c, srs->parts[0], out, cap, written) : TP_OK; });
   if (!srs->pairing) return fail(ctx, TP_ERR_INVALID_ARG, "srs_serialize: the SRS has no G2 points (tp_srs_set_g2)");
   const size_t need = 8 + srs->len * TP_WIRE_G1_BYTES + 2 * TP_WIRE_G2_BYTES;
   if (written) *written = need;
@@ -323,6 +325,19 @@ int tp_srs_serialize(tp_ctx* ctx, const tp_srs* srs, uint8_t* out, size_t cap, s
 
 int tp_srs_deserialize(tp_ctx* ctx, const uint8_t* bytes, size_t len, int check, tp_srs** out) {
   if (!ctx || !bytes || !out || check < 0 || check > 2) return TP_ERR_INVALID_ARG;
+  if (!ctx->children.empty()) {   // device group: every rank decodes (and validates) its own copy
+    tp_srs* front = new tp_srs();
+    front->parts.assign(ctx->children.size(), nullptr);
+    int rc = group_run(ctx, [&](tp_ctx* c, int r) { return tp_srs_deserialize(c, bytes, len, check, &front->parts[r]); });
+    if (rc != TP_OK) {
+      group_run(ctx, [&](tp_ctx* c, int r) { return tp_srs_destroy(c, front->parts[r]); });
+      delete front;
+      return rc;
+    }
+    front->len = front->parts[0]->len;
+    *out = front;
+    return TP_OK;
+  }
   if (len < 8 + 2 * TP_WIRE_G2_BYTES) return fail(ctx, TP_ERR_MALFORMED, "srs_deserialize: truncated");
   uint64_t n64;
   memcpy(&n64, bytes, 8);

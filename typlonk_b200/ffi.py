@@ -24,7 +24,8 @@ ERRORS = {
 
 # every symbol include/typlonk_b200.h declares
 SYMBOLS = [
-    "tp_ctx_create", "tp_ctx_destroy", "tp_last_error", "tp_sync", "tp_ctx_set_shard", "tp_ctx_set_broadcast",
+    "tp_ctx_create", "tp_ctx_destroy", "tp_last_error", "tp_sync", "tp_comm_unique_id", "tp_ctx_comm_init_rank",
+    "tp_ctx_create_multi", "tp_ctx_group_size",
     "tp_prof_enable", "tp_prof_reset", "tp_prof_get", "tp_launch_count",
     "tp_srs_from_secret", "tp_srs_upload", "tp_srs_len", "tp_srs_g1_download", "tp_srs_destroy",
     "tp_commit", "tp_commit_dev", "tp_open", "tp_ntt", "tp_ntt_dev", "tp_perm_prove",
@@ -40,8 +41,17 @@ SYMBOLS = [
     "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp",
 ]
 
-ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
-BCAST_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """tp_comm_unique_id: rank 0 makes it, the host language hands it to every rank once (e.g. one
+    torch.distributed.broadcast at start-up), every rank passes it to Context.comm_init_rank."""
+    out = (C.c_char * COMM_ID_BYTES)()
+    rc = lib().tp_comm_unique_id(out)
+    if rc != 0:
+        raise TyplonkError(rc, "tp_comm_unique_id: libnccl.so.2 could not be loaded")
+    return bytes(out)
 
 
 class DeviceView:
@@ -377,45 +387,32 @@ class Context:
         self._check(lib().tp_ctx_get_stat(self._h, name.encode(), C.byref(v)))
         return v.value
 
-    def set_shard(self, rank, world, allgather=None):
-        """allgather(send: bytes) -> bytes of world * len(send) (e.g. via torch.distributed)."""
-        if world > 1:
-            def cb(_user, send, recv, nbytes):
-                try:
-                    data = C.string_at(send, nbytes)
-                    out = allgather(data)
-                    assert len(out) == nbytes * world
-                    C.memmove(recv, out, len(out))
-                    return 0
-                except Exception:  # noqa: BLE001 -- must not unwind through C
-                    import traceback
-                    traceback.print_exc()
-                    return 1
-            self._cb = ALLGATHER_FN(cb)
-            self._check(lib().tp_ctx_set_shard(self._h, rank, world, self._cb, None))
-        else:
-            self._cb = None
-            self._check(lib().tp_ctx_set_shard(self._h, 0, 1, C.cast(None, ALLGATHER_FN), None))
+    def comm_init_rank(self, rank: int, world: int, unique_id: bytes = None):
+        """One process per GPU: join the library-owned NCCL communicator as rank `rank` of `world` (before the SRS is
+        created).  From here on every MSM is sharded by bucket, the quotient by coset, the witness upload by rows;
+        no host-language code runs during a proof."""
+        self._check(lib().tp_ctx_comm_init_rank(self._h, C.c_int(rank), C.c_int(world),
+                                                _buf(unique_id) if unique_id is not None else None))
 
-    def set_broadcast(self, bcast=None):
-        """bcast(dev_ptr: int, nbytes: int, root: int): in-place broadcast of device memory from rank
-        `root`, ordered after the work already queued on the ctx stream (e.g. torch.distributed.broadcast
-        on torch.as_tensor(DeviceView(dev_ptr, nbytes), device=...)).  Enables coset sharding of the quotient."""
-        if bcast is None:
-            self._bcb = None
-            self._check(lib().tp_ctx_set_broadcast(self._h, C.cast(None, BCAST_DEV_FN), None))
-            return
+    @classmethod
+    def multi(cls, devices):
+        """tp_ctx_create_multi: ONE context over several GPUs of this process (a device listed twice = two ranks on
+        it, exchanging through peer copies instead of NCCL -- how the single-GPU tests run the sharded path)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._cb = None
+        self.device = devices[0]
+        arr = (C.c_int * len(devices))(*devices)
+        rc = lib().tp_ctx_create_multi(arr, C.c_int(len(devices)), C.byref(self._h))
+        if rc != 0:
+            raise TyplonkError(rc, "tp_ctx_create_multi failed (no CUDA device? there is no CPU fallback)")
+        return self
 
-        def cb(_user, ptr, nbytes, root):
-            try:
-                bcast(int(ptr), int(nbytes), int(root))
-                return 0
-            except Exception:  # noqa: BLE001 -- must not unwind through C
-                import traceback
-                traceback.print_exc()
-                return 1
-        self._bcb = BCAST_DEV_FN(cb)
-        self._check(lib().tp_ctx_set_broadcast(self._h, self._bcb, None))
+    def group_size(self):
+        """(ranks behind this context, whether they exchange through NCCL)."""
+        n, nc = C.c_int(0), C.c_int(0)
+        self._check(lib().tp_ctx_group_size(self._h, C.byref(n), C.byref(nc)))
+        return n.value, bool(nc.value)
 
     # ---- SRS ---------------------------------------------------------------------------
     def srs_from_secret(self, tau_mont: bytes, gates: int):
