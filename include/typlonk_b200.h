@@ -101,7 +101,9 @@ int tp_ctx_group_size(const tp_ctx* ctx, int* ndev, int* uses_nccl);
  *   "msm_affine_chains" (0/1, $TP_MSM_AFFINE): accumulate buckets in affine coordinates, 16 chunks of the
  *       bucket-sorted list per thread in lockstep with one shared inversion per step (5M + 1S per addition);
  *   "msm_affine_rounds" (0..8, $TP_MSM_AFF_ROUNDS): batch-affine pair-addition rounds run on the bucket-sorted
- *       points before the XYZZ accumulation (kept for comparison; see profiles/). */
+ *       points before the XYZZ accumulation (kept for comparison; see profiles/);
+ *   "quotient_all_cosets" (0/1): evaluate the quotient numerator on all four cosets of the 4n domain even when it is
+ *       known to vanish on H (gates and copy constraints hold); by default that coset is skipped. */
 int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value);
 /* Work counters since the last tp_prof_reset: "msm_entries" (bucket additions issued by the accumulation
  * kernels), "msm_calls"; and the plan of the last MSM: "msm_window_bits", "msm_windows", "msm_table_levels",

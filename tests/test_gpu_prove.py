@@ -154,6 +154,24 @@ def test_mul_chain_2_20_bytes_vs_c_oracle_live_and_golden(ctx):
     group.close()
 
 
+def test_quotient_coset_skip_equals_all_four_cosets(ctx):
+    """An honest witness lets the prover skip coset 0 of the 4n domain (the numerator vanishes on H); forcing all four
+    cosets must give the same bytes.  The broken-copy witness [3, 4, 6] always takes four (floor quotient)."""
+    from typlonk_b200 import field as F, synthetic
+    for log_n in (3, 9, 12):
+        n = 1 << log_n
+        circuit = synthetic.mul_chain_direct(ctx, log_n)
+        cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
+        fast = circuit.handle.prove_inputs(cols, bytes(32))
+        ctx.set_option("quotient_all_cosets", 1)
+        try:
+            assert circuit.handle.prove_inputs(cols, bytes(32)) == fast
+        finally:
+            ctx.set_option("quotient_all_cosets", 0)
+        circuit.handle.destroy()
+        circuit.srs.handle.destroy()
+
+
 def test_golden_big_proofs_2_16_and_2_18(ctx):
     import json
     from typlonk_b200 import field as F, synthetic

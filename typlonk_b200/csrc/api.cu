@@ -92,6 +92,12 @@ int tp_ctx_destroy(tp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   comm_release(ctx);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->side_stream) {
+    cudaStreamSynchronize(ctx->side_stream);
+    cudaStreamDestroy(ctx->side_stream);
+    for (auto& e : ctx->side_ev)
+      if (e) cudaEventDestroy(e);
+  }
   if (ctx->copy_stream) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamDestroy(ctx->copy_stream);
@@ -142,6 +148,11 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
   if (strcmp(name, "msm_affine_chains") == 0) {
     if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_affine_chains must be 0 or 1");
     ctx->msm_affine_chains = (unsigned)value;
+    return TP_OK;
+  }
+  if (strcmp(name, "quotient_all_cosets") == 0) {
+    if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: quotient_all_cosets must be 0 or 1");
+    ctx->quotient_all_cosets = (unsigned)value;
     return TP_OK;
   }
   return fail(ctx, TP_ERR_INVALID_ARG, "set_option: unknown option");
@@ -655,6 +666,28 @@ static void put_fr(uint8_t*& w, const HFr& x) {
   w += 32;
 }
 
+// The prover's second stream: the forward coset NTTs of the quotient do not depend on any Fiat-Shamir challenge, so they
+// are queued here as soon as their polynomial exists and run underneath the commitment MSMs of the main stream -- above
+// all during the latency-bound tail of each MSM (bucket reduction, host round trip), when most SMs are idle.
+struct StreamSwap {
+  tp_ctx* c;
+  cudaStream_t saved;
+  StreamSwap(tp_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
+  ~StreamSwap() { c->stream = saved; }
+};
+static int side_stream_init(tp_ctx* ctx) {
+  if (ctx->side_stream) return TP_OK;
+  TP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  for (auto& e : ctx->side_ev) TP_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  return TP_OK;
+}
+// rank that evaluates coset k of the 4n domain when cosets first..3 are to be done (first = 1: coset 0 skipped)
+static int coset_owner(const tp_ctx* ctx, bool shard, unsigned first, unsigned k) {
+  if (!shard) return ctx->rank;
+  const unsigned ncos = 4u - first, j = k - first, world = (unsigned)ctx->world;
+  return world < ncos ? (int)(j % world) : (int)(j * world / ncos);
+}
+
 // `col_ready` (may be null): three events on another stream, one per witness column, recorded when that column's
 // upload has landed.  The prover then interpolates column k as soon as it is there -- while the next one is still
 // crossing PCIe -- instead of waiting for all three and running the batched transform.
@@ -694,6 +727,45 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
     TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, pi_zero ? 3 : 4, c->log_n, true));
   }
+  // Quotient cosets of a, b, c on the side stream, under the round-1 MSMs.  Which cosets this rank owns depends on
+  // whether coset 0 will be skipped (known only after the grand product): the honest case is assumed here and the
+  // rest, if any, is done later.
+  static const bool no_coset_shard = getenv("TP_NO_COSET_SHARD") && *getenv("TP_NO_COSET_SHARD") == '1';
+  static const bool no_side_stream = getenv("TP_NO_SIDE_STREAM") && *getenv("TP_NO_SIDE_STREAM") == '1';
+  const bool shard = comm_ready(ctx) && !no_coset_shard;
+  HFr gens[4];
+  for (unsigned k = 0; k < 4; k++) gens[k] = omega_for_log(c->log_n + 2).pow_u64(k);
+  bool have[4][4] = {{false}};   // have[poly][coset]: evaluations of poly (a, b, c, z) on coset k are in buf4[poly]
+  auto queue_cosets = [&](int poly_lo, int poly_hi, unsigned first) -> int {
+    const Fr* src[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef};
+    const Fr* ins[16];
+    Fr* outs[16];
+    const uint64_t* cos[16];
+    int cnt = 0;
+    for (unsigned k = first; k < 4; k++) {
+      if (coset_owner(ctx, shard, first, k) != ctx->rank) continue;
+      for (int i = poly_lo; i < poly_hi; i++) {
+        if (have[i][k]) continue;
+        have[i][k] = true;
+        ins[cnt] = src[i];
+        outs[cnt] = c->buf4[i] + (size_t)k * n;
+        cos[cnt] = k == 0 ? nullptr : gens[k].v;
+        cnt++;
+      }
+    }
+    return ntt_batch_dev(ctx, ins, outs, cos, cnt, c->log_n, false);
+  };
+  const bool side = !no_side_stream;
+  if (side) {
+    TP_TRY(side_stream_init(ctx));
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[0], ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
+    {
+      StreamSwap sw(ctx, ctx->side_stream);
+      TP_TRY(queue_cosets(0, 3, ctx->quotient_all_cosets ? 0u : 1u));
+    }
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
+  }
   // round 1 commitments (proof.rs:107-110)
   uint8_t com[4][TP_G1_BYTES];
   {
@@ -702,45 +774,54 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
   }
   HFr beta, gamma;
   tph::challenges2({com[0], com[1], com[2]}, &beta, &gamma);
-  // grand product z (proof.rs:117-131)
+  // grand product z (proof.rs:117-131); z_closes: the last value, which the reference pops (proof.rs:120), is 1
+  bool z_closes = false;
   {
     const Fr* v[3] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2]};
     const Fr* idp[3] = {c->id[0], c->id[1], c->id[2]};
     const Fr* sg[3] = {c->sig_eval[0], c->sig_eval[1], c->sig_eval[2]};
-    TP_TRY(perm_grand_product_dev(ctx, v, idp, sg, n, to_dev(beta), to_dev(gamma), c->z_eval));
+    TP_TRY(perm_grand_product_dev(ctx, v, idp, sg, n, to_dev(beta), to_dev(gamma), c->z_eval, &z_closes));
   }
   TP_TRY(ntt_dev(ctx, c->z_eval, c->z_coef, c->log_n, true, nullptr));
+  const bool skip0 = z_closes && !ctx->quotient_all_cosets;
+  const unsigned first = skip0 ? 1u : 0u;
+  if (side) {
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[2], ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[2], 0));
+    {
+      StreamSwap sw(ctx, ctx->side_stream);
+      TP_TRY(queue_cosets(0, 4, first));   // z on this rank's cosets; a, b, c only where the guess above missed
+    }
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[3], ctx->side_stream));
+  }
   TP_TRY(msm_dev(ctx, srs, c->z_coef, n, com[3]));
   HFr alpha, zeta;
   tph::challenges2({com[0], com[1], com[2], com[3]}, &alpha, &zeta);
 
-  // quotient (proof.rs:292-375) on the 4n domain, coset by coset: five coset NTTs, the pointwise
-  // numerator, one inverse coset NTT each.  Sharded over ranks by coset when the caller wired a
-  // context is sharded (comm.cu); every rank then rebuilds t from the four interpolants.
+  // quotient (proof.rs:292-375) on the 4n domain, coset by coset: four coset NTTs, the pointwise numerator, one
+  // inverse coset NTT each.  Coset 0 is H itself, where the numerator is zero whenever the witness satisfies the gates
+  // (checked above) and the copy constraints (z closes: the permutation line holds at the last row too) -- its
+  // interpolant is then known to be zero and the coset is skipped: 15 transforms instead of 20.  A witness that breaks
+  // a copy constraint takes all four cosets and gets the reference's floor quotient (proof.rs:373).
+  // Sharded over ranks by coset when the context is sharded (comm.cu); every rank then rebuilds t from the interpolants.
   {
-    const Fr* src[5] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef, c->pi_coef};
-    static const bool no_coset_shard = getenv("TP_NO_COSET_SHARD") && *getenv("TP_NO_COSET_SHARD") == '1';
-    const bool shard = comm_ready(ctx) && !no_coset_shard;
-    auto owner = [&](unsigned k) { return !shard ? ctx->rank : (ctx->world < 4 ? (int)(k % ctx->world) : (int)(k * (ctx->world / 4))); };
     unsigned mine[4];
     int nmine = 0;
-    for (unsigned k = 0; k < 4; k++)
-      if (owner(k) == ctx->rank) mine[nmine++] = k;
-    HFr gens[4];
-    for (unsigned k = 0; k < 4; k++) gens[k] = omega_for_log(c->log_n + 2).pow_u64(k);
-    {
-      const Fr* ins[20];
-      Fr* outs[20];
-      const uint64_t* cos[20];
-      int cnt = 0;
-      for (int m = 0; m < nmine; m++)
-        for (int i = 0; i < (pi_zero ? 4 : 5); i++) {
-          ins[cnt] = src[i];
-          outs[cnt] = c->buf4[i] + (size_t)mine[m] * n;
-          cos[cnt] = mine[m] == 0 ? nullptr : gens[mine[m]].v;
-          cnt++;
-        }
-      TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, cnt, c->log_n, false));
+    for (unsigned k = first; k < 4; k++)
+      if (coset_owner(ctx, shard, first, k) == ctx->rank) mine[nmine++] = k;
+    auto owner = [&](unsigned k) { return coset_owner(ctx, shard, first, k); };
+    if (side) TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[3], 0));   // everything queued on the side stream
+    TP_TRY(queue_cosets(0, 4, first));   // without the side stream: all of them here
+    if (!pi_zero) {
+      const Fr* ins[4];
+      Fr* outs[4];
+      const uint64_t* cos[4];
+      for (int m = 0; m < nmine; m++) {
+        ins[m] = c->pi_coef;
+        outs[m] = c->buf4[4] + (size_t)mine[m] * n;
+        cos[m] = mine[m] == 0 ? nullptr : gens[mine[m]].v;
+      }
+      TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, nmine, c->log_n, false));
     }
     QuotientArgs qa;
     for (int i = 0; i < 5; i++) qa.sel4[i] = c->sel4[i];
@@ -772,10 +853,9 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
       TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, nmine, c->log_n, true));
     }
     if (shard) {
-      for (unsigned k = 0; k < 4; k++)
-        TP_TRY(comm_bcast(ctx, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)));
+      for (unsigned k = first; k < 4; k++) TP_TRY(comm_bcast(ctx, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)));
     }
-    TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, qa.tw4, c->t));
+    TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, skip0, c->t));
   }
 
   // openings (proof.rs:147-163)

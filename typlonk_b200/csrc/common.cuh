@@ -53,6 +53,7 @@ struct tp_ctx {
   // tunables (tp_ctx_set_option)
   unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
+  unsigned quotient_all_cosets = 0;  // 1: evaluate the quotient numerator on all four cosets even when it is known to vanish on H
   // work counters (tp_ctx_get_stat)
   double stat_msm_entries = 0, stat_msm_calls = 0, stat_msm_c = 0, stat_msm_nwin = 0, stat_msm_levels = 0, stat_msm_chunk = 0;
   // profiling
@@ -81,6 +82,9 @@ struct tp_ctx {
   void* fixed_base = nullptr;  // 32 x 255 affine multiples of G for SRS generation
   // tp_prove / tp_prove_inputs: the witness columns cross PCIe on their own stream, one event per column, so that
   // column k is interpolated while column k + 1 is still in flight (created on first use)
+  // the prover's second compute stream (api.cu): challenge-independent coset NTTs run under the commitment MSMs
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // [0..2] column landed, [3] compute stream reached the upload
 };
@@ -211,7 +215,8 @@ int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, 
 void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]);
 // poly.cu
 int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],
-                           size_t n, const Fr& beta, const Fr& gamma, Fr* out /* n+1 */);
+                           size_t n, const Fr& beta, const Fr& gamma, Fr* out /* n+1 */, bool* closes = nullptr);
+// *closes (may be null): out[n] == 1, i.e. the copy constraints hold on the witness
 // q[k-1] = p[k] + z q[k]; writes q (len-1 coeffs, then a zero at [len-1]) and returns y = p(z)
 int poly_open_dev(tp_ctx* ctx, const Fr* p, size_t len, const Fr& z, Fr* q_out /* len, may be null */, tph::HFr* y);
 // up to 8 polynomials of the same length at once (own point each; q_out[b] may be null = evaluation only)
@@ -234,7 +239,8 @@ struct QuotientArgs {   // every 4n-sized array is coset-major: slot k * n + i <
 };
 int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a, const unsigned* cosets, int ncosets);
 // t = floor(N / (X^n - 1)) (3n coefficients) from the four per-coset interpolants of N (coset-major, 4n)
-int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, const Fr* tw4, Fr* t /* 3n */);
+// c0_is_zero: coset 0 (H itself) was skipped because the numerator is known to vanish there
+int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, bool c0_is_zero, Fr* t /* 3n */);
 int l0_evals_4n_dev(tp_ctx* ctx, const Fr* tw4, size_t n, Fr* out /* 4n */);
 struct LinTerm {
   const Fr* p;

@@ -1,7 +1,7 @@
 // Elementwise and scan kernels of the prover (all HBM-streaming integer work over Fr):
 //   * permutation grand product   -- permutation/src/proving.rs:7-31 (one inversion per cell in
-//     the reference) as elementwise num/den, chunked Montgomery batch inversion, and a
-//     hierarchical prefix-product scan
+//     the reference) as a prefix-product scan of the numerators and a suffix-product scan of the
+//     denominators sharing their launches, with ONE inversion per proof
 //   * opening polynomial          -- kzg/src/lib.rs:55-64: Horner evaluation and the division
 //     by (X - z) are one linear recurrence q[k-1] = p[k] + z q[k], solved as a hierarchical scan
 //   * gate check                  -- the `vanishes(line1)` assert, plonk/src/proof.rs:317-321
@@ -26,130 +26,145 @@ __device__ __forceinline__ Fr pmul(const Fr& a, const Fr& b) { return fr_mul(a, 
 static inline unsigned ew_grid(size_t n) { return (unsigned)((n + EW_THREADS - 1) / EW_THREADS); }
 
 // =====================================================================================
-// prefix-product scan (in place).  chunk per thread, recursive on chunk totals.
+// exclusive prefix-product scan (in place).  chunk per thread, recursive on chunk totals.
 // =====================================================================================
 #define SCAN_CH 32
 #define SCAN_BASE 64
 
-__global__ void k_mulscan_serial(Fr* a, size_t n, int exclusive) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// two independent scans of the same length side by side (blockIdx.y picks the array): the upper levels of a scan are
+// chains of small launches, so two cost what one costs
+struct ScanPair {
+  Fr* a[2];
+  Fr* tot[2];
+};
+__global__ void k_mulscan2_serial(ScanPair p, size_t n) {   // exclusive
+  if (threadIdx.x != 0) return;
+  Fr* a = p.a[blockIdx.x];
   Fr acc = fr_one();
   for (size_t i = 0; i < n; i++) {
     Fr x = fr_load(a + i);
-    if (exclusive) {
-      fr_store(a + i, acc);
-      acc = fr_mul(acc, x);
-    } else {
-      acc = fr_mul(acc, x);
-      fr_store(a + i, acc);
-    }
+    fr_store(a + i, acc);
+    acc = fr_mul(acc, x);
   }
 }
-__global__ void k_mulscan_chunk(Fr* a, size_t n, Fr* tot, int exclusive) {
+__global__ void k_mulscan2_chunk(ScanPair p, size_t n) {    // exclusive
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t lo = t * SCAN_CH;
   if (lo >= n) return;
+  Fr* a = p.a[blockIdx.y];
   size_t hi = lo + SCAN_CH < n ? lo + SCAN_CH : n;
   Fr acc = fr_one();
   for (size_t i = lo; i < hi; i++) {
     Fr x = fr_load(a + i);
-    if (exclusive) {
-      fr_store(a + i, acc);
-      acc = fr_mul(acc, x);
-    } else {
-      acc = fr_mul(acc, x);
-      fr_store(a + i, acc);
-    }
+    fr_store(a + i, acc);
+    acc = fr_mul(acc, x);
   }
-  fr_store(tot + t, acc);
+  fr_store(p.tot[blockIdx.y] + t, acc);
 }
-__global__ void k_mulscan_apply(Fr* a, size_t n, const Fr* carry) {
+__global__ void k_mulscan2_apply(ScanPair p, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   size_t ch = i / SCAN_CH;
   if (ch == 0) return;
-  fr_store(a + i, fr_mul(fr_load(a + i), fr_load(carry + ch)));
+  Fr* a = p.a[blockIdx.y];
+  fr_store(a + i, fr_mul(fr_load(a + i), fr_load(p.tot[blockIdx.y] + ch)));
 }
-
-static int mulscan(tp_ctx* ctx, Fr* a, size_t n, bool exclusive, int level) {
+// exclusive prefix products of a0[0..n) and a1[0..n), in place
+static int mulscan2_exclusive(tp_ctx* ctx, Fr* a0, Fr* a1, size_t n, int level) {
+  ScanPair p;
+  p.a[0] = a0;
+  p.a[1] = a1;
+  p.tot[0] = p.tot[1] = nullptr;
   if (n <= SCAN_BASE) {
-    k_mulscan_serial<<<1, 1, 0, ctx->stream>>>(a, n, exclusive ? 1 : 0);
-    TP_LAUNCH(ctx, "k_mulscan_serial");
+    k_mulscan2_serial<<<2, 32, 0, ctx->stream>>>(p, n);
+    TP_LAUNCH(ctx, "k_mulscan2_serial");
     return TP_OK;
   }
   size_t nch = (n + SCAN_CH - 1) / SCAN_CH;
-  TP_TRY(ensure(ctx, ctx->scan_tmp[level], nch * sizeof(Fr)));
-  Fr* tot = (Fr*)ctx->scan_tmp[level].p;
-  k_mulscan_chunk<<<ew_grid(nch), EW_THREADS, 0, ctx->stream>>>(a, n, tot, exclusive ? 1 : 0);
-  TP_LAUNCH(ctx, "k_mulscan_chunk");
-  TP_TRY(mulscan(ctx, tot, nch, true, level + 1));
-  k_mulscan_apply<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(a, n, tot);
-  TP_LAUNCH(ctx, "k_mulscan_apply");
+  TP_TRY(ensure(ctx, ctx->scan_tmp[level], 2 * nch * sizeof(Fr)));
+  p.tot[0] = (Fr*)ctx->scan_tmp[level].p;
+  p.tot[1] = p.tot[0] + nch;
+  k_mulscan2_chunk<<<dim3(ew_grid(nch), 2), EW_THREADS, 0, ctx->stream>>>(p, n);
+  TP_LAUNCH(ctx, "k_mulscan2_chunk");
+  TP_TRY(mulscan2_exclusive(ctx, p.tot[0], p.tot[1], nch, level + 1));
+  k_mulscan2_apply<<<dim3(ew_grid(n), 2), EW_THREADS, 0, ctx->stream>>>(p, n);
+  TP_LAUNCH(ctx, "k_mulscan2_apply");
   return TP_OK;
 }
 
 // =====================================================================================
-// grand product
+// grand product  (permutation/src/proving.rs:7-31)
 // =====================================================================================
+// z[0] = 1, z[j+1] = prod_{k<=j} num_k / den_k with num_k = prod_i (v_ik + beta id_ik + gamma), den_k likewise over
+// sigma.  The reference inverts every denominator; here NOTHING is inverted per element:
+//     1 / prod_{k<=j} den_k = Dtot^-1 * prod_{k>j} den_k,
+// so z[j+1] = (prefix product of num up to j) * (suffix product of den after j) * Dtot^-1 -- two product scans that
+// share their launches and ONE inversion per proof, done by the host between the up- and the down-sweep (it also
+// replaces the zero-denominator flag: a zero denominator makes Dtot zero).  About 15 field products per row in all.
+#define PERM_CH 16   // rows per thread
 struct PermArgs {
   const Fr* v[3];
   const Fr* id[3];
   const Fr* sg[3];
   Fr beta, gamma;
   size_t n;
-  Fr* num;
-  Fr* den;
-  unsigned* flag;
+  Fr* pre;     // n: prefix product of num inside the row's chunk (inclusive)
+  Fr* den;     // n: den of the row
+  Fr* tot_num; // nch + 1: chunk totals of num, then a trailing one
+  Fr* tot_den; // nch + 1: chunk totals of den in REVERSE chunk order, then a trailing one
+  size_t nch;
 };
-__global__ void k_perm_numden(PermArgs a) {
-  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.n) return;
-  Fr num = fr_one(), den = fr_one();
-  bool zero = false;
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    Fr v = fr_add(fr_load(a.v[i] + j), a.gamma);
-    Fr nu = fr_add(v, pmul(a.beta, fr_load(a.id[i] + j)));
-    Fr de = fr_add(v, pmul(a.beta, fr_load(a.sg[i] + j)));
-    zero |= fr_is_zero(de);
-    num = i == 0 ? nu : pmul(num, nu);
-    den = i == 0 ? de : pmul(den, de);
-  }
-  if (zero) atomicOr(a.flag, 1u);
-  fr_store(a.num + j, num);
-  fr_store(a.den + j, den);
-}
-// ratio[j] = num[j] / den[j] with one Fermat inversion per BINV_CH elements; written to out[j].
-#define BINV_CH 16
-__global__ void k_batch_ratio(const Fr* num, const Fr* den, size_t n, Fr* out) {
+__global__ void __launch_bounds__(128) k_perm_chunks(PermArgs a) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t lo = t * BINV_CH;
-  if (lo >= n) return;
-  int cnt = (int)(lo + BINV_CH < n ? BINV_CH : n - lo);
-  Fr pre[BINV_CH];
-  Fr acc = fr_one();
-  for (int i = 0; i < cnt; i++) {
-    pre[i] = acc;  // product of den[lo .. lo+i-1]
-    acc = pmul(acc, fr_load(den + lo + i));
+  if (t > a.nch) return;
+  if (t == a.nch) {   // the trailing ones: the exclusive scans then leave the grand totals there
+    fr_store(a.tot_num + a.nch, fr_one());
+    fr_store(a.tot_den + a.nch, fr_one());
+    return;
   }
-  Fr inv = fr_inv(acc);
-  for (int i = cnt - 1; i >= 0; i--) {
-    Fr d = fr_load(den + lo + i);
-    Fr di = pmul(inv, pre[i]);  // 1 / den[lo+i]
-    inv = pmul(inv, d);
-    fr_store(out + lo + i, pmul(fr_load(num + lo + i), di));
+  const size_t lo = t * PERM_CH;
+  const size_t hi = lo + PERM_CH < a.n ? lo + PERM_CH : a.n;
+  Fr pn = fr_one(), pd = fr_one();
+  for (size_t j = lo; j < hi; j++) {
+    Fr num, den;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Fr v = fr_add(fr_load(a.v[i] + j), a.gamma);
+      Fr nu = fr_add(v, pmul(a.beta, fr_load(a.id[i] + j)));
+      Fr de = fr_add(v, pmul(a.beta, fr_load(a.sg[i] + j)));
+      num = i == 0 ? nu : pmul(num, nu);
+      den = i == 0 ? de : pmul(den, de);
+    }
+    pn = j == lo ? num : pmul(pn, num);
+    pd = j == lo ? den : pmul(pd, den);
+    fr_store(a.pre + j, pn);
+    fr_store(a.den + j, den);
   }
+  fr_store(a.tot_num + t, pn);
+  fr_store(a.tot_den + (a.nch - 1 - t), pd);
 }
-__global__ void k_set_one(Fr* p) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) fr_store(p, fr_one());
+// carry_num[t] = product of num over the chunks before t; carry_den[nch-1-t] = product of den over the chunks after t
+__global__ void __launch_bounds__(128) k_perm_finish(PermArgs a, Fr dtot_inv, Fr* __restrict__ z /* n + 1 */) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.nch) return;
+  const size_t lo = t * PERM_CH;
+  const size_t hi = lo + PERM_CH < a.n ? lo + PERM_CH : a.n;
+  if (t == 0) fr_store(z, fr_one());
+  Fr k = pmul(pmul(fr_load(a.tot_num + t), fr_load(a.tot_den + (a.nch - 1 - t))), dtot_inv);
+  // walk the chunk backwards: k = (carries) * Dtot^-1 * product of the chunk's den after row j
+  for (size_t j = hi; j-- > lo;) {
+    fr_store(z + j + 1, pmul(fr_load(a.pre + j), k));
+    if (j > lo) k = pmul(k, fr_load(a.den + j));
+  }
 }
 
 int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],
-                           size_t n, const Fr& beta, const Fr& gamma, Fr* out) {
+                           size_t n, const Fr& beta, const Fr& gamma, Fr* out, bool* closes) {
   ProfScope prof(ctx, TP_PHASE_PERM);
+  const size_t nch = (n + PERM_CH - 1) / PERM_CH;
   TP_TRY(ensure(ctx, ctx->misc[0], n * sizeof(Fr)));
   TP_TRY(ensure(ctx, ctx->misc[1], n * sizeof(Fr)));
-  TP_TRY(ensure(ctx, ctx->flag, sizeof(unsigned)));
+  TP_TRY(ensure(ctx, ctx->misc[2], 2 * (nch + 1) * sizeof(Fr)));
   PermArgs a;
   for (int i = 0; i < 3; i++) {
     a.v[i] = values[i];
@@ -159,21 +174,26 @@ int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* con
   a.beta = beta;
   a.gamma = gamma;
   a.n = n;
-  a.num = (Fr*)ctx->misc[0].p;
+  a.nch = nch;
+  a.pre = (Fr*)ctx->misc[0].p;
   a.den = (Fr*)ctx->misc[1].p;
-  a.flag = (unsigned*)ctx->flag.p;
-  TP_CUDA_OK(ctx, cudaMemsetAsync(a.flag, 0, sizeof(unsigned), ctx->stream));
-  k_perm_numden<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(a);
-  TP_LAUNCH(ctx, "k_perm_numden");
-  size_t nth = (n + BINV_CH - 1) / BINV_CH;
-  k_batch_ratio<<<(unsigned)((nth + 127) / 128), 128, 0, ctx->stream>>>(a.num, a.den, n, out + 1);
-  TP_LAUNCH(ctx, "k_batch_ratio");
-  TP_TRY(mulscan(ctx, out + 1, n, false, 0));
-  k_set_one<<<1, 1, 0, ctx->stream>>>(out);
-  TP_LAUNCH(ctx, "k_set_one");
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, a.flag, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  a.tot_num = (Fr*)ctx->misc[2].p;
+  a.tot_den = a.tot_num + (nch + 1);
+  k_perm_chunks<<<(unsigned)((nch + 1 + 127) / 128), 128, 0, ctx->stream>>>(a);
+  TP_LAUNCH(ctx, "k_perm_chunks");
+  TP_TRY(mulscan2_exclusive(ctx, a.tot_num, a.tot_den, nch + 1, 0));
+  // the one inversion: Dtot = product of every denominator (the last slot of the reversed den scan)
+  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, a.tot_den + nch, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  TP_CUDA_OK(ctx, cudaMemcpyAsync((uint8_t*)ctx->pinned + 32, a.tot_num + nch, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  if (*(unsigned*)ctx->pinned) return fail(ctx, TP_ERR_ZERO_DENOMINATOR, "permutation prove: zero denominator");
+  tph::HFr dtot, ntot;
+  memcpy(dtot.v, ctx->pinned, 32);
+  memcpy(ntot.v, (uint8_t*)ctx->pinned + 32, 32);
+  if (dtot.is_zero()) return fail(ctx, TP_ERR_ZERO_DENOMINATOR, "permutation prove: zero denominator");
+  const tph::HFr dinv = dtot.inv();
+  if (closes) *closes = ntot * dinv == tph::HFr::one();   // out[n], the value the caller pops (proof.rs:120)
+  k_perm_finish<<<(unsigned)((nch + 127) / 128), 128, 0, ctx->stream>>>(a, to_dev(dinv), out);
+  TP_LAUNCH(ctx, "k_perm_finish");
   return TP_OK;
 }
 
@@ -428,10 +448,14 @@ int quotient_numerator_dev(tp_ctx* ctx, const QuotientArgs& a, const unsigned* c
 // N(X) = sum_j X^(jn) N_j(X), deg N_j < n.  On coset k, x^n = iota^k (iota = omega_4n^n, iota^2 = -1),
 // so the interpolant of coset k is C_k = sum_j iota^(kj) N_j and N_j = 1/4 sum_k iota^(-kj) C_k.
 // Then t_2 = N_3, t_1 = N_2 + t_2, t_0 = N_1 + t_1.
-__global__ void k_quotient_combine(const Fr* __restrict__ c4, size_t n, Fr iota_inv, Fr quarter, Fr* __restrict__ t) {
+// c0_is_zero: the numerator vanishes on H itself (always, for a witness that satisfies the copy constraints), so
+// coset 0 was never evaluated and its slot holds nothing.
+__global__ void k_quotient_combine(const Fr* __restrict__ c4, size_t n, Fr iota_inv, Fr quarter, int c0_is_zero,
+                                   Fr* __restrict__ t) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const Fr c0 = fr_load(c4 + i), c1 = fr_load(c4 + n + i), c2 = fr_load(c4 + 2 * n + i), c3 = fr_load(c4 + 3 * n + i);
+  const Fr c0 = c0_is_zero ? fr_zero() : fr_load(c4 + i);
+  const Fr c1 = fr_load(c4 + n + i), c2 = fr_load(c4 + 2 * n + i), c3 = fr_load(c4 + 3 * n + i);
   const Fr e = fr_add(c0, c2), f = fr_sub(c0, c2), g = fr_add(c1, c3);
   const Fr h = fr_mul(iota_inv, fr_sub(c1, c3));
   const Fr n1 = fr_mul(quarter, fr_add(f, h));
@@ -442,16 +466,14 @@ __global__ void k_quotient_combine(const Fr* __restrict__ c4, size_t n, Fr iota_
   fr_store(t + n + i, t1);
   fr_store(t + i, fr_add(n1, t1));
 }
-int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, const Fr* tw4, Fr* t) {
+int quotient_combine_dev(tp_ctx* ctx, const Fr* c4, size_t n, bool c0_is_zero, Fr* t) {
   ProfScope prof(ctx, TP_PHASE_QUOTIENT);
-  // iota^-1 = -iota is read back once per call from the twiddle table (tw4[n]); quarter = 4^-1
-  Fr iota;
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, tw4 + n, sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(&iota, ctx->pinned, sizeof(Fr));
-  tph::HFr iota_inv = to_host(iota).neg();
+  // iota = omega_4n^n is a primitive fourth root of unity: iota^-1 = -iota; quarter = 4^-1
+  unsigned log_n = 0;
+  while (((size_t)1 << log_n) < n) log_n++;
+  tph::HFr iota_inv = omega_for_log(log_n + 2).pow_u64((uint64_t)n).neg();
   tph::HFr quarter = tph::HFr::from_u64(4).inv();
-  k_quotient_combine<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(c4, n, to_dev(iota_inv), to_dev(quarter), t);
+  k_quotient_combine<<<ew_grid(n), EW_THREADS, 0, ctx->stream>>>(c4, n, to_dev(iota_inv), to_dev(quarter), c0_is_zero ? 1 : 0, t);
   TP_LAUNCH(ctx, "k_quotient_combine");
   return TP_OK;
 }
