@@ -853,7 +853,9 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
       TP_TRY(ntt_batch_dev(ctx, ins, outs, cos, nmine, c->log_n, true));
     }
     if (shard) {
+      TP_TRY(comm_group_begin(ctx));
       for (unsigned k = first; k < 4; k++) TP_TRY(comm_bcast(ctx, c->buf4[0] + (size_t)k * n, n * sizeof(Fr), owner(k)));
+      TP_TRY(comm_group_end(ctx));
     }
     TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, skip0, c->t));
   }
@@ -984,8 +986,10 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
     uint8_t* stage = (uint8_t*)c->buf4[0];                       // [rank][column][rows], at most 4n Fr in total
     for (int j = 0; j < ncols; j++)
       TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * ncols + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
+    TP_TRY(comm_group_begin(ctx));
     for (int r = 0; r < ctx->world; r++)
       TP_TRY(comm_bcast(ctx, stage + (size_t)r * ncols * slice, ncols * slice, r));
+    TP_TRY(comm_group_end(ctx));
     for (int j = 0; j < ncols; j++)
       TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, ncols * slice, slice, world,
                                         cudaMemcpyDeviceToDevice, ctx->stream));

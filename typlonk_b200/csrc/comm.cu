@@ -32,6 +32,8 @@ struct NcclApi {
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   bool ok = false;
 };
 static NcclApi& nccl_api() {
@@ -53,7 +55,9 @@ static NcclApi& nccl_api() {
     api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
     api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllGather && api.Broadcast &&
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.ok = api.GroupStart && api.GroupEnd && api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.AllGather && api.Broadcast &&
              api.GetErrorString;
   });
   return api;
@@ -127,6 +131,23 @@ int comm_bcast(tp_ctx* ctx, void* dev_ptr, size_t bytes, int root) {
     return TP_OK;
   }
   return fail(ctx, TP_ERR_COLLECTIVE, "sharded context without a communicator (tp_ctx_comm_init_rank)");
+}
+
+// Several broadcasts with different roots issued as ONE NCCL group run concurrently (every root's links are busy at
+// the same time) instead of one after the other.  No-ops on the other transports.
+int comm_group_begin(tp_ctx* ctx) {
+  if (ctx->world > 1 && ctx->nccl) {
+    ncclResult_t r = nccl_api().GroupStart();
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclGroupStart", r);
+  }
+  return TP_OK;
+}
+int comm_group_end(tp_ctx* ctx) {
+  if (ctx->world > 1 && ctx->nccl) {
+    ncclResult_t r = nccl_api().GroupEnd();
+    if (r != ncclSuccess) return nccl_fail(ctx, "ncclGroupEnd", r);
+  }
+  return TP_OK;
 }
 
 // ---- worker threads of a device group -------------------------------------------------------------------

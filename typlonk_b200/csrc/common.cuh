@@ -191,6 +191,8 @@ struct ProfScope {
 // every rank calls with the same sizes; ordered after the work already queued on ctx->stream
 int comm_allgather(tp_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes_per_rank);
 int comm_bcast(tp_ctx* ctx, void* dev_ptr, size_t bytes, int root);
+int comm_group_begin(tp_ctx* ctx);   // broadcasts between begin and end run as one concurrent group (NCCL)
+int comm_group_end(tp_ctx* ctx);
 inline bool comm_ready(const tp_ctx* ctx) { return ctx->world > 1 && (ctx->nccl || ctx->local); }
 void comm_release(tp_ctx* ctx);
 // fn(children[r], r) on every worker thread of a group front at once; first non-zero status, error text copied up
