@@ -345,6 +345,10 @@ int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_
  * `StdRng::seed_from_u64(seed)` (ChaCha12), written as Montgomery limbs -- the same stream the
  * reference's Fiat-Shamir uses (plonk/src/proof/challenges.rs:38-45).  Host only. */
 int tp_fr_rand_stream(uint64_t seed, size_t count, uint64_t* out);
+/* The raw output words of the library's `StdRng` (rand 0.8: ChaCha12; csrc/transcript.h), seeded either with a 32-byte
+ * seed (`from_seed`, seed32 != NULL) or with `seed_from_u64(seed_u64)` (rand_core 0.6 PCG32 expansion).  Host only; lets
+ * the generator behind the Fiat-Shamir challenges be checked against the rand crates' own value-stability constants. */
+int tp_stdrng_words(const uint8_t* seed32, uint64_t seed_u64, size_t count, uint32_t* out);
 /* "tp-build-stamp:<sha256 of the sources and flags this binary was compiled from>" (host only). */
 const char* tp_build_stamp(void);
 /* Self-test of the device field/curve arithmetic against host arithmetic; 0 failures expected. */

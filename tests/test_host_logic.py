@@ -202,3 +202,30 @@ def test_integration_doc_names_every_entry_point():
         doc = doc.replace("…_" + short, "tp_permutation_builder_" + short)
     missing = [n for n in declared if n not in doc]
     assert not missing, missing
+
+
+def test_library_stdrng_matches_the_rand_crates_own_constants():
+    """The generator behind the product's Fiat-Shamir challenges (csrc/transcript.h), checked WITHOUT the oracle against
+    constants from the pinned crates' own tests: rand_core 0.6 `test_seed_from_u64` (5029875928683246316) and rand 0.8
+    `test_stdrng_construction` ([10719222850664546238, 14064965282130556830])."""
+    import struct
+    from typlonk_b200 import ffi
+    # seed_from_u64(0): the ChaCha key is the PCG32 expansion; recover its first 8 bytes through a second generator
+    # seeded with the oracle-free formula is not possible from outside, so compare streams instead: from_seed(key) and
+    # seed_from_u64(0) must agree when key starts with the crate constant
+    w = ffi.stdrng_words(4, seed32=bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16))
+    assert w[0] | (w[1] << 32) == 10719222850664546238
+    w = ffi.stdrng_words(10, seed32=bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16))
+    seed1 = struct.pack("<8I", *w[2:10])
+    w1 = ffi.stdrng_words(2, seed32=seed1)
+    assert w1[0] | (w1[1] << 32) == 14064965282130556830
+    # PCG32 expansion: the key seed_from_u64(0) builds starts with the bytes of 5029875928683246316 (little endian);
+    # brute-force free check: a from_seed generator whose key is that expansion (known in full from the same recurrence)
+    mul, inc, state, key = 6364136223846793005, 11634580027462260723, 0, b""
+    for _ in range(8):
+        state = (state * mul + inc) & (2**64 - 1)
+        xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+        rot = state >> 59
+        key += struct.pack("<I", ((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
+    assert int.from_bytes(key[:8], "little") == 5029875928683246316
+    assert ffi.stdrng_words(40, seed_u64=0) == ffi.stdrng_words(40, seed32=key)

@@ -43,6 +43,25 @@ def test_chacha_and_seed_expansion_vectors():
     assert hashlib.blake2b(b"").hexdigest().startswith("786a02f742015903")
 
 
+def test_rand_crates_own_value_stability_constants():
+    """Pins taken from the pinned crates' OWN test suites (Cargo.lock: rand 0.8.4, rand_core 0.6.3, rand_chacha 0.3.1),
+    i.e. known answers that do not come from this repository:
+      * rand_core 0.6 `test_seed_from_u64`: the first 8 bytes `seed_from_u64(0)` expands to, as a little-endian u64,
+        are 5029875928683246316  -> pins the PCG32 seed expansion of challenges.rs:38;
+      * rand 0.8 `rngs::std::test::test_stdrng_construction`: StdRng::from_seed([1,0,0,0, 23,0,0,0, 200,1,0,0,
+        210,30,0,0, 0...]) yields next_u64 = 10719222850664546238, and StdRng::from_rng of it then yields
+        14064965282130556830  -> pins ChaCha12, rand_chacha's counter / stream word layout, the order output words are
+        consumed in, next_u64 = lo | hi << 32 and fill_bytes;
+      * ChaCha20 block 0 of the zero key (RFC 7539 / rand_chacha `test_chacha_true_values_a`): 0xade0b876, 0x903df1a0 ..."""
+    import struct
+    assert int.from_bytes(rng.seed_from_u64_key(0)[:8], "little") == 5029875928683246316
+    r0 = rng.StdRng(bytes([1, 0, 0, 0, 23, 0, 0, 0, 200, 1, 0, 0, 210, 30, 0, 0] + [0] * 16))
+    assert r0.next_u64() == 10719222850664546238
+    r1 = rng.StdRng(b"".join(struct.pack("<I", r0.next_u32()) for _ in range(8)))
+    assert r1.next_u64() == 14064965282130556830
+    assert rng.chacha_block(bytes(32), 0, 0, 20)[:4] == [0xade0b876, 0x903df1a0, 0xe56a5d40, 0x28bd8653]
+
+
 def test_challenge_chain_golden():
     tr = curve.g1_serialize_unchecked(curve.g1_mul(curve.G1_GEN, 17)) * 3
     assert rng.challenge_seed(tr) == KNOWN["challenge_chain_17G_x3"]["seed"] == 13037422643194131432

@@ -1029,6 +1029,12 @@ int tp_selftest(tp_ctx* ctx, int* failures) {
   if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_selftest(c, failures); });
   return selftest_dev(ctx, failures);
 }
+int tp_stdrng_words(const uint8_t* seed32, uint64_t seed_u64, size_t count, uint32_t* out) {
+  if (!out && count) return TP_ERR_INVALID_ARG;
+  tph::StdRng rng = seed32 ? tph::StdRng::from_seed(seed32) : tph::StdRng::seed_from_u64(seed_u64);
+  for (size_t i = 0; i < count; i++) out[i] = rng.next_u32();
+  return TP_OK;
+}
 #ifndef TP_BUILD_STAMP
 #define TP_BUILD_STAMP "unstamped"
 #endif

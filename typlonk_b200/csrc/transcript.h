@@ -125,6 +125,15 @@ struct StdRng {
     r.pos = 16;
     return r;
   }
+  // `SeedableRng::from_seed`: the 32 bytes are the ChaCha key, little-endian words
+  static StdRng from_seed(const uint8_t seed[32]) {
+    StdRng r;
+    for (int i = 0; i < 8; i++)
+      r.key[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+    r.counter = 0;
+    r.pos = 16;
+    return r;
+  }
   void refill() {
     uint32_t init[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
     for (int i = 0; i < 8; i++) init[4 + i] = key[i];

@@ -38,7 +38,7 @@ SYMBOLS = [
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
     "tp_permutation_compile", "tp_fr_from_i64", "tp_fr_from_canonical", "tp_fr_to_canonical",
     "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
-    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp",
+    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp", "tp_stdrng_words",
 ]
 
 COMM_ID_BYTES = 128
@@ -109,6 +109,15 @@ def fr_rand_stream(seed: int, count: int) -> bytes:
     if rc != 0:
         raise TyplonkError(rc, "tp_fr_rand_stream")
     return bytes(out)
+
+
+def stdrng_words(count: int, seed32: bytes = None, seed_u64: int = 0):
+    """tp_stdrng_words: `count` raw u32 output words of the library's StdRng (host only)."""
+    out = (C.c_uint32 * count)()
+    rc = lib().tp_stdrng_words(_buf(seed32) if seed32 is not None else None, C.c_uint64(seed_u64), C.c_size_t(count), out)
+    if rc != 0:
+        raise TyplonkError(rc, "tp_stdrng_words")
+    return list(out)
 
 
 # ---- host-only entry points (no device, no context) --------------------------------------------
