@@ -175,6 +175,33 @@ def _cpu_prove(log_n, budget_s, max_steps):
     return sum(times) / len(times), len(times), coracle.threads(), proof
 
 
+def _b0_as_written(log_n):
+    """BASELINE.md B0: the reference's OWN algorithms (kzg/src/lib.rs:46-53 per-point double-and-add + affine conversion;
+    plonk/src/proof.rs:317-359 `naive_mul`), timed small on one core by the oracle's C++ statement of them and
+    EXTRAPOLATED to n = 2^log_n by their n and n^2 laws: 13 commitments of n points + ~19 n^2 schoolbook multiply-adds."""
+    from oracle import coracle
+    m = 1 << 10
+    tau, sel, perm, cols, pi = coracle.mul_chain_inputs(10)
+    c = coracle.Circuit(tau, sel, perm, m)
+    coeffs = coracle.fr_rand_stream(3, m)
+    t0 = time.perf_counter()
+    c.commit_as_written(coeffs)
+    t_point = (time.perf_counter() - t0) / m
+    c.close()
+    k = 1 << 11
+    a = coracle.fr_rand_stream(4, k)
+    t0 = time.perf_counter()
+    coracle.naive_mul(a, a)
+    t_pair = (time.perf_counter() - t0) / (k * k)
+    n = float(1 << log_n)
+    commit_s, quotient_s = 13 * n * t_point, 19 * n * n * t_pair
+    return {"value": (commit_s + quotient_s) * 1e3, "unit": UNIT, "cores": 1, "kind": "reference algorithm, EXTRAPOLATED",
+            "commit_us_per_point": round(t_point * 1e6, 2), "naive_mul_ns_per_coefficient_pair": round(t_pair * 1e9, 3),
+            "commit_s": round(commit_s, 1), "quotient_s": round(quotient_s, 1),
+            "sample": "measured: one as-written commit of 2^10 points and one 2^11 x 2^11 naive_mul on one core; "
+                      "extrapolated by 13 n and 19 n^2 to n=2^%d (never run at that size: it would take days)" % log_n}
+
+
 def run_reference(args):
     """CPU arm: the oracle's C++ port of the reference prover on the host cores, on the bench's own workload."""
     rank = int(os.environ.get("RANK", "0"))
@@ -418,6 +445,7 @@ def main():
         "north_star": None,
         "sweeps": None,
         "cpu_baseline": None,
+        "b0_as_written": None,
     }
 
     # ---- BASELINE.json configs[4] / the north-star target: the 2^22-gate circuit on these N GPUs, bytes checked -------
@@ -465,6 +493,7 @@ def main():
                 "sample": "ONE full prove of the same 2^%d workload by oracle/c (C++ port of the reference prover with "
                           "Pippenger + NTTs), %d host threads; no extrapolation" % (log_n, threads),
                 "same_bytes_as_gpu": cproof == proof}
+            line["b0_as_written"] = _b0_as_written(log_n)
         except Exception as e:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (e,)}
     if rank == 0 and args.dump_proof:

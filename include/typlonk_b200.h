@@ -102,6 +102,8 @@ int tp_ctx_group_size(const tp_ctx* ctx, int* ndev, int* uses_nccl);
  *       bucket-sorted list per thread in lockstep with one shared inversion per step (5M + 1S per addition);
  *   "msm_affine_rounds" (0..8, $TP_MSM_AFF_ROUNDS): batch-affine pair-addition rounds run on the bucket-sorted
  *       points before the XYZZ accumulation (kept for comparison; see profiles/);
+ *   "msm_reduce_l1" (0 = by size, 1 = never, 2 = whenever possible): whether the bucket reduction runs a level of
+ *       16-bucket running sums before its row / column tree sums (big bucket sets: yes; small / sharded ones: no);
  *   "quotient_all_cosets" (0/1): evaluate the quotient numerator on all four cosets of the 4n domain even when it is
  *       known to vanish on H (gates and copy constraints hold); by default that coset is skipped. */
 int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value);

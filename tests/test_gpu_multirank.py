@@ -76,6 +76,42 @@ def test_sharded_commit_edge_scalars(ctx, world):
     srs.destroy()
 
 
+@pytest.mark.parametrize("n", [40, 3000, 70000])
+def test_bucket_reduction_paths_agree(ctx, n):
+    """The bucket reduction has two shapes -- with and without the level of running sums in front of the tree sums --
+    chosen by the size of the bucket set; forced either way, on one device and on a 3-rank group, a commitment must
+    not change (and equals the oracle's on the small size)."""
+    from typlonk_b200 import field as F
+    from typlonk_b200.ffi import Context
+    from oracle.pyoracle import rng
+    tau = rng.fr_rand_stream(1, 1)[0]
+    srs = ctx.srs_from_secret(F.fr_to_bytes(tau), n - 3)
+    rnd = random.Random(n)
+    raw = F.fr_vec_to_bytes([rnd.randrange(F.R_MOD) for _ in range(n)])
+    want = ctx.commit(srs, raw)
+    if n <= 40:
+        from oracle.pyoracle import curve
+        pts, acc = [], curve.G1_GEN
+        for _ in range(n):
+            pts.append(acc)
+            acc = curve.g1_mul(acc, tau)
+        assert F.g1_from_abi(want) == curve.g1_msm(pts, F.fr_vec_from_bytes(raw))
+    for mode in (1, 2):
+        ctx.set_option("msm_reduce_l1", mode)
+        try:
+            assert ctx.commit(srs, raw) == want, "single device, msm_reduce_l1=%d" % mode
+        finally:
+            ctx.set_option("msm_reduce_l1", 0)
+    group = Context.multi([0, 0, 0])
+    gsrs = group.srs_from_secret(F.fr_to_bytes(tau), n - 3)
+    for mode in (0, 1, 2):
+        group.set_option("msm_reduce_l1", mode)
+        assert group.commit(gsrs, raw) == want, "3-rank group, msm_reduce_l1=%d" % mode
+    gsrs.destroy()
+    group.close()
+    srs.destroy()
+
+
 def test_group_refuses_device_pointer_entry_points(ctx):
     from typlonk_b200.ffi import Context, TyplonkError
     group = Context.multi([0, 0])

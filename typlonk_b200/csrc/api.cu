@@ -150,6 +150,11 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
     ctx->msm_affine_chains = (unsigned)value;
     return TP_OK;
   }
+  if (strcmp(name, "msm_reduce_l1") == 0) {
+    if (value < 0 || value > 2) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_reduce_l1 must be 0, 1 or 2");
+    ctx->msm_reduce_l1 = (unsigned)value;
+    return TP_OK;
+  }
   if (strcmp(name, "quotient_all_cosets") == 0) {
     if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: quotient_all_cosets must be 0 or 1");
     ctx->quotient_all_cosets = (unsigned)value;

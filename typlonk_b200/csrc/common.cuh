@@ -53,6 +53,7 @@ struct tp_ctx {
   // tunables (tp_ctx_set_option)
   unsigned msm_aff_rounds = 0;   // batch-affine rounds before the XYZZ accumulation (msm.cu 4a); 0 = off
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
+  unsigned msm_reduce_l1 = 0;     // bucket reduction's running-sum level: 0 by size, 1 never, 2 whenever the set allows it
   unsigned quotient_all_cosets = 0;  // 1: evaluate the quotient numerator on all four cosets even when it is known to vanish on H
   // work counters (tp_ctx_get_stat)
   double stat_msm_entries = 0, stat_msm_calls = 0, stat_msm_c = 0, stat_msm_nwin = 0, stat_msm_levels = 0, stat_msm_chunk = 0;

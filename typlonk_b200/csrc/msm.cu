@@ -15,12 +15,14 @@
 //                       coordinates, writes complete runs straight to their bucket and emits
 //                       head/tail partials for runs that cross chunk boundaries
 //   5. k_msm_merge    : stitches the boundary partials
-//   6. k_msm_wsum_level / k_msm_masked_sum: sum_v v * B_v of each bucket set without a single
-//                       scalar multiplication: levels of 16- then 4-bucket running sums, then the
-//                       remaining index bits as masked tree sums (see "bucket reduction" below)
-//   7. host           : <= 40 additions/doublings per bucket set + affine conversion (serial tail;
-//                       one CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic),
-//                       and the all-gather of partial points when the MSM is sharded over GPUs.
+//   6. k_msm_wsum_level / k_msm_rowcol / k_msm_bitsums: sum_v v * B_v of each bucket set without a
+//                       single scalar multiplication: (big sets) one level of 16-bucket running sums,
+//                       then row / column tree sums, then the remaining index bits as masked tree
+//                       sums (see "bucket reduction" below)
+//   7. sharded over GPUs (comm.cu): every rank does 1-6 for the buckets it owns; the ranks' step-6
+//                       outputs are all-gathered on the stream and combined by k_msm_combine
+//   8. host           : ~50 additions/doublings per bucket set + affine conversion (serial tail;
+//                       one CPU thread is ~10x faster than one GPU thread at 381-bit arithmetic).
 //
 // Fixed-base tables: the SRS never changes, so tp_srs holds `levels` copies of it, level k =
 // 2^(c k) * P_i (srs.cu).  Window w of scalar i then adds table[w % levels][i] into bucket set
@@ -171,7 +173,7 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
       }
     }
     keys[(size_t)(wbase + w) * n + i] = key;
-    ranks[(size_t)(wbase + w) * n + i] = rank;
+    if (key != MSM_NONE) ranks[(size_t)(wbase + w) * n + i] = rank;   // the scatter reads ranks of owned entries only
   }
 }
 
@@ -820,18 +822,12 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
 // Wanted per bucket set: V = sum_b (b + 1) * B_b = P + F(B), with P = sum_b B_b and
 // F(A) = sum_m m * A_m.  Writing m = S * seg + j:
 //     F(A) = sum_seg t_seg + S * F(R),   t_seg = sum_j j * A[S seg + j],  R_seg = sum_j A[S seg + j]
-// k_msm_wsum_level computes (t_seg, R_seg) with running sums (2 additions per element) and shrinks
-// the array S-fold.  After the levels the short array R is finished bit by bit,
-//     F(R) = sum_k 2^k * (sum of R_m over the m with bit k set),     P = sum_m R_m,
-// all of them masked tree sums (k_msm_masked_sum) that run side by side in one launch together with
-// the plain sums T_l = sum_seg t_seg of every level.  The host then needs ~40 group operations per
-// set (S is a power of two) instead of a Horner walk over all windows.  No thread ever does a
-// scalar multiplication and the longest dependent chain is 2 S additions per level.
-#define WSUM_S_FIRST 16      // segment length of the first level (where the work is: 2 additions per bucket)
-#define WSUM_S_NEXT 4        // later levels are latency-bound: shorter chains
-#define WSUM_MIN 8192        // keep levelling while a set still has at least this many entries
-                             // (swept on B200 at 2^20: (32768,8,4) 11.9 ms of reduction per proof, (8192,16,4) 10.1 ms)
-#define WSUM_MAX_LEVELS 6
+// k_msm_wsum_level computes (t_seg, R_seg) with running sums (2 additions per element, every lane busy) and
+// shrinks the array S-fold; the plain sum T = sum_seg t_seg and F(R) are left to the tree-sum kernels below.
+// No thread ever does a scalar multiplication.
+#define WSUM_S_FIRST 16      // segment length of the first running-sum level (where the work is)
+#define WSUM_S_NEXT 8        // and of the later ones
+#define WSUM_MAX_LEVELS 4
 __global__ void __launch_bounds__(128) k_msm_wsum_level(const G1Xyzz* __restrict__ in, const unsigned* __restrict__ hist,
                                                         unsigned m_in, unsigned seg, unsigned total_out,
                                                         G1Xyzz* __restrict__ r_out, G1Xyzz* __restrict__ t_out) {
@@ -851,46 +847,54 @@ __global__ void __launch_bounds__(128) k_msm_wsum_level(const G1Xyzz* __restrict
   xyzz_store(t_out + t, tot);
 }
 
-// Masked sums.  Task k covers `nmask[k]` consecutive mask slots starting at mask_base[k]: slot 0 of
-// a task is the plain sum of in[k][set * m[k] + i], slot 1 + b sums the i with bit b set.
-// grid = (slices, total mask slots, sets); every block tree-sums its slice.
-#define SUM_MAX_TASKS (WSUM_MAX_LEVELS + 1)
-struct MsmSumTasks {
-  const G1Xyzz* in[SUM_MAX_TASKS];
-  const unsigned* hist[SUM_MAX_TASKS];  // non-null: element present iff hist != 0 (raw buckets)
-  unsigned m[SUM_MAX_TASKS];
-  unsigned slices[SUM_MAX_TASKS];       // blocks per mask slot of this task (<= gridDim.x)
-  unsigned mask_base[SUM_MAX_TASKS + 1];
+// Tree sums.  What the running-sum levels leave (or, for a small bucket set, the raw buckets themselves) is an array
+// A of m entries per set, viewed as a rows x cols matrix, entry index = cols * hi + lo.  With the row sums
+// D[hi] = sum_lo A[hi, lo] and the column sums C[lo] = sum_hi A[hi, lo],
+//     F(A) = sum_i i A_i = F(C) + cols * F(D),      P = sum_i A_i = sum_hi D[hi]
+// -- two additions per entry again, but as tree sums whose longest dependent chain is cols / 64 + 6 additions instead
+// of the 2 S of a running-sum level: that chain is what a small (sharded, or single-MSM) bucket set is bound by.
+// The short arrays D and C are then finished bit by bit, F(X) = sum_k 2^k (sum of the X_i with bit k of i set).
+// Both stages are lists of JOBS of one shape -- sum `count` entries `stride` apart, optionally only those whose
+// index has a given bit set, optionally skipping buckets the histogram says were never written -- one block per
+// (job, set); a stage is one launch.
+#define TS_THREADS 64
+#define TS_MAX_TASKS 32
+struct TreeTask {
+  const G1Xyzz* src;      // first entry of job 0 of set 0
+  const unsigned* hist;   // parallel to src (raw buckets) or null
+  G1Xyzz* dst;            // result of job 0 of set 0
+  size_t set_stride;      // entries between the sets of src
+  unsigned dst_set_stride;
+  unsigned njobs;         // jobs per set
+  unsigned job_stride;    // entries between the first entries of consecutive jobs
+  unsigned count, stride; // entries a job sums and their distance
+  int bit;                // >= 0: only entries whose index (0 .. count) has this bit set; for such tasks njobs == 1
+};
+struct TreeTasks {
+  TreeTask t[TS_MAX_TASKS];
+  unsigned first[TS_MAX_TASKS + 1];  // block index of each task's job 0
   int ntasks;
 };
-#define SUM_THREADS 64
-__global__ void __launch_bounds__(SUM_THREADS) k_msm_masked_sum(MsmSumTasks tasks, G1Xyzz* __restrict__ out) {
-  __shared__ G1Xyzz sh[SUM_THREADS];
+__global__ void __launch_bounds__(TS_THREADS) k_msm_treesum(TreeTasks tasks) {
+  __shared__ G1Xyzz sh[TS_THREADS];
   int k = 0;
-  while (k + 1 < tasks.ntasks && blockIdx.y >= tasks.mask_base[k + 1]) k++;
-  G1Xyzz* dst = out + ((size_t)blockIdx.z * tasks.mask_base[tasks.ntasks] + blockIdx.y) * gridDim.x + blockIdx.x;
-  const unsigned slices = tasks.slices[k];
-  if (blockIdx.x >= slices) {  // this task needs fewer blocks than the widest one
-    if (threadIdx.x == 0) xyzz_store(dst, xyzz_identity());
-    return;
-  }
-  const unsigned mask = blockIdx.y - tasks.mask_base[k];
-  const unsigned m = tasks.m[k];
-  const unsigned per = (m + slices - 1) / slices;
-  const unsigned lo = blockIdx.x * per;
-  const unsigned hi = lo + per < m ? lo + per : m;
-  const G1Xyzz* in = tasks.in[k] + (size_t)blockIdx.z * m;
-  const unsigned* hist = tasks.hist[k] ? tasks.hist[k] + (size_t)blockIdx.z * m : nullptr;
+  while (k + 1 < tasks.ntasks && blockIdx.x >= tasks.first[k + 1]) k++;
+  const TreeTask& tk = tasks.t[k];
+  const unsigned job = blockIdx.x - tasks.first[k], set = blockIdx.y;
+  const size_t base = (size_t)set * tk.set_stride + (size_t)job * tk.job_stride;
+  const G1Xyzz* src = tk.src + base;
+  const unsigned* h = tk.hist ? tk.hist + base : nullptr;
   G1Xyzz acc = xyzz_identity();
-  for (unsigned i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    if (mask != 0 && !((i >> (mask - 1)) & 1)) continue;
-    if (hist && hist[i] == 0) continue;
-    G1Xyzz p = xyzz_load(in + i);
+  for (unsigned i = threadIdx.x; i < tk.count; i += TS_THREADS) {
+    if (tk.bit >= 0 && !((i >> tk.bit) & 1)) continue;
+    const size_t e = (size_t)i * tk.stride;
+    if (h && h[e] == 0) continue;   // raw buckets: empty ones were never written
+    G1Xyzz p = xyzz_load(src + e);
     xyzz_add(acc, p);
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
-  for (unsigned d = blockDim.x / 2; d > 0; d >>= 1) {
+  for (unsigned d = TS_THREADS / 2; d > 0; d >>= 1) {
     if (threadIdx.x < d) {
       G1Xyzz a = sh[threadIdx.x];
       G1Xyzz b = sh[threadIdx.x + d];
@@ -899,7 +903,7 @@ __global__ void __launch_bounds__(SUM_THREADS) k_msm_masked_sum(MsmSumTasks task
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) xyzz_store(dst, sh[0]);
+  if (threadIdx.x == 0) xyzz_store(tk.dst + (size_t)set * tk.dst_set_stride + job, sh[0]);
 }
 
 // ---- 7. cross-rank combination (sharded MSM) --------------------------------------------------------
@@ -1222,38 +1226,39 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
       TP_LAUNCH(ctx, "k_msm_accumulate");
     }
   }
-  // reduction plan: levels of running sums (segment 16, then 4), then masked sums over what is left
+  // Reduction plan.  Running-sum levels (every lane busy, two additions per entry, but a chain of 2 S dependent
+  // additions per thread) while the batch still has entries enough to keep the whole GPU busy with them -- 16-bucket
+  // segments first, 8 after that -- then the tree sums.  A small bucket set (a sharded rank's share, a single small
+  // MSM) is latency-bound from the start and goes straight to the tree sums.
+  static const unsigned env_l1 = env_uint("TP_MSM_REDUCE_L1", 0);   // 1: no running-sum level, 2: as many as fit
+  const unsigned l1_mode = ctx->msm_reduce_l1 ? ctx->msm_reduce_l1 : env_l1;
   unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1];
   int nl = 0;
   m_level[0] = pl.nbuck;
   seg_level[0] = 1;
-  // Long first-level segments and deep levelling pay when there are buckets enough to keep every SM busy with
-  // them (>= 2^19 over the batch: 16/4/8192, 10.1 ms of reduction per 2^20 proof instead of 11.9); small bucket
-  // sets are latency-bound and keep short chains (8/4/32768: 0.47 instead of 0.66 ms at 2^16).
-  const bool wide = (size_t)nsets_total * pl.nbuck >= ((size_t)1 << 19);
-  static const unsigned env_min = env_uint("TP_MSM_WSUM_MIN", 0), env_s1 = env_uint("TP_MSM_WSUM_S1", 0),
-                        env_s2 = env_uint("TP_MSM_WSUM_S2", 0);
-  const unsigned wsum_min = env_min ? env_min : (wide ? WSUM_MIN : 32768u);
-  const unsigned wsum_s1 = env_s1 ? env_s1 : (wide ? WSUM_S_FIRST : 8u), wsum_s2 = env_s2 ? env_s2 : WSUM_S_NEXT;
-  while (nl < WSUM_MAX_LEVELS && m_level[nl] >= wsum_min && m_level[nl] >= 2 * (nl == 0 ? wsum_s1 : wsum_s2)) {
-    seg_level[nl + 1] = nl == 0 ? wsum_s1 : wsum_s2;
-    m_level[nl + 1] = m_level[nl] / seg_level[nl + 1];
+  while (nl < WSUM_MAX_LEVELS) {
+    const unsigned sg = nl == 0 ? WSUM_S_FIRST : WSUM_S_NEXT;
+    if (m_level[nl] < 2 * sg || l1_mode == 1) break;
+    if (l1_mode != 2 && (size_t)nsets_total * m_level[nl] < ((size_t)1 << (nl == 0 ? 19 : 18))) break;
+    seg_level[nl + 1] = sg;
+    m_level[nl + 1] = m_level[nl] / sg;
     nl++;
   }
-  const unsigned m_last = m_level[nl];
-  unsigned nbits = 0;
-  while ((1u << nbits) < m_last) nbits++;
-  const unsigned total_masks = 1 + nbits + nl;  // [P, bit_0 .. bit_{nbits-1}, T_1 .. T_nl]
-  auto slices_for = [](unsigned m) {
-    unsigned sl = (m + 511) / 512;
-    return sl > 128 ? 128u : (sl < 1 ? 1u : sl);
-  };
-  unsigned slices = slices_for(m_last);
-  for (int l = 1; l <= nl; l++) slices = slices_for(m_level[l]) > slices ? slices_for(m_level[l]) : slices;
-  size_t slab = 0;  // R_l and t_l arrays, l = 1..nl
-  for (int l = 1; l <= nl; l++) slab += 2 * (size_t)nsets_total * m_level[l];
-  slab += (size_t)nsets_total * total_masks * slices;  // stage A partial sums
-  TP_TRY(ensure(ctx, ctx->msm_seg, (slab ? slab : 1) * sizeof(G1Xyzz)));
+  const unsigned m_rc = m_level[nl];   // length of the array the row / column sums run over
+  unsigned log_m = 0;
+  while ((1u << log_m) < m_rc) log_m++;
+  const unsigned bC = (log_m + 1) / 2, bD = log_m - bC;
+  const unsigned cols = 1u << bC, rows = 1u << bD;
+  const unsigned total_masks = 1 + bD + bC + (unsigned)nl;   // [P, bits of D, bits of C, T_1 .. T_nl]
+  // the t array of level l (m_level[l] entries per set) only needs its plain sum: first per run of tcount[l] entries
+  unsigned tcount[WSUM_MAX_LEVELS + 1], tjobs[WSUM_MAX_LEVELS + 1];
+  size_t slab = (size_t)nsets_total * (rows + cols);
+  for (int l = 1; l <= nl; l++) {
+    tcount[l] = m_level[l] > 256 ? 256u : m_level[l];
+    tjobs[l] = m_level[l] / tcount[l];
+    slab += 2 * (size_t)nsets_total * m_level[l] + (size_t)nsets_total * tjobs[l];
+  }
+  TP_TRY(ensure(ctx, ctx->msm_seg, slab * sizeof(G1Xyzz)));
   TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)nsets_total * total_masks * sizeof(G1Xyzz)));
   if ((size_t)nsets_total * total_masks * sizeof(G1Xyzz) > ctx->pinned_cap)
     return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
@@ -1285,11 +1290,9 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     G1Xyzz* cursor = (G1Xyzz*)ctx->msm_seg.p;
     const G1Xyzz* cur_in = buckets;
     const unsigned* cur_hist = hist;
-    MsmSumTasks tasks;
-    memset(&tasks, 0, sizeof(tasks));
     const G1Xyzz* t_arr[WSUM_MAX_LEVELS + 1] = {nullptr};
     for (int l = 1; l <= nl; l++) {
-      unsigned total_out = nsets_total * m_level[l];
+      const unsigned total_out = nsets_total * m_level[l];
       G1Xyzz* r_out = cursor;
       G1Xyzz* t_out = cursor + total_out;
       cursor += 2 * (size_t)total_out;
@@ -1300,34 +1303,46 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
       cur_hist = nullptr;
       t_arr[l] = t_out;
     }
-    tasks.ntasks = 1 + nl;
-    tasks.in[0] = cur_in;
-    tasks.hist[0] = cur_hist;
-    tasks.m[0] = m_last;
-    tasks.slices[0] = slices_for(m_last);
-    tasks.mask_base[0] = 0;
-    tasks.mask_base[1] = 1 + nbits;
+    G1Xyzz* D = cursor;
+    G1Xyzz* C = D + (size_t)nsets_total * rows;
+    cursor = C + (size_t)nsets_total * cols;
+    G1Xyzz* TPs[WSUM_MAX_LEVELS + 1] = {nullptr};
     for (int l = 1; l <= nl; l++) {
-      tasks.in[l] = t_arr[l];
-      tasks.hist[l] = nullptr;
-      tasks.m[l] = m_level[l];
-      tasks.slices[l] = slices_for(m_level[l]);
-      tasks.mask_base[l + 1] = tasks.mask_base[l] + 1;
+      TPs[l] = cursor;
+      cursor += (size_t)nsets_total * tjobs[l];
     }
-    G1Xyzz* part = cursor;
+    auto add_task = [](TreeTasks& tt, const G1Xyzz* src, const unsigned* h, G1Xyzz* dst, size_t set_stride, unsigned dst_set_stride,
+                       unsigned njobs, unsigned job_stride, unsigned count, unsigned stride, int bit) {
+      TreeTask& k = tt.t[tt.ntasks];
+      k.src = src; k.hist = h; k.dst = dst; k.set_stride = set_stride; k.dst_set_stride = dst_set_stride;
+      k.njobs = njobs; k.job_stride = job_stride; k.count = count; k.stride = stride; k.bit = bit;
+      tt.first[tt.ntasks + 1] = tt.first[tt.ntasks] + njobs;
+      tt.ntasks++;
+    };
+    // stage A: row sums, column sums, partial sums of every level's t array
+    TreeTasks ta;
+    memset(&ta, 0, sizeof(ta));
+    add_task(ta, cur_in, cur_hist, D, m_rc, rows, rows, cols, cols, 1, -1);
+    add_task(ta, cur_in, cur_hist, C, m_rc, cols, cols, 1, rows, cols, -1);
+    for (int l = 1; l <= nl; l++) add_task(ta, t_arr[l], nullptr, TPs[l], m_level[l], tjobs[l], tjobs[l], tcount[l], tcount[l], 1, -1);
+    k_msm_treesum<<<dim3(ta.first[ta.ntasks], nsets_total), TS_THREADS, 0, ctx->stream>>>(ta);
+    TP_LAUNCH(ctx, "k_msm_treesum");
+    // stage B: one slot each -- P, the bit sums of D and of C, the totals of the t arrays.  The bit sums are single jobs
+
     G1Xyzz* fin = (G1Xyzz*)ctx->msm_winsums.p;
-    k_msm_masked_sum<<<dim3(slices, total_masks, nsets_total), SUM_THREADS, 0, ctx->stream>>>(tasks, slices > 1 ? part : fin);
-    TP_LAUNCH(ctx, "k_msm_masked_sum");
-    if (slices > 1) {
-      MsmSumTasks fold;
-      memset(&fold, 0, sizeof(fold));
-      fold.ntasks = 1;
-      fold.in[0] = part;
-      fold.m[0] = slices;
-      fold.slices[0] = 1;
-      fold.mask_base[1] = 1;
-      k_msm_masked_sum<<<dim3(1, 1, nsets_total * total_masks), SUM_THREADS, 0, ctx->stream>>>(fold, fin);
-      TP_LAUNCH(ctx, "k_msm_masked_sum");
+    struct Slot { const G1Xyzz* src; size_t set_stride; unsigned count; int bit; };
+    std::vector<Slot> slots;
+    slots.push_back({D, rows, rows, -1});
+    for (unsigned k = 0; k < bD; k++) slots.push_back({D, rows, rows, (int)k});
+    for (unsigned k = 0; k < bC; k++) slots.push_back({C, cols, cols, (int)k});
+    for (int l = 1; l <= nl; l++) slots.push_back({TPs[l], tjobs[l], tjobs[l], -1});
+    for (size_t s0 = 0; s0 < slots.size(); s0 += TS_MAX_TASKS) {
+      TreeTasks tb;
+      memset(&tb, 0, sizeof(tb));
+      for (size_t q = s0; q < slots.size() && q < s0 + TS_MAX_TASKS; q++)
+        add_task(tb, slots[q].src, nullptr, fin + q, slots[q].set_stride, total_masks, 1, 0, slots[q].count, 1, slots[q].bit);
+      k_msm_treesum<<<dim3(tb.first[tb.ntasks], nsets_total), TS_THREADS, 0, ctx->stream>>>(tb);
+      TP_LAUNCH(ctx, "k_msm_treesum");
     }
   }
   // Sharded: the ranks' reduction outputs meet on the device -- all-gather on the stream, one combine kernel -- and the
@@ -1370,14 +1385,22 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
       if (q != (int)pl.nsets - 1)
         for (unsigned d = 0; d < pl.c * pl.levels; d++) acc = tph::g1_dbl(acc);
       unsigned set = (unsigned)b * pl.nsets + (unsigned)q;
-      tph::HG1 f = tph::HG1::identity();  // F(R) = sum_k 2^k bit_k
-      for (int k = (int)nbits - 1; k >= 0; k--) {
-        f = tph::g1_dbl(f);
-        f = tph::g1_add(f, point(set, 1 + (unsigned)k));
-      }
+      // F(X) = F(C) + cols * F(D), each from its bit sums (Horner from the top bit); X = the R array of the last
+      // running-sum level, unwound level by level
+      auto bits = [&](unsigned first_slot, unsigned nb) {
+        tph::HG1 v = tph::HG1::identity();
+        for (int k = (int)nb - 1; k >= 0; k--) {
+          v = tph::g1_dbl(v);
+          v = tph::g1_add(v, point(set, first_slot + (unsigned)k));
+        }
+        return v;
+      };
+      tph::HG1 f = bits(1, bD);
+      for (unsigned d = 0; d < bC; d++) f = tph::g1_dbl(f);
+      f = tph::g1_add(f, bits(1 + bD, bC));
       for (int l = nl; l >= 1; l--) {  // F(level l-1) = T_l + S_l * F(level l)
         for (unsigned d = 1; d < seg_level[l]; d <<= 1) f = tph::g1_dbl(f);
-        f = tph::g1_add(f, point(set, 1 + nbits + (unsigned)(l - 1)));
+        f = tph::g1_add(f, point(set, 1 + bD + bC + (unsigned)(l - 1)));
       }
       if (world == 1) {
         f = tph::g1_add(f, raw_point((size_t)set * width));   // V = F + P
