@@ -111,7 +111,7 @@ int tp_ctx_destroy(tp_ctx* ctx) {
   }
   DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_sorted,
                     &ctx->msm_sorted_keys, &ctx->msm_hist, &ctx->msm_offsets, &ctx->msm_blocksums, &ctx->msm_buckets,
-                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_gather, &ctx->msm_aff_pts,
+                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_gather, &ctx->msm_compact, &ctx->msm_aff_pts,
                     &ctx->msm_sorted2, &ctx->msm_aff_cnt, &ctx->msm_aff_plan, &ctx->msm_aff_rec, &ctx->flag};
   for (auto* b : bufs) release(*b);
   for (auto& b : ctx->scan_tmp) release(b);
@@ -725,8 +725,28 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     c->pi_buffers_zero = false;
   }
   // witness + public-input polynomials (proof.rs:50, 105-106)
+  static const bool no_intt_shard = getenv("TP_NO_INTT_SHARD") && *getenv("TP_NO_INTT_SHARD") == '1';
   if (col_ready) {
     if (!pi_zero) TP_TRY(ntt_dev(ctx, c->pi_eval, c->pi_coef, c->log_n, true, nullptr));
+  } else if (comm_ready(ctx) && !no_intt_shard && n >= 4096) {
+    // sharded context: the interpolations are split by column (column j on rank j mod world) and the coefficient
+    // vectors exchanged with one group of device broadcasts -- 32 n bytes over NVLink cost less than an inverse NTT
+    const Fr* evs[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
+    Fr* cfs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
+    const int ncol = pi_zero ? 3 : 4;
+    const Fr* ins[4];
+    Fr* outs[4];
+    int cnt = 0;
+    for (int j = 0; j < ncol; j++)
+      if (j % ctx->world == ctx->rank) {
+        ins[cnt] = evs[j];
+        outs[cnt] = cfs[j];
+        cnt++;
+      }
+    TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, cnt, c->log_n, true));
+    TP_TRY(comm_group_begin(ctx));
+    for (int j = 0; j < ncol; j++) TP_TRY(comm_bcast(ctx, cfs[j], n * sizeof(Fr), j % ctx->world));
+    TP_TRY(comm_group_end(ctx));
   } else {
     const Fr* ins[4] = {c->adv_eval[0], c->adv_eval[1], c->adv_eval[2], c->pi_eval};
     Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};

@@ -74,7 +74,7 @@ struct tp_ctx {
   // scratch
   tp::DevBuf ntt_scratch;
   tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_sorted, msm_sorted_keys, msm_hist, msm_offsets, msm_blocksums,
-      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_gather, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
+      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_gather, msm_compact, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
   tp::DevBuf scan_tmp[8];
   tp::DevBuf misc[16];
   tp::DevBuf flag;

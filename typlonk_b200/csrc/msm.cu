@@ -177,6 +177,95 @@ __global__ void k_msm_digits(MsmScalarSets sets, size_t n, unsigned c, unsigned 
   }
 }
 
+// ---- 1b. digits of a sharded MSM ----------------------------------------------------------------
+// Rank r of `world` owns the buckets b with b % world == r.  Every rank walks ALL scalars (digit extraction is cheap)
+// but only about 1 / world of the digits are its own: writing a window-major key array for all of them and reading it
+// back in the scatter would cost every rank the memory traffic of an unsharded MSM.  Instead the owned entries go to a
+// COMPACT list -- (bucket key | sign, rank inside the bucket, table index) -- in blocks: a thread first computes its
+// digits and takes their histogram slots, the block sums its threads' counts and reserves its share of the list with one
+// atomicAdd, and the threads write their entries there.  The scatter then runs over the compact list only.
+struct MsmEntry {
+  unsigned key, rank, idx;
+};
+#define MSM_MAX_WIN 128   // windows_for(2) = 128
+__global__ void __launch_bounds__(256) k_msm_digits_sharded(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
+                                                            unsigned levels, unsigned nsets, unsigned world, unsigned my_rank,
+                                                            unsigned stride, unsigned* __restrict__ hist,
+                                                            unsigned* __restrict__ list_count, MsmEntry* __restrict__ list) {
+  __shared__ unsigned warp_tot[8];
+  __shared__ unsigned block_base;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned sbase = blockIdx.y * nsets;
+  Fr s;
+  if (i < n) s = fr_from_mont(fr_load(sets.p[blockIdx.y] + i));
+  // pass 1: count (the digits are recomputed in pass 2: cheaper than keeping up to 128 of them)
+  auto walk = [&](auto&& emit) {
+    unsigned carry = 0;
+    for (unsigned w = 0; w < nwin; w++) {
+      unsigned bit = w * c;
+      unsigned raw = 0;
+      if (bit < 256) {
+        unsigned limb = bit >> 5, off = bit & 31;
+        unsigned long long two = s.v[limb];
+        if (limb + 1 < 8) two |= (unsigned long long)s.v[limb + 1] << 32;
+        raw = (unsigned)(two >> off) & ((1u << c) - 1);
+      }
+      raw += carry;
+      carry = 0;
+      if (raw == 0) continue;
+      unsigned mag = raw, neg = 0;
+      if (raw > (1u << (c - 1))) {
+        mag = (1u << c) - raw;
+        neg = 1;
+        carry = 1;
+      }
+      if (mag == 0) continue;
+      const unsigned b = mag - 1;
+      if (b % world != my_rank) continue;
+      emit(w, (sbase + w / levels) * nbuck + b / world, neg);
+    }
+  };
+  unsigned mine = 0;
+  if (i < n) walk([&](unsigned, unsigned, unsigned) { mine++; });
+  // block-wide exclusive prefix of `mine`
+  const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned incl = mine;
+  for (unsigned d = 1; d < 32; d <<= 1) {
+    unsigned v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned run = 0;
+    for (unsigned k = 0; k < blockDim.x / 32; k++) {
+      unsigned v = warp_tot[k];
+      warp_tot[k] = run;
+      run += v;
+    }
+    block_base = run ? atomicAdd(list_count, run) : 0;
+  }
+  __syncthreads();
+  unsigned pos = block_base + warp_tot[wid] + incl - mine;
+  if (i < n)
+    walk([&](unsigned w, unsigned k, unsigned neg) {
+      MsmEntry e;
+      e.key = k | (neg << 31);
+      e.rank = atomicAdd(&hist[k], 1u);
+      e.idx = (w % levels) * stride + (unsigned)i;   // level (w % levels) of the fixed-base table holds 2^(c (w % levels)) * P_i
+      list[pos++] = e;
+    });
+}
+__global__ void __launch_bounds__(256) k_msm_scatter_compact(const MsmEntry* __restrict__ list, const unsigned* __restrict__ count_ptr,
+                                                             const unsigned* __restrict__ offsets, uint2* __restrict__ sorted) {
+  const unsigned count = *count_ptr;
+  for (unsigned e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const MsmEntry en = list[e];
+    const unsigned k = en.key & MSM_NONE;
+    sorted[offsets[k] + en.rank] = make_uint2(en.idx | (en.key & 0x80000000u), k);
+  }
+}
+
 // ---- 2. exclusive scan (3 kernels; T = u32, or u64 carrying two packed u32 counters) -------------
 #define SCAN_BLOCK 1024
 template <typename T>
@@ -1033,40 +1122,55 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     MsmScalarSets sets;
     for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < batch ? b : 0];
     dim3 grid((unsigned)((len + 255) / 256), (unsigned)batch);
-    k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, world,
-                                                (unsigned)ctx->rank, hist, keys, ranks);
-    TP_LAUNCH(ctx, "k_msm_digits");
-    TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
-    {
-      // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
-      // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
-      // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
-      // is several L2s long gains little (2^24: 9.9 -> 9.4 ms with four).  TP_MSM_SCATTER_SLICES forces a count.
-      static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
-      static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
-      unsigned log_slices = 0;
-      if (env_slices) {
-        while ((2u << log_slices) <= env_slices) log_slices++;
-      } else {
-        const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
-        if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
-        else if (per_msm > window) log_slices = 1;
-      }
-      unsigned log_nbuck = 0;
-      while ((1u << log_nbuck) < pl.nbuck) log_nbuck++;
-      if (world > 1) {   // a rank scatters 1 / world of the list: fewer slices bring it inside the L2
-        unsigned lw = 0;
-        while ((2u << lw) <= world) lw++;
-        log_slices = log_slices > lw ? log_slices - lw : 0;
-      }
-      if (log_slices > log_nbuck) log_slices = log_nbuck;
-      const unsigned slice_shift = log_nbuck - log_slices;
-      const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
-      for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
-        k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
-                                                                                 pl.levels, (unsigned)srs->len, sorted,
-                                                                                 pl.nbuck - 1, slice_shift, sl);
-        TP_LAUNCH(ctx, "k_msm_scatter");
+    static const bool no_compact = env_uint("TP_MSM_NO_COMPACT", 0) != 0;
+    if (world > 1 && !no_compact) {
+      // sharded: owned entries into a compact list, scatter over that list (see 1b)
+      TP_TRY(ensure(ctx, ctx->msm_compact, total * sizeof(MsmEntry) + 16));
+      unsigned* list_count = (unsigned*)ctx->msm_compact.p;
+      MsmEntry* list = (MsmEntry*)((char*)ctx->msm_compact.p + 16);
+      TP_CUDA_OK(ctx, cudaMemsetAsync(list_count, 0, sizeof(unsigned), ctx->stream));
+      k_msm_digits_sharded<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, world,
+                                                          (unsigned)ctx->rank, (unsigned)srs->len, hist, list_count, list);
+      TP_LAUNCH(ctx, "k_msm_digits_sharded");
+      TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
+      k_msm_scatter_compact<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(list, list_count, offsets, sorted);
+      TP_LAUNCH(ctx, "k_msm_scatter_compact");
+    } else {
+      k_msm_digits<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, world,
+                                                  (unsigned)ctx->rank, hist, keys, ranks);
+      TP_LAUNCH(ctx, "k_msm_digits");
+      TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
+      {
+        // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
+        // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
+        // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
+        // is several L2s long gains little (2^24: 9.9 -> 9.4 ms with four).  TP_MSM_SCATTER_SLICES forces a count.
+        static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
+        static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
+        unsigned log_slices = 0;
+        if (env_slices) {
+          while ((2u << log_slices) <= env_slices) log_slices++;
+        } else {
+          const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
+          if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
+          else if (per_msm > window) log_slices = 1;
+        }
+        unsigned log_nbuck = 0;
+        while ((1u << log_nbuck) < pl.nbuck) log_nbuck++;
+        if (world > 1) {   // a rank scatters 1 / world of the list: fewer slices bring it inside the L2
+          unsigned lw = 0;
+          while ((2u << lw) <= world) lw++;
+          log_slices = log_slices > lw ? log_slices - lw : 0;
+        }
+        if (log_slices > log_nbuck) log_slices = log_nbuck;
+        const unsigned slice_shift = log_nbuck - log_slices;
+        const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
+        for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
+          k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
+                                                                                   pl.levels, (unsigned)srs->len, sorted,
+                                                                                   pl.nbuck - 1, slice_shift, sl);
+          TP_LAUNCH(ctx, "k_msm_scatter");
+        }
       }
     }
     TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
