@@ -118,3 +118,20 @@ def test_group_refuses_device_pointer_entry_points(ctx):
     with pytest.raises(TyplonkError):
         group.ntt_dev(0x1000, 4)
     group.close()
+
+
+def test_comm_init_rank_argument_checks():
+    """One process per GPU: world = 1 needs no communicator; world > 1 needs rank 0's id; a device group owns its own."""
+    from typlonk_b200.ffi import Context, TyplonkError
+    c = Context(0)
+    c.comm_init_rank(0, 1)
+    assert c.group_size() == (1, False)
+    with pytest.raises(TyplonkError):
+        c.comm_init_rank(0, 2, None)
+    with pytest.raises(TyplonkError):
+        c.comm_init_rank(2, 2, bytes(128))
+    c.close()
+    g = Context.multi([0, 0])
+    with pytest.raises(TyplonkError):
+        g.comm_init_rank(0, 1)
+    g.close()

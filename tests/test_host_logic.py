@@ -100,6 +100,31 @@ def test_no_cpu_fallback():
             ffi.Context(0)
 
 
+def test_multi_gpu_entry_points_validate_their_arguments():
+    """tp_ctx_create_multi / tp_ctx_comm_init_rank / tp_comm_unique_id / tp_ctx_group_size without a device: bad
+    arguments are refused, and a device group fails like a single context does (no CPU fallback)."""
+    import ctypes as C
+    L = ffi.lib()
+    h = C.c_void_p()
+    assert L.tp_ctx_create_multi(None, 2, C.byref(h)) == 1                      # TP_ERR_INVALID_ARG
+    devs = (C.c_int * 2)(0, 0)
+    assert L.tp_ctx_create_multi(devs, 0, C.byref(h)) == 1
+    assert L.tp_ctx_create_multi(devs, 17, C.byref(h)) == 1                     # more than TP_MAX_GROUP
+    assert L.tp_ctx_create_multi(devs, 2, None) == 1
+    assert L.tp_ctx_group_size(None, None, None) == 1
+    assert L.tp_ctx_comm_init_rank(None, 0, 1, None) == 1
+    assert L.tp_comm_unique_id(None) == 1
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        has_gpu = False
+    if not has_gpu:
+        assert L.tp_ctx_create_multi(devs, 2, C.byref(h)) == 7                  # TP_ERR_NO_DEVICE
+        with pytest.raises(ffi.TyplonkError):
+            ffi.Context.multi([0, 0])
+
+
 def test_product_package_does_not_import_the_oracle():
     pkg = os.path.join(ROOT, "typlonk_b200")
     for dirpath, _, files in os.walk(pkg):

@@ -699,10 +699,55 @@ static int coset_owner(const tp_ctx* ctx, bool shard, unsigned first, unsigned k
 static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const cudaEvent_t* col_ready = nullptr) {
   const size_t n = c->n;
   const tp_srs* srs = c->srs;
+  // Quotient cosets of a, b, c on the side stream, under the round-1 MSMs.  Which cosets this rank owns depends on
+  // whether coset 0 will be skipped (known only after the grand product): the honest case is assumed here and the
+  // rest, if any, is done later.
+  static const bool no_coset_shard = getenv("TP_NO_COSET_SHARD") && *getenv("TP_NO_COSET_SHARD") == '1';
+  static const bool no_side_stream = getenv("TP_NO_SIDE_STREAM") && *getenv("TP_NO_SIDE_STREAM") == '1';
+  const bool shard = comm_ready(ctx) && !no_coset_shard;
+  HFr gens[4];
+  for (unsigned k = 0; k < 4; k++) gens[k] = omega_for_log(c->log_n + 2).pow_u64(k);
+  bool have[4][4] = {{false}};   // have[poly][coset]: evaluations of poly (a, b, c, z) on coset k are in buf4[poly]
+  auto queue_cosets = [&](int poly_lo, int poly_hi, unsigned first) -> int {
+    const Fr* src[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef};
+    const Fr* ins[16];
+    Fr* outs[16];
+    const uint64_t* cos[16];
+    int cnt = 0;
+    for (unsigned k = first; k < 4; k++) {
+      if (coset_owner(ctx, shard, first, k) != ctx->rank) continue;
+      for (int i = poly_lo; i < poly_hi; i++) {
+        if (have[i][k]) continue;
+        have[i][k] = true;
+        ins[cnt] = src[i];
+        outs[cnt] = c->buf4[i] + (size_t)k * n;
+        cos[cnt] = k == 0 ? nullptr : gens[k].v;
+        cnt++;
+      }
+    }
+    return ntt_batch_dev(ctx, ins, outs, cos, cnt, c->log_n, false);
+  };
+  const bool side = !no_side_stream;
+  if (side) TP_TRY(side_stream_init(ctx));
+  const unsigned first_guess = ctx->quotient_all_cosets ? 0u : 1u;
+  // polynomials poly_lo .. poly_hi - 1 exist on the main stream: their quotient cosets go to the side stream
+  auto side_cosets = [&](int poly_lo, int poly_hi, unsigned first, int ev) -> int {
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[ev], ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[ev], 0));
+    {
+      StreamSwap sw(ctx, ctx->side_stream);
+      TP_TRY(queue_cosets(poly_lo, poly_hi, first));
+    }
+    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[ev + 1], ctx->side_stream));
+    return TP_OK;
+  };
   if (col_ready) {
+    // host buffers, one GPU: column k is interpolated as soon as its upload has landed, and its quotient cosets are
+    // evaluated on the side stream while the next column is still crossing PCIe
     for (int k = 0; k < 3; k++) {
       TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, col_ready[k], 0));
       TP_TRY(ntt_dev(ctx, c->adv_eval[k], c->adv_coef[k], c->log_n, true, nullptr));
+      if (side) TP_TRY(side_cosets(k, k + 1, first_guess, 0));
     }
   }
   // gate equation on every row (the reference asserts it via vanishes(line1), proof.rs:317-321) -- first, because it
@@ -752,45 +797,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     Fr* outs[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->pi_coef};
     TP_TRY(ntt_batch_dev(ctx, ins, outs, nullptr, pi_zero ? 3 : 4, c->log_n, true));
   }
-  // Quotient cosets of a, b, c on the side stream, under the round-1 MSMs.  Which cosets this rank owns depends on
-  // whether coset 0 will be skipped (known only after the grand product): the honest case is assumed here and the
-  // rest, if any, is done later.
-  static const bool no_coset_shard = getenv("TP_NO_COSET_SHARD") && *getenv("TP_NO_COSET_SHARD") == '1';
-  static const bool no_side_stream = getenv("TP_NO_SIDE_STREAM") && *getenv("TP_NO_SIDE_STREAM") == '1';
-  const bool shard = comm_ready(ctx) && !no_coset_shard;
-  HFr gens[4];
-  for (unsigned k = 0; k < 4; k++) gens[k] = omega_for_log(c->log_n + 2).pow_u64(k);
-  bool have[4][4] = {{false}};   // have[poly][coset]: evaluations of poly (a, b, c, z) on coset k are in buf4[poly]
-  auto queue_cosets = [&](int poly_lo, int poly_hi, unsigned first) -> int {
-    const Fr* src[4] = {c->adv_coef[0], c->adv_coef[1], c->adv_coef[2], c->z_coef};
-    const Fr* ins[16];
-    Fr* outs[16];
-    const uint64_t* cos[16];
-    int cnt = 0;
-    for (unsigned k = first; k < 4; k++) {
-      if (coset_owner(ctx, shard, first, k) != ctx->rank) continue;
-      for (int i = poly_lo; i < poly_hi; i++) {
-        if (have[i][k]) continue;
-        have[i][k] = true;
-        ins[cnt] = src[i];
-        outs[cnt] = c->buf4[i] + (size_t)k * n;
-        cos[cnt] = k == 0 ? nullptr : gens[k].v;
-        cnt++;
-      }
-    }
-    return ntt_batch_dev(ctx, ins, outs, cos, cnt, c->log_n, false);
-  };
-  const bool side = !no_side_stream;
-  if (side) {
-    TP_TRY(side_stream_init(ctx));
-    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[0], ctx->stream));
-    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
-    {
-      StreamSwap sw(ctx, ctx->side_stream);
-      TP_TRY(queue_cosets(0, 3, ctx->quotient_all_cosets ? 0u : 1u));
-    }
-    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
-  }
+  if (side) TP_TRY(side_cosets(0, 3, first_guess, 0));   // whatever the per-column path above has not queued yet
   // round 1 commitments (proof.rs:107-110)
   uint8_t com[4][TP_G1_BYTES];
   {
@@ -810,15 +817,7 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
   TP_TRY(ntt_dev(ctx, c->z_eval, c->z_coef, c->log_n, true, nullptr));
   const bool skip0 = z_closes && !ctx->quotient_all_cosets;
   const unsigned first = skip0 ? 1u : 0u;
-  if (side) {
-    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[2], ctx->stream));
-    TP_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[2], 0));
-    {
-      StreamSwap sw(ctx, ctx->side_stream);
-      TP_TRY(queue_cosets(0, 4, first));   // z on this rank's cosets; a, b, c only where the guess above missed
-    }
-    TP_CUDA_OK(ctx, cudaEventRecord(ctx->side_ev[3], ctx->side_stream));
-  }
+  if (side) TP_TRY(side_cosets(0, 4, first, 2));   // z on this rank's cosets; a, b, c only where the guess above missed
   TP_TRY(msm_dev(ctx, srs, c->z_coef, n, com[3]));
   HFr alpha, zeta;
   tph::challenges2({com[0], com[1], com[2], com[3]}, &alpha, &zeta);
