@@ -463,15 +463,23 @@ def main():
             f_res()
             ctx.prof_reset()
             ctx.prof_enable(True)
-            ns_steps = 3
-            ms_ns, pr = timed(f_res, ns_steps)
+            ns_steps = 5
+            # every step timed on its own (barrier + events), so that a single stalled upload shows as an outlier in
+            # `*_per_step` instead of silently inflating the mean
+            res_ms, e2e_ms, pr, pr2 = [], [], None, None
+            for _ in range(ns_steps):
+                t_ms, pr = timed(f_res, 1)
+                res_ms.append(round(t_ms, 3))
             ns_prof = ctx.prof_get()
             ctx.prof_enable(False)
             f_e2e()
             f_e2e()   # two warm-ups: the first sharded upload of a new size also sets up its NCCL transfers
-            ms_ns_e2e, pr2 = timed(f_e2e, ns_steps)
+            for _ in range(ns_steps):
+                t_ms, pr2 = timed(f_e2e, 1)
+                e2e_ms.append(round(t_ms, 3))
             line["north_star"] = {"workload": "mulchain_prove_n=2^%d" % lg, "gates": (1 << lg) - 3, "n_gpus": world,
-                                  "prove_ms": round(ms_ns / ns_steps, 3), "e2e_ms": round(ms_ns_e2e / ns_steps, 3),
+                                  "prove_ms": round(sum(res_ms) / ns_steps, 3), "e2e_ms": round(sum(e2e_ms) / ns_steps, 3),
+                                  "prove_ms_per_step": res_ms, "e2e_ms_per_step": e2e_ms,
                                   "steps": ns_steps, "warmup": 2, "parity": _parity(pr, lg), "e2e_same_bytes": pr == pr2,
                                   "phases_ms_per_step": {p: round(ns_prof[p][0] / ns_steps, 3) for p in PHASES},
                                   "setup_s": round(bsetup, 1)}
