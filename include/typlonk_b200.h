@@ -220,6 +220,15 @@ int tp_prove_dev(tp_ctx* ctx, tp_circuit* c, const void* const advice_dev[3], co
 int tp_prove_inputs(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3], const uint64_t* public_inputs,
                     size_t n_public, uint8_t* proof_out, size_t proof_cap);
 
+/* Inspection: an intermediate polynomial of the LAST proof made with `c`, read from the prover's device buffers
+ * (Montgomery Fr): the quotient t as 3n coefficients (quotient_polynomial, proof.rs:292-375; slices t0 | t1 | t2), the
+ * linearisation polynomial r (proof.rs:376-439; n coefficients), the grand product as its n + 1 evaluations
+ * (CompiledPermutation::prove, permutation/src/proving.rs:7-31) and as coefficients, the witness polynomials.  With
+ * out == NULL only *count is written.  Lets tests compare every stage with the reference's own function, not only
+ * the final bytes. */
+enum { TP_POLY_QUOTIENT = 0, TP_POLY_LINEARISATION = 1, TP_POLY_Z_EVALS = 2, TP_POLY_Z = 3, TP_POLY_A = 4, TP_POLY_B = 5, TP_POLY_C = 6 };
+int tp_circuit_read_poly(tp_ctx* ctx, tp_circuit* c, int which, uint64_t* out, size_t cap_elems, size_t* count);
+
 /* verify() (proof.rs:195-233, 441-503): `proof` is the TP_PROOF_FIXED_BYTES block tp_prove writes, `public_inputs`
  * the proof's public-input vector (n_public Montgomery Fr; resized to n like proof.rs:204-205).  The device
  * interpolates and evaluates the public-input polynomial, evaluates sigma_1..3 at the challenge point and (first call

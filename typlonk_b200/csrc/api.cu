@@ -1044,6 +1044,30 @@ int tp_prove_inputs(tp_ctx* ctx, tp_circuit* c, const uint64_t* const advice[3],
   return prove_from_host(ctx, c, advice, public_inputs, n_public, proof_out, proof_cap);
 }
 
+// Intermediate polynomials of the LAST proof of this circuit, straight from the prover's device buffers: the parity
+// tests compare them one by one with the reference's own functions (quotient_polynomial, linearisation_poly,
+// CompiledPermutation::prove), not only through the final proof bytes.
+int tp_circuit_read_poly(tp_ctx* ctx, tp_circuit* c, int which, uint64_t* out, size_t cap_elems, size_t* count) {
+  if (!ctx) return TP_ERR_INVALID_ARG;
+  if (!c || !count) return fail(ctx, TP_ERR_INVALID_ARG, "read_poly: null argument");
+  if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* cc) { return tp_circuit_read_poly(cc, c->parts[0], which, out, cap_elems, count); });
+  const size_t n = c->n;
+  const Fr* src = nullptr;
+  size_t len = 0;
+  switch (which) {
+    case TP_POLY_QUOTIENT: src = c->t; len = 3 * n; break;
+    case TP_POLY_LINEARISATION: src = c->r; len = n; break;
+    case TP_POLY_Z_EVALS: src = c->z_eval; len = n + 1; break;
+    case TP_POLY_Z: src = c->z_coef; len = n; break;
+    case TP_POLY_A: case TP_POLY_B: case TP_POLY_C: src = c->adv_coef[which - TP_POLY_A]; len = n; break;
+    default: return fail(ctx, TP_ERR_INVALID_ARG, "read_poly: unknown polynomial id");
+  }
+  *count = len;
+  if (!out) return TP_OK;
+  if (cap_elems < len) return fail(ctx, TP_ERR_BUFFER_TOO_SMALL, "read_poly: output buffer too small");
+  return d2h_sync(ctx, out, src, len * sizeof(Fr));
+}
+
 // ---- helpers -------------------------------------------------------------------------------------
 int tp_measure_imad_peak(tp_ctx* ctx, double* imad_per_s, double* imad_wide_per_s) {
   if (is_group(ctx)) return on_rank0(ctx, [&](tp_ctx* c) { return tp_measure_imad_peak(c, imad_per_s, imad_wide_per_s); });

@@ -38,7 +38,7 @@ SYMBOLS = [
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
     "tp_permutation_compile", "tp_fr_from_i64", "tp_fr_from_canonical", "tp_fr_to_canonical",
     "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
-    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp", "tp_stdrng_words",
+    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp", "tp_stdrng_words", "tp_circuit_read_poly",
 ]
 
 COMM_ID_BYTES = 128
@@ -596,6 +596,16 @@ class CircuitHandle:
                                         _buf(public_inputs_mont) if public_inputs_mont else None,
                                         C.c_size_t(len(public_inputs_mont) // 32), C.byref(ok)))
         return bool(ok.value)
+
+    POLY_QUOTIENT, POLY_LINEARISATION, POLY_Z_EVALS, POLY_Z, POLY_A, POLY_B, POLY_C = range(7)
+
+    def read_poly(self, which: int) -> bytes:
+        """tp_circuit_read_poly: an intermediate polynomial of the last proof (Montgomery bytes)."""
+        cnt = C.c_size_t(0)
+        self.ctx._check(lib().tp_circuit_read_poly(self.ctx._h, self._h, C.c_int(which), None, C.c_size_t(0), C.byref(cnt)))
+        out = (C.c_char * (32 * cnt.value))()
+        self.ctx._check(lib().tp_circuit_read_poly(self.ctx._h, self._h, C.c_int(which), out, C.c_size_t(cnt.value), C.byref(cnt)))
+        return bytes(out)
 
     def sigma_commitments(self):
         out = (C.c_char * (3 * G1_BYTES))()
