@@ -340,6 +340,9 @@ int tp_proof_encode(const uint8_t* fixed, const uint64_t* public_inputs, size_t 
  * `public_inputs_out` (Montgomery, capacity cap_public elements) and `fixed_out` may be NULL. */
 int tp_proof_decode(const uint8_t* bytes, size_t len, uint8_t fixed_out[TP_PROOF_FIXED_BYTES],
                     uint64_t* public_inputs_out, size_t cap_public, size_t* n_public);
+/* The prime-order subgroup check ark-serialize's checked deserialisation adds on top of tp_proof_decode's "on the
+ * curve": *ok = 1 iff [r]P = 0 for all 13 points of the fixed block (host only; a malformed point -> TP_ERR_MALFORMED). */
+int tp_proof_points_in_subgroup(const uint8_t* fixed, size_t len, int* ok);
 /* Srs (kzg/src/srs.rs:8-14) = Vec<G1> | G2 | tau G2.  The device converts the points out of /
  * into Montgomery form and validates them, one point per thread.  check: 0 = canonical
  * encoding only (ark `deserialize_unchecked`), 1 = + on the curve, 2 = + in the prime-order

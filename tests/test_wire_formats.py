@@ -80,6 +80,26 @@ def test_proof_decode_rejects_malformed():
             ffi.proof_challenges(bytes(bad[:1472]))
 
 
+def test_proof_points_subgroup_check():
+    """tp_proof_points_in_subgroup: golden proofs pass; a point that is on the curve but outside the prime-order
+    subgroup (cofactor component) passes tp_proof_decode's curve check and is caught here."""
+    raw = _golden()
+    assert ffi.proof_points_in_subgroup(bytes(raw[:1472]))
+    # a curve point of the full group: x = small, y = sqrt(x^3 + 4); almost surely not in the r-torsion
+    q = fields.Q_MOD
+    x = 1
+    while True:
+        rhs = (x * x * x + 4) % q
+        y = pow(rhs, (q + 1) // 4, q)
+        if y * y % q == rhs:      # on the curve; inside the subgroup only with probability 1 / cofactor ~ 2^-126
+            break
+        x += 1
+    bad = bytearray(raw[:1472])
+    bad[0:96] = x.to_bytes(48, "little") + y.to_bytes(48, "little")
+    ffi.proof_decode(bytes(bad) + bytes(raw[1472:]))          # on the curve: decode accepts
+    assert not ffi.proof_points_in_subgroup(bytes(bad))
+
+
 def test_proof_encode_checks_its_arguments():
     raw = _golden()
     with pytest.raises(ffi.TyplonkError):

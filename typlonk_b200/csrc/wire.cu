@@ -244,6 +244,34 @@ int tp_proof_encode(const uint8_t* fixed, const uint64_t* public_inputs, size_t 
   return TP_OK;
 }
 
+// ark-serialize's CHECKED deserialisation also verifies [r]P = 0 for every point; tp_proof_decode stops at "on the
+// curve" (the reference's transcript uses the unchecked form).  This is the additional check, on the host: 13 scalar
+// multiplications by r.
+int tp_proof_points_in_subgroup(const uint8_t* fixed, size_t len, int* ok) {
+  if (!fixed || !ok || len < TP_PROOF_FIXED_BYTES) return TP_ERR_INVALID_ARG;
+  *ok = 0;
+  const uint8_t* p = fixed;
+  for (const char* k = kProofLayout; *k; k++) {
+    if (*k != 'G') {
+      p += 32;
+      continue;
+    }
+    if (!tp::g1_wire_valid(p)) return TP_ERR_MALFORMED;
+    uint8_t flags = 0;
+    G1Aff a;
+    a.inf = false;
+    tp::fq_from_wire(p, 0, &a.x, nullptr);
+    tp::fq_from_wire(p + 48, 0xc0, &a.y, &flags);
+    if (!(flags & 0x40)) {
+      HG1 m = g1_mul_u64limbs(g1_from_affine(a.x, a.y), FR_PARAMS.mod, 4);
+      if (!m.is_identity()) return TP_OK;   // *ok stays 0
+    }
+    p += TP_WIRE_G1_BYTES;
+  }
+  *ok = 1;
+  return TP_OK;
+}
+
 int tp_proof_decode(const uint8_t* bytes, size_t len, uint8_t fixed_out[TP_PROOF_FIXED_BYTES],
                     uint64_t* public_inputs_out, size_t cap_public, size_t* n_public) {
   if (!bytes || !n_public) return TP_ERR_INVALID_ARG;

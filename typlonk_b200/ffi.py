@@ -38,7 +38,7 @@ SYMBOLS = [
     "tp_permutation_builder_add_constrain", "tp_permutation_builder_build",
     "tp_permutation_compile", "tp_fr_from_i64", "tp_fr_from_canonical", "tp_fr_to_canonical",
     "tp_proof_encoded_size", "tp_proof_encode", "tp_proof_decode",
-    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp", "tp_stdrng_words", "tp_circuit_read_poly",
+    "tp_srs_serialized_size", "tp_srs_serialize", "tp_srs_deserialize", "tp_build_stamp", "tp_stdrng_words", "tp_circuit_read_poly", "tp_proof_points_in_subgroup",
 ]
 
 COMM_ID_BYTES = 128
@@ -180,6 +180,17 @@ def proof_decode(raw: bytes):
     if rc != 0:
         raise TyplonkError(rc, "tp_proof_decode")
     return bytes(fixed), bytes(pis)[: 32 * n.value]
+
+
+def proof_points_in_subgroup(fixed: bytes) -> bool:
+    """tp_proof_points_in_subgroup: [r]P = 0 for every G1 point of the proof (ark's checked deserialisation)."""
+    ok = C.c_int(0)
+    rc = lib().tp_proof_points_in_subgroup(_buf(fixed), C.c_size_t(len(fixed)), C.byref(ok))
+    if rc == 12:
+        raise Malformed(rc, "tp_proof_points_in_subgroup: malformed point")
+    if rc != 0:
+        raise TyplonkError(rc, "tp_proof_points_in_subgroup")
+    return bool(ok.value)
 
 
 GATE_MUL, GATE_ADD, GATE_DUMMY = 0, 1, 2
