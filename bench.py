@@ -235,6 +235,9 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the MSM / NTT size sweeps (N = 1)")
     ap.add_argument("--no-north-star", action="store_true", help="skip the 2^22-gate prove")
     ap.add_argument("--north-star-log-n", type=int, default=22)
+    ap.add_argument("--ab", action="append", default=[], metavar="OPT=VAL[,OPT=VAL]",
+                    help="also time the resident prove with these tp_ctx_set_option settings (repeatable); reported under "
+                         "'ab', never as the headline value")
     ap.add_argument("--dump-proof", default=None, help="write the proof bytes of the last timed step to this file (rank 0)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -257,7 +260,9 @@ def main():
 
     # a non-default torch stream: its handle is what the library launches on, so torch.cuda.Event
     # timings bracket the library's kernels (the legacy default stream has handle 0 = "make your own")
-    tstream = torch.cuda.Stream(device=dev)
+    # (priority -1: above the lowest-priority stream the library's MSM pipe accumulates on, so the scans and transforms
+    # the prover queues between two sub-batches are not stuck behind the accumulation's pending blocks)
+    tstream = torch.cuda.Stream(device=dev, priority=-1)
     torch.cuda.set_stream(tstream)
     ctx = Context(local_rank, tstream.cuda_stream)
 
@@ -362,6 +367,26 @@ def main():
     verify = {"first_call_ms": round(tv[0], 2), "ms": round(min(tv[1:]), 2), "accepted": True,
               "note": "first call includes the 8 circuit-commitment MSMs, cached afterwards"}
 
+    # library tunables A/B-ed in this very process (same box, same clocks, same circuit): each variant is warmed up,
+    # timed like the headline, byte-checked, and the defaults are restored
+    DEFAULTS = {"msm_pipeline": 1, "msm_acc_staged": 0, "msm_reduce_l1": 0, "quotient_all_cosets": 0}
+    ab = []
+    for spec in args.ab:
+        opts = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(","))}
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        for _ in range(2):
+            step_resident()
+        ctx.prof_reset()
+        ctx.prof_enable(True)
+        ms_ab, proof_ab = timed(step_resident, args.steps)
+        prof_ab = ctx.prof_get()
+        ctx.prof_enable(False)
+        for k in opts:
+            ctx.set_option(k, DEFAULTS.get(k, 0))
+        ab.append({"options": opts, "prove_ms": round(ms_ab / args.steps, 3), "same_bytes": proof_ab == proof,
+                   "phases_ms_per_step": {p_: round(prof_ab[p_][0] / args.steps, 3) for p_ in PHASES}})
+
     # BASELINE.json's metric names two more numbers next to the prove time: G1 MSM Mpts/s and NTT GB/s (algorithmic
     # 64 * N bytes per transform), "at 1/2/4/8 B200".  Measured here on the prover's own SRS and a witness
     # column, device resident, after the timed region: the MSM sharded over the N GPUs like the prover's (every rank
@@ -442,6 +467,7 @@ def main():
         "proof_sha256": parity["sha256"][:16],
         "verify": verify,
         "standalone": standalone,
+        "ab": ab or None,
         "north_star": None,
         "sweeps": None,
         "cpu_baseline": None,
@@ -477,12 +503,22 @@ def main():
             for _ in range(ns_steps):
                 t_ms, pr2 = timed(f_e2e, 1)
                 e2e_ms.append(round(t_ms, 3))
+            ns_ab = []
+            for spec in args.ab:
+                opts = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(","))}
+                for k, v in opts.items():
+                    ctx.set_option(k, v)
+                f_res()
+                t_ms, pr_ab = timed(f_res, 3)
+                for k in opts:
+                    ctx.set_option(k, DEFAULTS.get(k, 0))
+                ns_ab.append({"options": opts, "prove_ms": round(t_ms / 3, 3), "same_bytes": pr_ab == pr})
             line["north_star"] = {"workload": "mulchain_prove_n=2^%d" % lg, "gates": (1 << lg) - 3, "n_gpus": world,
                                   "prove_ms": round(sum(res_ms) / ns_steps, 3), "e2e_ms": round(sum(e2e_ms) / ns_steps, 3),
                                   "prove_ms_per_step": res_ms, "e2e_ms_per_step": e2e_ms,
                                   "steps": ns_steps, "warmup": 2, "parity": _parity(pr, lg), "e2e_same_bytes": pr == pr2,
                                   "phases_ms_per_step": {p: round(ns_prof[p][0] / ns_steps, 3) for p in PHASES},
-                                  "setup_s": round(bsetup, 1)}
+                                  "ab": ns_ab or None, "setup_s": round(bsetup, 1)}
             big.handle.destroy()
             big.srs.handle.destroy()
             del bdev, bhost

@@ -135,3 +135,52 @@ def test_comm_init_rank_argument_checks():
     with pytest.raises(TyplonkError):
         g.comm_init_rank(0, 1)
     g.close()
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_msm_pipeline_same_bytes(ctx, world):
+    """The MSM pipe (msm.cu "pipeline": sub-batches on three streams, lanes of scratch buffers, one exchange and one
+    read-back per batch) against the one-stream path: same proof bytes, same commitments on the edge-case scalar
+    vectors, with the staged accumulation kernel and without.  `msm_pipe_min_log` = 0 brings small circuits onto the
+    path that only large ones take by default."""
+    from typlonk_b200 import field as F, synthetic
+    from typlonk_b200.ffi import Context
+    from oracle.pyoracle import rng
+    log_n = 11
+    n = 1 << log_n
+    plain = synthetic.mul_chain_direct(ctx, log_n)
+    cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
+    ctx.set_option("msm_pipeline", 0)
+    want = plain.handle.prove(cols, bytes(32 * n))
+    ctx.set_option("msm_pipeline", 1)
+    g = ctx if world == 1 else Context.multi([0] * world)
+    try:
+        circuit = plain if world == 1 else synthetic.mul_chain_direct(g, log_n)
+        for staged in (0, 1):
+            g.set_option("msm_acc_staged", staged)
+            for mode in (0, 2):
+                g.set_option("msm_pipeline", mode)
+                g.set_option("msm_pipe_min_log", 0)
+                for _ in range(2):   # twice: the lanes are reused
+                    assert circuit.handle.prove(cols, bytes(32 * n)) == want, (world, staged, mode)
+                assert circuit.handle.prove_inputs(cols, bytes(32)) == want
+        # commitments: zeros (a job with no entries at all), one repeated scalar (one bucket), r - 1
+        tau = F.fr_to_bytes(rng.fr_rand_stream(1, 1)[0])
+        m = 3000
+        srs = g.srs_from_secret(tau, m - 3)
+        ref = ctx.srs_from_secret(tau, m - 3)
+        rnd = random.Random(11)
+        vecs = {"zeros": [0] * m, "same": [12345] * m, "top": [F.R_MOD - 1] * m,
+                "uniform": [rnd.randrange(F.R_MOD) for _ in range(m)]}
+        ctx.set_option("msm_pipeline", 0)
+        expect = {name: ctx.commit(ref, F.fr_vec_to_bytes(vec)) for name, vec in vecs.items()}
+        g.set_option("msm_pipeline", 2)
+        g.set_option("msm_pipe_min_log", 0)
+        for name, vec in vecs.items():
+            assert g.commit(srs, F.fr_vec_to_bytes(vec)) == expect[name], name
+    finally:
+        g.set_option("msm_pipeline", 1)
+        g.set_option("msm_pipe_min_log", 15)
+        g.set_option("msm_acc_staged", 0)
+        if world != 1:
+            g.close()

@@ -46,6 +46,12 @@ static int on_rank0(tp_ctx* g, const std::function<int(tp_ctx*)>& fn) {
     if (is_group(ctx)) return fail(ctx, TP_ERR_INVALID_ARG, what ": device pointers belong to one device -- not available on a device group"); \
   } while (0)
 
+static int mid_stream_priority() {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) return 0;
+  return (least + greatest) / 2;   // numerically lower = more urgent; the range is [0, -5] on sm_100
+}
+
 extern "C" {
 
 // ---- context ------------------------------------------------------------------------------
@@ -67,7 +73,9 @@ int tp_ctx_create(int device, void* stream, tp_ctx** out) {
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // middle priority: the MSM pipe puts its accumulation on a lowest-priority stream, so what the prover queues here
+    // between two sub-batches (scans, transforms) gets SM slots ahead of the accumulation's pending blocks (msm.cu)
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, mid_stream_priority()) != cudaSuccess) {
       delete ctx;
       return TP_ERR_CUDA;
     }
@@ -109,9 +117,9 @@ int tp_ctx_destroy(tp_ctx* ctx) {
     cudaFree(c.lo);
     cudaFree(c.hi);
   }
-  DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_sorted,
-                    &ctx->msm_sorted_keys, &ctx->msm_hist, &ctx->msm_offsets, &ctx->msm_blocksums, &ctx->msm_buckets,
-                    &ctx->msm_part_keys, &ctx->msm_part_pts, &ctx->msm_seg, &ctx->msm_winsums, &ctx->msm_gather, &ctx->msm_compact, &ctx->msm_aff_pts,
+  msm_pipe_destroy(ctx);
+  DevBuf* bufs[] = {&ctx->ntt_scratch, &ctx->msm_scalars, &ctx->msm_keys, &ctx->msm_ranks, &ctx->msm_blocksums,
+                    &ctx->msm_winsums, &ctx->msm_gather, &ctx->msm_compact, &ctx->msm_aff_pts,
                     &ctx->msm_sorted2, &ctx->msm_aff_cnt, &ctx->msm_aff_plan, &ctx->msm_aff_rec, &ctx->flag};
   for (auto* b : bufs) release(*b);
   for (auto& b : ctx->scan_tmp) release(b);
@@ -153,6 +161,21 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
   if (strcmp(name, "msm_reduce_l1") == 0) {
     if (value < 0 || value > 2) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_reduce_l1 must be 0, 1 or 2");
     ctx->msm_reduce_l1 = (unsigned)value;
+    return TP_OK;
+  }
+  if (strcmp(name, "msm_pipeline") == 0) {
+    if (value < 0 || value > 2) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_pipeline must be 0, 1 or 2");
+    ctx->msm_pipeline = (unsigned)value;
+    return TP_OK;
+  }
+  if (strcmp(name, "msm_pipe_min_log") == 0) {
+    if (value < 0 || value > 27) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_pipe_min_log must be 0..27");
+    ctx->msm_pipe_min_log = (unsigned)value;
+    return TP_OK;
+  }
+  if (strcmp(name, "msm_acc_staged") == 0) {
+    if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_acc_staged must be 0 or 1");
+    ctx->msm_acc_staged = (unsigned)value;
     return TP_OK;
   }
   if (strcmp(name, "quotient_all_cosets") == 0) {
@@ -674,15 +697,9 @@ static void put_fr(uint8_t*& w, const HFr& x) {
 // The prover's second stream: the forward coset NTTs of the quotient do not depend on any Fiat-Shamir challenge, so they
 // are queued here as soon as their polynomial exists and run underneath the commitment MSMs of the main stream -- above
 // all during the latency-bound tail of each MSM (bucket reduction, host round trip), when most SMs are idle.
-struct StreamSwap {
-  tp_ctx* c;
-  cudaStream_t saved;
-  StreamSwap(tp_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
-  ~StreamSwap() { c->stream = saved; }
-};
 static int side_stream_init(tp_ctx* ctx) {
   if (ctx->side_stream) return TP_OK;
-  TP_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+  TP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->side_stream, cudaStreamNonBlocking, mid_stream_priority()));
   for (auto& e : ctx->side_ev) TP_CUDA_OK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   return TP_OK;
 }
@@ -884,6 +901,14 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     TP_TRY(quotient_combine_dev(ctx, c->buf4[0], n, skip0, c->t));
   }
 
+  // The three t commitments (proof.rs:175,181) need nothing that follows: with the MSM pipe they are queued now and
+  // accumulate while this stream computes the opening polynomials; the opening witnesses follow as two more sub-batches
+  // (the five plain openings, then the linearisation's) and one finish collects all nine points.
+  const bool piped = msm_pipe_overlaps(ctx, n);
+  if (piped) {
+    const Fr* sets[3] = {c->t, c->t + n, c->t + 2 * n};
+    TP_TRY(msm_pipe_submit(ctx, srs, sets, 3, n));
+  }
   // openings (proof.rs:147-163)
   uint8_t wit[6][TP_G1_BYTES];
   HFr ev[5];
@@ -903,6 +928,10 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
     sig_bar[0] = ys[5];
     sig_bar[1] = ys[6];
     pi_bar = pi_zero ? HFr::zero() : ys[7];
+  }
+  if (piped) {
+    const Fr* sets[5] = {c->q[0], c->q[1], c->q[2], c->q[3], c->q[4]};
+    TP_TRY(msm_pipe_submit(ctx, srs, sets, 5, n));
   }
   // linearisation (proof.rs:376-439)
   HFr a = ev[0], b = ev[1], cc = ev[2], zw = ev[4];
@@ -935,9 +964,16 @@ static int prove_resident(tp_ctx* ctx, tp_circuit* c, uint8_t* proof_out, const 
   HFr r_bar;
   TP_TRY(poly_open_dev(ctx, c->r, n, to_dev(zeta), c->q[5], &r_bar));
   // the six opening witnesses and the three t commitments (proof.rs:149,162,163,175,181) are
-  // independent of one another: one batched MSM.  (q[i][n-1] == 0, so length n is exact.)
+  // independent of one another: one batch of MSMs.  (q[i][n-1] == 0, so length n is exact.)
   uint8_t tcom[3][TP_G1_BYTES];
-  {
+  if (piped) {
+    const Fr* sets[1] = {c->q[5]};
+    TP_TRY(msm_pipe_submit(ctx, srs, sets, 1, n));
+    uint8_t outs[9][TP_G1_BYTES];
+    TP_TRY(msm_pipe_finish(ctx, outs, 9));
+    for (int i = 0; i < 3; i++) memcpy(tcom[i], outs[i], TP_G1_BYTES);
+    for (int i = 0; i < 6; i++) memcpy(wit[i], outs[3 + i], TP_G1_BYTES);
+  } else {
     const Fr* sets[9] = {c->q[0], c->q[1], c->q[2], c->q[3], c->q[4], c->q[5], c->t, c->t + n, c->t + 2 * n};
     uint8_t outs[9][TP_G1_BYTES];
     TP_TRY(msm_batch_dev(ctx, srs, sets, 9, n, outs));

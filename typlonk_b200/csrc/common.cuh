@@ -22,6 +22,7 @@ struct DevBuf {
 };
 
 struct LocalGroup;
+struct MsmPipe;
 struct NttTables {
   Fr* tw = nullptr;  // omega_N^i, i in [0, N/2]
 };
@@ -55,6 +56,10 @@ struct tp_ctx {
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
   unsigned msm_reduce_l1 = 0;     // bucket reduction's running-sum level: 0 by size, 1 never, 2 whenever the set allows it
   unsigned quotient_all_cosets = 0;  // 1: evaluate the quotient numerator on all four cosets even when it is known to vanish on H
+  unsigned msm_pipeline = 1;      // MSM batches as overlapped sub-batches on the pipe's own streams (msm.cu, "pipeline"):
+                                  // 0 never, 1 on sharded contexts, 2 always
+  unsigned msm_pipe_min_log = 15; // ... for inputs of at least 2^this points (tests lower it to reach the path with small circuits)
+  unsigned msm_acc_staged = 0;    // 1: the accumulation stages the next table point in shared memory with cp.async
   // work counters (tp_ctx_get_stat)
   double stat_msm_entries = 0, stat_msm_calls = 0, stat_msm_c = 0, stat_msm_nwin = 0, stat_msm_levels = 0, stat_msm_chunk = 0;
   // profiling
@@ -73,8 +78,10 @@ struct tp_ctx {
   std::vector<tp::CosetTable> coset_tables;
   // scratch
   tp::DevBuf ntt_scratch;
-  tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_sorted, msm_sorted_keys, msm_hist, msm_offsets, msm_blocksums,
-      msm_buckets, msm_part_keys, msm_part_pts, msm_seg, msm_winsums, msm_gather, msm_compact, msm_aff_pts, msm_sorted2, msm_aff_cnt, msm_aff_plan, msm_aff_rec;
+  // (the per-job buffers -- histogram, offsets, sorted list, buckets, partials, reduction levels -- live in the pipe's lanes)
+  tp::DevBuf msm_scalars, msm_keys, msm_ranks, msm_blocksums, msm_winsums, msm_gather, msm_compact, msm_aff_pts, msm_sorted2,
+      msm_aff_cnt, msm_aff_plan, msm_aff_rec;
+  tp::MsmPipe* msm_pipe = nullptr;   // streams, lanes of scratch buffers and the queued sub-batches (msm.cu)
   tp::DevBuf scan_tmp[8];
   tp::DevBuf misc[16];
   tp::DevBuf flag;
@@ -155,6 +162,14 @@ inline int check_launch(tp_ctx* ctx, const char* what) {
 }
 #define TP_LAUNCH(ctx, name) TP_TRY(tp::check_launch(ctx, name))
 
+// Work queued while one of these is alive goes to `s` instead of the context's own stream.
+struct StreamSwap {
+  tp_ctx* c;
+  cudaStream_t saved;
+  StreamSwap(tp_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
+  ~StreamSwap() { c->stream = saved; }
+};
+
 // ---- profiling scopes (CUDA events on the ctx stream) ---------------------------------
 struct ProfScope {
   tp_ctx* ctx;
@@ -216,6 +231,13 @@ int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, u
 int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len,
                   uint8_t (*out)[TP_G1_BYTES]);
 void encode_g1(const tph::HG1& p, uint8_t out[TP_G1_BYTES]);
+// The same in two steps, so that the caller can queue other work in between: `submit` queues one sub-batch (its sort
+// runs at once, under the accumulation of the sub-batch submitted before it), `finish` returns all results in
+// submission order.  msm_pipe_overlaps: would a submit of this size run on the pipe's own streams?
+int msm_pipe_submit(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len);
+int msm_pipe_finish(tp_ctx* ctx, uint8_t (*out)[TP_G1_BYTES], int count);
+bool msm_pipe_overlaps(const tp_ctx* ctx, size_t len);
+void msm_pipe_destroy(tp_ctx* ctx);
 // poly.cu
 int perm_grand_product_dev(tp_ctx* ctx, const Fr* const values[3], const Fr* const id[3], const Fr* const sigma[3],
                            size_t n, const Fr& beta, const Fr& gamma, Fr* out /* n+1 */, bool* closes = nullptr);

@@ -188,8 +188,24 @@ struct MsmEntry {
   unsigned key, rank, idx;
 };
 #define MSM_MAX_WIN 128   // windows_for(2) = 128
+// c-bit field w of the canonical scalar (no carry applied)
+__device__ __forceinline__ unsigned msm_raw_digit(const Fr& s, unsigned w, unsigned c) {
+  const unsigned bit = w * c;
+  if (bit >= 256) return 0;
+  const unsigned limb = bit >> 5, off = bit & 31;
+  unsigned long long two = s.v[limb];
+  if (limb + 1 < 8) two |= (unsigned long long)s.v[limb + 1] << 32;
+  return (unsigned)(two >> off) & ((1u << c) - 1);
+}
+// Ownership of bucket b: rank b % world, local index b / world -- a mask and a shift when world is a power of two (the
+// general division costs more than the digit extraction itself, and every rank pays it for ALL digits).
+struct MsmOwner {
+  unsigned world, rank, mask, shift;   // shift == 32: world is not a power of two
+  __device__ __forceinline__ bool mine(unsigned b) const { return shift != 32 ? (b & mask) == rank : b % world == rank; }
+  __device__ __forceinline__ unsigned local(unsigned b) const { return shift != 32 ? b >> shift : b / world; }
+};
 __global__ void __launch_bounds__(256) k_msm_digits_sharded(MsmScalarSets sets, size_t n, unsigned c, unsigned nwin, unsigned nbuck,
-                                                            unsigned levels, unsigned nsets, unsigned world, unsigned my_rank,
+                                                            unsigned levels, unsigned nsets, MsmOwner own,
                                                             unsigned stride, unsigned* __restrict__ hist,
                                                             unsigned* __restrict__ list_count, MsmEntry* __restrict__ list) {
   __shared__ unsigned warp_tot[8];
@@ -198,35 +214,31 @@ __global__ void __launch_bounds__(256) k_msm_digits_sharded(MsmScalarSets sets, 
   const unsigned sbase = blockIdx.y * nsets;
   Fr s;
   if (i < n) s = fr_from_mont(fr_load(sets.p[blockIdx.y] + i));
-  // pass 1: count (the digits are recomputed in pass 2: cheaper than keeping up to 128 of them)
+  const unsigned half = 1u << (c - 1);
+  // pass 1: one walk over the windows notes which digits are this rank's and the carry that entered each of them (a bit
+  // each: nwin <= 32, i.e. c >= 8); pass 2 visits the owned windows only -- about nwin / world of them
+  unsigned own_mask = 0, carry_mask = 0, mine = 0;
+  const bool masks = nwin <= 32;
   auto walk = [&](auto&& emit) {
     unsigned carry = 0;
     for (unsigned w = 0; w < nwin; w++) {
-      unsigned bit = w * c;
-      unsigned raw = 0;
-      if (bit < 256) {
-        unsigned limb = bit >> 5, off = bit & 31;
-        unsigned long long two = s.v[limb];
-        if (limb + 1 < 8) two |= (unsigned long long)s.v[limb + 1] << 32;
-        raw = (unsigned)(two >> off) & ((1u << c) - 1);
-      }
-      raw += carry;
-      carry = 0;
-      if (raw == 0) continue;
-      unsigned mag = raw, neg = 0;
-      if (raw > (1u << (c - 1))) {
-        mag = (1u << c) - raw;
-        neg = 1;
-        carry = 1;
-      }
-      if (mag == 0) continue;
-      const unsigned b = mag - 1;
-      if (b % world != my_rank) continue;
-      emit(w, (sbase + w / levels) * nbuck + b / world, neg);
+      const unsigned raw = msm_raw_digit(s, w, c) + carry;
+      const unsigned cin = carry;
+      carry = raw > half ? 1u : 0u;
+      if (raw == 0 || raw == (1u << c)) continue;
+      const unsigned mag = carry ? (1u << c) - raw : raw;
+      if (!own.mine(mag - 1)) continue;
+      emit(w, cin);
     }
   };
-  unsigned mine = 0;
-  if (i < n) walk([&](unsigned, unsigned, unsigned) { mine++; });
+  if (i < n)
+    walk([&](unsigned w, unsigned cin) {
+      mine++;
+      if (masks) {
+        own_mask |= 1u << w;
+        carry_mask |= cin << w;
+      }
+    });
   // block-wide exclusive prefix of `mine`
   const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   unsigned incl = mine;
@@ -247,14 +259,27 @@ __global__ void __launch_bounds__(256) k_msm_digits_sharded(MsmScalarSets sets, 
   }
   __syncthreads();
   unsigned pos = block_base + warp_tot[wid] + incl - mine;
-  if (i < n)
-    walk([&](unsigned w, unsigned k, unsigned neg) {
-      MsmEntry e;
-      e.key = k | (neg << 31);
-      e.rank = atomicAdd(&hist[k], 1u);
-      e.idx = (w % levels) * stride + (unsigned)i;   // level (w % levels) of the fixed-base table holds 2^(c (w % levels)) * P_i
-      list[pos++] = e;
-    });
+  auto put = [&](unsigned w, unsigned cin) {
+    const unsigned raw = msm_raw_digit(s, w, c) + cin;
+    const unsigned neg = raw > half ? 1u : 0u;
+    const unsigned mag = neg ? (1u << c) - raw : raw;
+    const unsigned k = (sbase + w / levels) * nbuck + own.local(mag - 1);
+    MsmEntry e;
+    e.key = k | (neg << 31);
+    e.rank = atomicAdd(&hist[k], 1u);
+    e.idx = (w % levels) * stride + (unsigned)i;   // level (w % levels) of the fixed-base table holds 2^(c (w % levels)) * P_i
+    list[pos++] = e;
+  };
+  if (i >= n) return;
+  if (masks) {
+    while (own_mask) {
+      const unsigned w = __ffs(own_mask) - 1;
+      own_mask &= own_mask - 1;
+      put(w, (carry_mask >> w) & 1u);
+    }
+  } else {
+    walk(put);
+  }
 }
 __global__ void __launch_bounds__(256) k_msm_scatter_compact(const MsmEntry* __restrict__ list, const unsigned* __restrict__ count_ptr,
                                                              const unsigned* __restrict__ offsets, uint2* __restrict__ sorted) {
@@ -590,13 +615,20 @@ __global__ void __launch_bounds__(AFF_THREADS, 4) k_aff_round(const G1Affine* __
 #ifndef TP_ACC_MIN_BLOCKS
 #define TP_ACC_MIN_BLOCKS 3   // 162 registers, 3 warps per scheduler: FMA-heavy pipe 80 % -> 87 % busy (profiles N)
 #endif
-__global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
+// STAGED: the table point of entry e + 1 travels global -> shared memory with cp.async (a thread-private 96-byte slot, two
+// stages) while the addition of entry e runs, instead of stalling the addition on a load from a multi-GB table with
+// three warps per scheduler to cover it; costs no registers (a prefetch hint into L1 / L2 measured slower, section 7 of
+// DESIGN.md).
+#define ACC_THREADS 128
+template <bool STAGED>
+__global__ void __launch_bounds__(ACC_THREADS, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const G1Affine* __restrict__ bases,
                                                         const G1Affine* __restrict__ scratch, unsigned split,
                                                         const uint2* __restrict__ sorted /* (index | sign, key) */,
                                                         const unsigned* __restrict__ m_ptr /* live entry count */,
                                                         unsigned nchunks,
                                                         G1Xyzz* __restrict__ buckets, unsigned* __restrict__ part_keys,
                                                         G1Xyzz* __restrict__ part_pts, unsigned chunk) {
+  __shared__ uint4 stage_sh[STAGED ? 2 * 6 * ACC_THREADS : 1];   // [stage][16-byte piece][thread]: conflict-free
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nchunks) return;
   const unsigned m_total = *m_ptr;
@@ -610,8 +642,25 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
   G1Xyzz acc = xyzz_identity();
   unsigned cur = sorted[start].y;
   bool is_first_run = true;
+  auto stage_point = [&](unsigned st, unsigned idx) {
+    const uint4* src = (const uint4*)msm_point(bases, scratch, split, idx & 0x7fffffffu);
+#pragma unroll
+    for (int c = 0; c < 6; c++) cp_async16(&stage_sh[(st * 6 + c) * ACC_THREADS + threadIdx.x], src + c);
+    asm volatile("cp.async.commit_group;");
+  };
+  uint2 ent_next = sorted[start];
+  if (STAGED) stage_point(0, ent_next.x);
   for (unsigned e = start; e < end; e++) {
-    const uint2 ent = sorted[e];
+    const uint2 ent = STAGED ? ent_next : sorted[e];
+    if (STAGED) {
+      if (e + 1 < end) {
+        ent_next = sorted[e + 1];
+        stage_point((e + 1 - start) & 1, ent_next.x);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+    }
     const unsigned key = ent.y;
     if (key != cur) {
       if (is_first_run) {
@@ -625,21 +674,34 @@ __global__ void __launch_bounds__(128, TP_ACC_MIN_BLOCKS) k_msm_accumulate(const
       cur = key;
     }
     const unsigned idx = ent.x;
+    G1Affine p;
+    if (STAGED) {
+      const unsigned st = (e - start) & 1;
+      uint4 w[6];
+#pragma unroll
+      for (int c = 0; c < 6; c++) w[c] = stage_sh[(st * 6 + c) * ACC_THREADS + threadIdx.x];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        p.x.v[4 * c] = w[c].x; p.x.v[4 * c + 1] = w[c].y; p.x.v[4 * c + 2] = w[c].z; p.x.v[4 * c + 3] = w[c].w;
+        p.y.v[4 * c] = w[3 + c].x; p.y.v[4 * c + 1] = w[3 + c].y; p.y.v[4 * c + 2] = w[3 + c].z; p.y.v[4 * c + 3] = w[3 + c].w;
+      }
+    } else {
 #ifdef TP_ACC_PREFETCH
-    // The next entry's point sits anywhere in a multi-GB table: ask for its line(s) now, one addition
-    // (thousands of cycles) ahead of the load, instead of stalling on an HBM miss with three warps per scheduler.
-    if (e + 1 < end) {
-      const char* nx = (const char*)msm_point(bases, scratch, split, sorted[e + 1].x & 0x7fffffffu);
+      // The next entry's point sits anywhere in a multi-GB table: ask for its line(s) now, one addition
+      // (thousands of cycles) ahead of the load, instead of stalling on an HBM miss with three warps per scheduler.
+      if (e + 1 < end) {
+        const char* nx = (const char*)msm_point(bases, scratch, split, sorted[e + 1].x & 0x7fffffffu);
 #if TP_ACC_PREFETCH == 2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 80));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + 80));
 #else
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 80));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 80));
 #endif
+      }
+#endif
+      p = affine_load(msm_point(bases, scratch, split, idx & 0x7fffffffu));
     }
-#endif
-    G1Affine p = affine_load(msm_point(bases, scratch, split, idx & 0x7fffffffu));
     if (!affine_is_identity(p)) xyzz_madd(acc, p, (idx >> 31) != 0);
   }
   if (is_first_run) {
@@ -996,19 +1058,20 @@ __global__ void __launch_bounds__(TS_THREADS) k_msm_treesum(TreeTasks tasks) {
 }
 
 // ---- 7. cross-rank combination (sharded MSM) --------------------------------------------------------
-// `gathered` holds every rank's reduction output, [world][sets][slots] (the all-gather of msm_winsums).  The tail the
+// `gathered` holds every rank's reduction output: rank r's [sets][slots] block of this job starts at r * rank_stride
+// (the all-gather of msm_winsums, which carries all jobs of a batch).  The tail the
 // host runs per bucket set is linear in the slots and, except for slot 0 (P = sum of the rank's buckets, which enters
 // with the rank-dependent factor rank + 1), the same on every rank: slots >= 1 are therefore summed over ranks here --
 // one warp per (set, slot), lane r holding rank r's point, a shared-memory tree -- and the `world` P points pass
 // through.  out: [sets][(slots - 1) sums | world P points].
-__global__ void __launch_bounds__(32) k_msm_combine(const G1Xyzz* __restrict__ gathered, unsigned world, unsigned sets,
+__global__ void __launch_bounds__(32) k_msm_combine(const G1Xyzz* __restrict__ gathered, unsigned world, unsigned rank_stride,
                                                     unsigned slots, G1Xyzz* __restrict__ out) {
   __shared__ G1Xyzz sh[32];
   const unsigned set = blockIdx.x / slots, slot = blockIdx.x % slots;
   const unsigned width = slots - 1 + world;
   const unsigned r = threadIdx.x;
   G1Xyzz p = xyzz_identity();
-  if (r < world) p = xyzz_load(gathered + ((size_t)r * sets + set) * slots + slot);
+  if (r < world) p = xyzz_load(gathered + (size_t)r * rank_stride + (size_t)set * slots + slot);
   if (slot == 0) {
     if (r < world) xyzz_store(out + (size_t)set * width + (slots - 1) + r, p);
     return;
@@ -1081,56 +1144,194 @@ static int exclusive_scan(tp_ctx* ctx, const T* in, T* out, size_t n, unsigned* 
   return TP_OK;
 }
 
-// `batch` MSMs over the first `len` bases at once: all scalar vectors share one sort / accumulate / merge / reduce
-// pipeline (bucket set index = b * nsets + q), which amortises the latency-bound reduction tail and the launch
-// overhead.  On a sharded context (world > 1) this rank handles the buckets it owns, the ranks' reduction outputs are
-// all-gathered and combined on the device (comm.cu, k_msm_combine) and every rank returns the complete sums.
-static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, int batch, size_t len,
-                     tph::HG1* results) {
-  for (int b = 0; b < batch; b++) results[b] = tph::HG1::identity();
-  if (len == 0 || batch == 0) return TP_OK;
-  if (batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: batch too large");
-  if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
-  const unsigned world = ctx->world > 1 ? (unsigned)ctx->world : 1u;
-  const MsmPlan pl = msm_plan(srs, world);
-  if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nsets * pl.nbuck * batch >= ((size_t)1 << 30)) {
-    if (batch == 1) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
-    int half = batch / 2;  // split the batch until the entry count fits 31 bits
-    TP_TRY(msm_local(ctx, srs, scalars, half, len, results));
-    return msm_local(ctx, srs, scalars + half, batch - half, len, results + half);
+// ---- pipeline ------------------------------------------------------------------------------------------------------
+// An MSM is three kinds of work: a sort bound by atomics and random stores, an accumulation (and the first
+// running-sum level of the reduction) bound by the wide-multiply pipe, and latency-bound tails (boundary fix-up, tree
+// sums) that keep a few hundred threads busy.  Run back to back on one stream, the first and the last leave the
+// multiplier idle: 7 of 82 ms of a 2^20 proof.  A batch is therefore cut into SUB-BATCHES (jobs) that travel through
+// three streams -- sort (high priority), accumulate + running sums (normal priority), tails (high priority) -- linked
+// by events, each job on its own LANE of scratch buffers:
+//
+//     sort:   S0 S1       S2
+//     acc:       A0 ------A1 ------ W0  A2 ------ W1  W2          (W = running-sum levels of the reduction)
+//     tails:              F0        F1  T0        F2  T1  T2      (F = boundary fix-up, T = tree sums)
+//
+// so the sort and the tails of one job run underneath the accumulation of its neighbours; the high priority makes the
+// block scheduler place their (few, small) blocks ahead of the accumulation's pending ones as SM slots come free.  The
+// host waits once per job for the sort's two counters (live entries, largest bucket: they size the accumulation) --
+// while the previous job accumulates -- and once at the end for ALL jobs' reduction outputs, which share one buffer:
+// one all-gather (sharded), one copy to the host, then the serial tails on host threads.
+// msm_pipe_submit / msm_pipe_finish expose the two halves so that the prover can queue other work in between
+// (api.cu: the quotient's commitments start while the opening polynomials are still being computed).
+// Not overlapped (option msm_pipeline = 0, small inputs, the opt-in affine variants): the same stages run in order
+// on the context's stream.
+#define MSM_LANES 3
+struct MsmLane {
+  DevBuf hist, offsets, sorted, buckets, part_keys, part_pts, seg;
+  cudaEvent_t ev_sorted = nullptr, ev_acc = nullptr, ev_fix = nullptr, ev_wsum = nullptr, ev_done = nullptr;
+  bool busy = false;   // ev_done belongs to a job that may still be running
+};
+struct MsmJob {
+  int lane = 0, batch = 0, first_result = 0;
+  size_t len = 0;
+  const tp_srs* srs = nullptr;
+  MsmPlan pl;
+  unsigned nsets_total = 0;
+  size_t nkeys = 0;
+  unsigned m_total = 0, max_bucket = 0, nchunks = 0;
+  bool pair_path = true, empty = false, reduce_queued = false;
+  // reduction plan
+  int nl = 0;
+  unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1], tcount[WSUM_MAX_LEVELS + 1], tjobs[WSUM_MAX_LEVELS + 1];
+  unsigned bC = 0, bD = 0, cols = 0, rows = 0, total_masks = 0;
+  size_t win_off = 0;    // first slot of this job in msm_winsums
+  size_t host_off = 0;   // first slot of this job in the buffer the host reads back
+};
+struct MsmPipe {
+  cudaStream_t s_sort = nullptr, s_acc = nullptr, s_tail = nullptr;
+  cudaEvent_t ev_in = nullptr;
+  MsmLane lane[MSM_LANES];
+  unsigned* counts = nullptr;   // pinned, [lane][2]: live entries, largest bucket
+  std::vector<MsmJob> jobs;
+  bool overlap = false;         // mode of the batch being queued
+  size_t win_used = 0;          // slots of msm_winsums the queued jobs take
+  int results = 0;              // results the queued jobs will return
+  int next_lane = 0;
+  ProfScope* total = nullptr;   // TP_PHASE_MSM_TOTAL of an overlapped batch: first submit to the end of finish
+};
+
+// grow-only like ensure(), but the old buffer may be in use on any of the pipe's streams
+static int ensure_idle(tp_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap && b.p) return TP_OK;
+  if (b.p) TP_CUDA_OK(ctx, cudaDeviceSynchronize());
+  return ensure(ctx, b, bytes);
+}
+
+static int pipe_get(tp_ctx* ctx, MsmPipe** out) {
+  if (!ctx->msm_pipe) {
+    MsmPipe* p = new MsmPipe();
+    ctx->msm_pipe = p;
+    if (cudaMallocHost(&p->counts, MSM_LANES * 2 * sizeof(unsigned)) != cudaSuccess) return fail(ctx, TP_ERR_CUDA, "msm: pinned allocation failed");
+    TP_CUDA_OK(ctx, cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    for (auto& l : p->lane)
+      for (cudaEvent_t* e : {&l.ev_sorted, &l.ev_acc, &l.ev_fix, &l.ev_wsum, &l.ev_done})
+        TP_CUDA_OK(ctx, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
   }
-  const G1Affine* bases = srs->g1;              // level k of point i lives at bases[k * srs->len + i]
-  const unsigned nsets_total = pl.nsets * batch;
-  size_t nkeys = (size_t)nsets_total * pl.nbuck;
-  size_t total = (size_t)pl.nwin * batch * len;
-  TP_TRY(ensure(ctx, ctx->msm_hist, (nkeys + 2) * sizeof(unsigned)));  // + scan sentinel + largest bucket
-  TP_TRY(ensure(ctx, ctx->msm_offsets, (nkeys + 1) * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_keys, total * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_ranks, total * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_sorted, total * sizeof(uint2)));
-  TP_TRY(ensure(ctx, ctx->msm_buckets, nkeys * sizeof(G1Xyzz)));
-  unsigned* hist = (unsigned*)ctx->msm_hist.p;
-  unsigned* offsets = (unsigned*)ctx->msm_offsets.p;
+  *out = ctx->msm_pipe;
+  return TP_OK;
+}
+static int pipe_streams(tp_ctx* ctx, MsmPipe* p) {
+  if (p->s_acc) return TP_OK;
+  int least = 0, greatest = 0;
+  TP_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  TP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&p->s_sort, cudaStreamNonBlocking, greatest));
+  TP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&p->s_tail, cudaStreamNonBlocking, greatest));
+  TP_CUDA_OK(ctx, cudaStreamCreateWithPriority(&p->s_acc, cudaStreamNonBlocking, least));
+  return TP_OK;
+}
+void msm_pipe_destroy(tp_ctx* ctx) {
+  MsmPipe* p = ctx->msm_pipe;
+  if (!p) return;
+  cudaDeviceSynchronize();
+  for (cudaStream_t s : {p->s_sort, p->s_acc, p->s_tail})
+    if (s) cudaStreamDestroy(s);
+  if (p->ev_in) cudaEventDestroy(p->ev_in);
+  for (auto& l : p->lane) {
+    for (DevBuf* b : {&l.hist, &l.offsets, &l.sorted, &l.buckets, &l.part_keys, &l.part_pts, &l.seg}) release(*b);
+    for (cudaEvent_t e : {l.ev_sorted, l.ev_acc, l.ev_fix, l.ev_wsum, l.ev_done})
+      if (e) cudaEventDestroy(e);
+  }
+  if (p->counts) cudaFreeHost(p->counts);
+  delete p->total;
+  delete p;
+  ctx->msm_pipe = nullptr;
+}
+// after an error: nothing of the queued batch survives
+static void pipe_abort(tp_ctx* ctx) {
+  MsmPipe* p = ctx->msm_pipe;
+  if (!p) return;
+  cudaDeviceSynchronize();
+  p->jobs.clear();
+  p->win_used = 0;
+  p->results = 0;
+  for (auto& l : p->lane) l.busy = false;
+  delete p->total;
+  p->total = nullptr;
+}
+
+static cudaStream_t pipe_sort_stream(tp_ctx* ctx, MsmPipe* p) { return p->overlap ? p->s_sort : ctx->stream; }
+static cudaStream_t pipe_acc_stream(tp_ctx* ctx, MsmPipe* p) { return p->overlap ? p->s_acc : ctx->stream; }
+static cudaStream_t pipe_tail_stream(tp_ctx* ctx, MsmPipe* p) { return p->overlap ? p->s_tail : ctx->stream; }
+static int pipe_wait(tp_ctx* ctx, MsmPipe* p, cudaStream_t s, cudaEvent_t e) {   // one stream when not overlapped: already ordered
+  if (p->overlap) TP_CUDA_OK(ctx, cudaStreamWaitEvent(s, e, 0));
+  return TP_OK;
+}
+static int pipe_record(tp_ctx* ctx, MsmPipe* p, cudaEvent_t e, cudaStream_t s) {
+  if (p->overlap) TP_CUDA_OK(ctx, cudaEventRecord(e, s));
+  return TP_OK;
+}
+
+// Inputs worth overlapping: from about 2^15 points the accumulation of a job is long enough to cover its neighbours' sort.
+bool msm_pipe_overlaps(const tp_ctx* ctx, size_t len) {
+  static const unsigned env_min_log = env_uint("TP_MSM_PIPE_MIN_LOG", 0);
+  const unsigned min_log = env_min_log ? env_min_log : ctx->msm_pipe_min_log;
+  static const bool env_off = getenv("TP_MSM_PIPELINE") && *getenv("TP_MSM_PIPELINE") == '0';
+  static const bool env_all = getenv("TP_MSM_PIPELINE") && *getenv("TP_MSM_PIPELINE") == '2';
+  // On one GPU the accumulation fills every SM's register file: a second kernel only gets slots as accumulation blocks
+  // retire, so the "overlapped" sort runs no sooner than it would alone, and the smaller sub-batches reduce less
+  // efficiently (2^20: 84.2 ms against 82.2, profiles/r2_summary.md I).  A sharded rank's accumulation leaves SMs free
+  // and the latency-bound stages are a larger share: there the pipe is on by default (1); 2 forces it everywhere.
+  const bool want = ctx->msm_pipeline == 2 || env_all || (ctx->msm_pipeline == 1 && ctx->world > 1);
+  return want && !env_off && ctx->msm_aff_rounds == 0 && ctx->msm_affine_chains == 0 && len >= ((size_t)1 << min_log);
+}
+
+// ---- stage 1: digits, bucket offsets, counting-sort scatter (sort stream); ends with the two counters on their way to the host
+static int job_sort(tp_ctx* ctx, MsmPipe* p, MsmJob& j, const Fr* const* scalars) {
+  MsmLane& ln = p->lane[j.lane];
+  const MsmPlan& pl = j.pl;
+  const unsigned world = ctx->world > 1 ? (unsigned)ctx->world : 1u;
+  const size_t len = j.len, nkeys = j.nkeys;
+  const size_t total = (size_t)pl.nwin * j.batch * len;
+  TP_TRY(ensure_idle(ctx, ln.hist, (nkeys + 2) * sizeof(unsigned)));  // + scan sentinel + largest bucket
+  TP_TRY(ensure_idle(ctx, ln.offsets, (nkeys + 1) * sizeof(unsigned)));
+  TP_TRY(ensure_idle(ctx, ln.sorted, total * sizeof(uint2)));
+  TP_TRY(ensure_idle(ctx, ln.buckets, nkeys * sizeof(G1Xyzz)));
+  unsigned* hist = (unsigned*)ln.hist.p;
+  unsigned* offsets = (unsigned*)ln.offsets.p;
+  uint2* sorted = (uint2*)ln.sorted.p;
+  const bool compact = world > 1 && !env_uint("TP_MSM_NO_COMPACT", 0);
+  if (compact) {
+    TP_TRY(ensure_idle(ctx, ctx->msm_compact, total * sizeof(MsmEntry) + 16));
+  } else {   // keys / ranks live from the digit pass to the scatter only: one copy, all sorts run on one stream
+    TP_TRY(ensure_idle(ctx, ctx->msm_keys, total * sizeof(unsigned)));
+    TP_TRY(ensure_idle(ctx, ctx->msm_ranks, total * sizeof(unsigned)));
+  }
+  {
+    const size_t nblocks = (nkeys + 1 + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    TP_TRY(ensure_idle(ctx, ctx->msm_blocksums, nblocks * sizeof(unsigned)));
+  }
   unsigned* keys = (unsigned*)ctx->msm_keys.p;
   unsigned* ranks = (unsigned*)ctx->msm_ranks.p;
-  uint2* sorted = (uint2*)ctx->msm_sorted.p;
-  G1Xyzz* buckets = (G1Xyzz*)ctx->msm_buckets.p;
-  unsigned m_total = 0, max_bucket = 0;
+  StreamSwap sw(ctx, pipe_sort_stream(ctx, p));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_SORT);
     TP_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (nkeys + 2) * sizeof(unsigned), ctx->stream));
     MsmScalarSets sets;
-    for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < batch ? b : 0];
-    dim3 grid((unsigned)((len + 255) / 256), (unsigned)batch);
-    static const bool no_compact = env_uint("TP_MSM_NO_COMPACT", 0) != 0;
-    if (world > 1 && !no_compact) {
+    for (int b = 0; b < MSM_MAX_BATCH; b++) sets.p[b] = scalars[b < j.batch ? b : 0];
+    dim3 grid((unsigned)((len + 255) / 256), (unsigned)j.batch);
+    if (compact) {
       // sharded: owned entries into a compact list, scatter over that list (see 1b)
-      TP_TRY(ensure(ctx, ctx->msm_compact, total * sizeof(MsmEntry) + 16));
       unsigned* list_count = (unsigned*)ctx->msm_compact.p;
       MsmEntry* list = (MsmEntry*)((char*)ctx->msm_compact.p + 16);
       TP_CUDA_OK(ctx, cudaMemsetAsync(list_count, 0, sizeof(unsigned), ctx->stream));
-      k_msm_digits_sharded<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, world,
-                                                          (unsigned)ctx->rank, (unsigned)srs->len, hist, list_count, list);
+      MsmOwner own;
+      own.world = world;
+      own.rank = (unsigned)ctx->rank;
+      own.mask = world - 1;
+      own.shift = 32;
+      if ((world & (world - 1)) == 0) own.shift = (unsigned)__builtin_ctz(world);
+      k_msm_digits_sharded<<<grid, 256, 0, ctx->stream>>>(sets, len, pl.c, pl.nwin, pl.nbuck, pl.levels, pl.nsets, own,
+                                                          (unsigned)j.srs->len, hist, list_count, list);
       TP_LAUNCH(ctx, "k_msm_digits_sharded");
       TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
       k_msm_scatter_compact<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(list, list_count, offsets, sorted);
@@ -1140,57 +1341,69 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
                                                   (unsigned)ctx->rank, hist, keys, ranks);
       TP_LAUNCH(ctx, "k_msm_digits");
       TP_TRY(exclusive_scan<unsigned>(ctx, hist, offsets, nkeys + 1, hist + nkeys + 1));
-      {
-        // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
-        // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
-        // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
-        // is several L2s long gains little (2^24: 9.9 -> 9.4 ms with four).  TP_MSM_SCATTER_SLICES forces a count.
-        static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
-        static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
-        unsigned log_slices = 0;
-        if (env_slices) {
-          while ((2u << log_slices) <= env_slices) log_slices++;
-        } else {
-          const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
-          if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
-          else if (per_msm > window) log_slices = 1;
-        }
-        unsigned log_nbuck = 0;
-        while ((1u << log_nbuck) < pl.nbuck) log_nbuck++;
-        if (world > 1) {   // a rank scatters 1 / world of the list: fewer slices bring it inside the L2
-          unsigned lw = 0;
-          while ((2u << lw) <= world) lw++;
-          log_slices = log_slices > lw ? log_slices - lw : 0;
-        }
-        if (log_slices > log_nbuck) log_slices = log_nbuck;
-        const unsigned slice_shift = log_nbuck - log_slices;
-        const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
-        for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
-          k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(keys, ranks, offsets, len, total, pl.nwin,
-                                                                                   pl.levels, (unsigned)srs->len, sorted,
-                                                                                   pl.nbuck - 1, slice_shift, sl);
-          TP_LAUNCH(ctx, "k_msm_scatter");
-        }
+      // Two slices when that brings one MSM's share of the sorted list (len * nwin entries of 8 bytes) from "about
+      // the L2" to "well inside it" (TP_MSM_SCATTER_WINDOW_MB, default 64); every further slice costs a full pass
+      // over the keys (~0.5 ms per proof at 2^20) and measured slower (4: +0.3 ms, 8: +2.3 ms), and a list that
+      // is several L2s long gains little (2^24: 9.9 -> 9.4 ms with four).  TP_MSM_SCATTER_SLICES forces a count.
+      static const unsigned env_slices = env_uint("TP_MSM_SCATTER_SLICES", 0);
+      static const unsigned window_mb = env_uint("TP_MSM_SCATTER_WINDOW_MB", 64);
+      unsigned log_slices = 0;
+      if (env_slices) {
+        while ((2u << log_slices) <= env_slices) log_slices++;
+      } else {
+        const size_t per_msm = (size_t)pl.nwin * len * sizeof(uint2), window = (size_t)window_mb << 20;
+        if (per_msm > 2 * window) log_slices = 2;   // several L2s long: four slices still save a little (2^22: 2.51 -> 2.15 ms)
+        else if (per_msm > window) log_slices = 1;
+      }
+      unsigned log_nbuck = 0;
+      while ((1u << log_nbuck) < pl.nbuck) log_nbuck++;
+      if (world > 1) {   // a rank scatters 1 / world of the list: fewer slices bring it inside the L2
+        unsigned lw = 0;
+        while ((2u << lw) <= world) lw++;
+        log_slices = log_slices > lw ? log_slices - lw : 0;
+      }
+      if (log_slices > log_nbuck) log_slices = log_nbuck;
+      const unsigned slice_shift = log_nbuck - log_slices;
+      const size_t per_block = (size_t)256 * 4 * SCATTER_UNROLL;
+      for (unsigned sl = 0; sl < (1u << log_slices); sl++) {
+        k_msm_scatter<<<(unsigned)((total + per_block - 1) / per_block), 256, 0, ctx->stream>>>(
+            keys, ranks, offsets, len, total, pl.nwin, pl.levels, (unsigned)j.srs->len, sorted, pl.nbuck - 1, slice_shift, sl);
+        TP_LAUNCH(ctx, "k_msm_scatter");
       }
     }
-    TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    TP_CUDA_OK(ctx, cudaMemcpyAsync((unsigned*)ctx->pinned + 1, hist + nkeys + 1, sizeof(unsigned), cudaMemcpyDeviceToHost,
-                                    ctx->stream));
-    TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    m_total = ((unsigned*)ctx->pinned)[0];
-    max_bucket = ((unsigned*)ctx->pinned)[1];
+    unsigned* cnt = p->counts + 2 * j.lane;
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(cnt, offsets + nkeys, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(cnt + 1, hist + nkeys + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   }
-  if (m_total == 0 && world == 1) return TP_OK;  // all scalars zero (a sharded rank still takes part in the exchange)
+  TP_TRY(pipe_record(ctx, p, ln.ev_sorted, ctx->stream));
+  return TP_OK;
+}
+
+// ---- stage 2: accumulation (accumulate stream) and boundary fix-up (tail stream), sized from the sort's counters
+static int job_accumulate(tp_ctx* ctx, MsmPipe* p, MsmJob& j) {
+  MsmLane& ln = p->lane[j.lane];
+  const MsmPlan& pl = j.pl;
+  const tp_srs* srs = j.srs;
+  const size_t nkeys = j.nkeys;
+  const G1Affine* bases = srs->g1;              // level k of point i lives at bases[k * srs->len + i]
+  unsigned* hist = (unsigned*)ln.hist.p;
+  unsigned* offsets = (unsigned*)ln.offsets.p;
+  unsigned* keys = (unsigned*)ctx->msm_keys.p;
+  uint2* sorted = (uint2*)ln.sorted.p;
+  G1Xyzz* buckets = (G1Xyzz*)ln.buckets.p;
+  const unsigned m_total = j.m_total;
+  StreamSwap sw(ctx, pipe_acc_stream(ctx, p));
+  TP_TRY(pipe_wait(ctx, p, ctx->stream, ln.ev_sorted));
   // ---- batch-affine rounds (4a): plan on the host from upper bounds, sizes stay on the device ----
   // bound[r] >= entries before round r + 1: every round leaves ceil(cnt / 2) per bucket.
   // Off by default: on sm_100a the rounds do not beat the XYZZ accumulation they replace (profiles/r1_summary.md K);
-  // tp_ctx_set_option("msm_affine_rounds", r) or TP_MSM_AFF_ROUNDS=r turn them on.
-  const unsigned aff_rounds_env = ctx->msm_aff_rounds;
+  // tp_ctx_set_option("msm_affine_rounds", r) or TP_MSM_AFF_ROUNDS=r turn them on (never overlapped: ctx scratch).
+  const unsigned aff_rounds_env = p->overlap ? 0u : ctx->msm_aff_rounds;
   const unsigned aff_disable = aff_rounds_env == 0;
   size_t bound[AFF_MAX_ROUNDS + 1];
   bound[0] = m_total;
   int rounds = 0;
-  unsigned max_b = max_bucket;
+  unsigned max_b = j.max_bucket;
   const size_t split = (size_t)pl.levels * srs->len;  // table indices are < split
   if (!aff_disable) {
     const int want = (int)(aff_rounds_env < AFF_MAX_ROUNDS ? aff_rounds_env : AFF_MAX_ROUNDS);
@@ -1295,7 +1508,7 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     }
   }
   // affine chains (4c): AFC_J chunks per thread, so the chunks shrink until the grid fills the GPU
-  const bool chains = rounds == 0 && ctx->msm_affine_chains != 0;
+  const bool chains = rounds == 0 && !p->overlap && ctx->msm_affine_chains != 0;
   if (chains) {
     static unsigned chunk_env = env_uint("TP_MSM_AFC_CHUNK", 0);
     const size_t want = (size_t)ctx->sm_count * 128 * AFC_MIN_BLOCKS * AFC_J;
@@ -1303,117 +1516,157 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     chunk = ch < 16 ? 16u : (ch > 64 ? 64u : (unsigned)ch);
     if (chunk_env) chunk = chunk_env;
   }
-  const bool pair_path = max_b < PAIR_MAX_SPAN * chunk && !msm_force_levels();
-  unsigned nchunks = (unsigned)((m_bound + chunk - 1) / chunk);
+  j.pair_path = max_b < PAIR_MAX_SPAN * chunk && !msm_force_levels();
+  const unsigned nchunks = (unsigned)((m_bound + chunk - 1) / chunk);
+  j.nchunks = nchunks;
   // first half: accumulate's partials; second half: ping-pong space for the merge levels
-  TP_TRY(ensure(ctx, ctx->msm_part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
-  TP_TRY(ensure(ctx, ctx->msm_part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
+  TP_TRY(ensure_idle(ctx, ln.part_keys, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(unsigned)));
+  TP_TRY(ensure_idle(ctx, ln.part_pts, ((size_t)2 * nchunks + (size_t)nchunks / 4 + 64) * sizeof(G1Xyzz)));
   ctx->stat_msm_entries += (double)m_total;
-  ctx->stat_msm_calls += batch;
+  ctx->stat_msm_calls += j.batch;
   ctx->stat_msm_c = pl.c;
   ctx->stat_msm_nwin = pl.nwin;
   ctx->stat_msm_levels = pl.levels;
   ctx->stat_msm_chunk = chunk;
   if (m_total > 0) {
-    ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
-    if (chains) {
-      TP_TRY(ensure(ctx, ctx->msm_aff_pts, (size_t)nchunks * sizeof(G1Affine)));
-      const unsigned nthreads = (nchunks + AFC_J - 1) / AFC_J;
-      k_msm_accumulate_affine<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(
-          bases, final_list, final_m, nchunks, chunk, (G1Affine*)ctx->msm_aff_pts.p, buckets,
-          (unsigned*)ctx->msm_part_keys.p, (G1Xyzz*)ctx->msm_part_pts.p);
-      TP_LAUNCH(ctx, "k_msm_accumulate_affine");
-    } else {
-      k_msm_accumulate<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>(bases, scratch, (unsigned)split, final_list, final_m,
-                                                                       nchunks, buckets, (unsigned*)ctx->msm_part_keys.p,
-                                                                       (G1Xyzz*)ctx->msm_part_pts.p, chunk);
-      TP_LAUNCH(ctx, "k_msm_accumulate");
+    {
+      ProfScope prof(ctx, TP_PHASE_MSM_ACCUM);
+      if (chains) {
+        TP_TRY(ensure(ctx, ctx->msm_aff_pts, (size_t)nchunks * sizeof(G1Affine)));
+        const unsigned nthreads = (nchunks + AFC_J - 1) / AFC_J;
+        k_msm_accumulate_affine<<<(nthreads + 127) / 128, 128, 0, ctx->stream>>>(
+            bases, final_list, final_m, nchunks, chunk, (G1Affine*)ctx->msm_aff_pts.p, buckets, (unsigned*)ln.part_keys.p,
+            (G1Xyzz*)ln.part_pts.p);
+        TP_LAUNCH(ctx, "k_msm_accumulate_affine");
+      } else {
+        if (ctx->msm_acc_staged)
+          k_msm_accumulate<true><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(
+              bases, scratch, (unsigned)split, final_list, final_m, nchunks, buckets, (unsigned*)ln.part_keys.p,
+              (G1Xyzz*)ln.part_pts.p, chunk);
+        else
+          k_msm_accumulate<false><<<(nchunks + ACC_THREADS - 1) / ACC_THREADS, ACC_THREADS, 0, ctx->stream>>>(
+              bases, scratch, (unsigned)split, final_list, final_m, nchunks, buckets, (unsigned*)ln.part_keys.p,
+              (G1Xyzz*)ln.part_pts.p, chunk);
+        TP_LAUNCH(ctx, "k_msm_accumulate");
+      }
     }
+    TP_TRY(pipe_record(ctx, p, ln.ev_acc, ctx->stream));
+    // boundary partials -> buckets, on the tail stream
+    StreamSwap st(ctx, pipe_tail_stream(ctx, p));
+    TP_TRY(pipe_wait(ctx, p, ctx->stream, ln.ev_acc));
+    {
+      ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
+      if (j.pair_path) {
+        k_msm_pair_fixup<<<(nchunks + 63) / 64, 64, 0, ctx->stream>>>((const unsigned*)ln.part_keys.p, (const G1Xyzz*)ln.part_pts.p,
+                                                                      nchunks, buckets);
+        TP_LAUNCH(ctx, "k_msm_pair_fixup");
+      } else {
+        unsigned* ka = (unsigned*)ln.part_keys.p;
+        G1Xyzz* pa = (G1Xyzz*)ln.part_pts.p;
+        unsigned* kb = ka + 2 * (size_t)nchunks;
+        G1Xyzz* pb = pa + 2 * (size_t)nchunks;
+        unsigned nslots = 2 * nchunks;
+        while (nslots > 2 * MERGE_B) {
+          unsigned nth = (nslots + MERGE_B - 1) / MERGE_B;
+          k_msm_merge_level<<<(nth + 127) / 128, 128, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 0);
+          TP_LAUNCH(ctx, "k_msm_merge_level");
+          std::swap(ka, kb);
+          std::swap(pa, pb);
+          nslots = 2 * nth;
+        }
+        k_msm_merge_level<<<1, 32, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 1);
+        TP_LAUNCH(ctx, "k_msm_merge_level");
+      }
+    }
+    TP_TRY(pipe_record(ctx, p, ln.ev_fix, ctx->stream));
+  } else {
+    // a sharded rank that owns none of the digits: its buckets are all empty (the histogram says so)
+    TP_TRY(pipe_record(ctx, p, ln.ev_fix, ctx->stream));
   }
-  // Reduction plan.  Running-sum levels (every lane busy, two additions per entry, but a chain of 2 S dependent
-  // additions per thread) while the batch still has entries enough to keep the whole GPU busy with them -- 16-bucket
-  // segments first, 8 after that -- then the tree sums.  A small bucket set (a sharded rank's share, a single small
-  // MSM) is latency-bound from the start and goes straight to the tree sums.
+  return TP_OK;
+}
+
+// Reduction plan.  Running-sum levels (every lane busy, two additions per entry, but a chain of 2 S dependent
+// additions per thread) while the batch still has entries enough to keep the whole GPU busy with them -- 16-bucket
+// segments first, 8 after that -- then the tree sums.  A small bucket set (a sharded rank's share, a single small
+// MSM) is latency-bound from the start and goes straight to the tree sums.
+static void job_plan_reduce(const tp_ctx* ctx, MsmJob& j) {
   static const unsigned env_l1 = env_uint("TP_MSM_REDUCE_L1", 0);   // 1: no running-sum level, 2: as many as fit
   const unsigned l1_mode = ctx->msm_reduce_l1 ? ctx->msm_reduce_l1 : env_l1;
-  unsigned m_level[WSUM_MAX_LEVELS + 1], seg_level[WSUM_MAX_LEVELS + 1];
   int nl = 0;
-  m_level[0] = pl.nbuck;
-  seg_level[0] = 1;
+  j.m_level[0] = j.pl.nbuck;
+  j.seg_level[0] = 1;
   while (nl < WSUM_MAX_LEVELS) {
     const unsigned sg = nl == 0 ? WSUM_S_FIRST : WSUM_S_NEXT;
-    if (m_level[nl] < 2 * sg || l1_mode == 1) break;
-    if (l1_mode != 2 && (size_t)nsets_total * m_level[nl] < ((size_t)1 << (nl == 0 ? 19 : 18))) break;
-    seg_level[nl + 1] = sg;
-    m_level[nl + 1] = m_level[nl] / sg;
+    if (j.m_level[nl] < 2 * sg || l1_mode == 1) break;
+    if (l1_mode != 2 && (size_t)j.nsets_total * j.m_level[nl] < ((size_t)1 << (nl == 0 ? 19 : 18))) break;
+    j.seg_level[nl + 1] = sg;
+    j.m_level[nl + 1] = j.m_level[nl] / sg;
     nl++;
   }
-  const unsigned m_rc = m_level[nl];   // length of the array the row / column sums run over
+  j.nl = nl;
+  const unsigned m_rc = j.m_level[nl];   // length of the array the row / column sums run over
   unsigned log_m = 0;
   while ((1u << log_m) < m_rc) log_m++;
-  const unsigned bC = (log_m + 1) / 2, bD = log_m - bC;
-  const unsigned cols = 1u << bC, rows = 1u << bD;
-  const unsigned total_masks = 1 + bD + bC + (unsigned)nl;   // [P, bits of D, bits of C, T_1 .. T_nl]
+  j.bC = (log_m + 1) / 2;
+  j.bD = log_m - j.bC;
+  j.cols = 1u << j.bC;
+  j.rows = 1u << j.bD;
+  j.total_masks = 1 + j.bD + j.bC + (unsigned)nl;   // [P, bits of D, bits of C, T_1 .. T_nl]
   // the t array of level l (m_level[l] entries per set) only needs its plain sum: first per run of tcount[l] entries
-  unsigned tcount[WSUM_MAX_LEVELS + 1], tjobs[WSUM_MAX_LEVELS + 1];
-  size_t slab = (size_t)nsets_total * (rows + cols);
   for (int l = 1; l <= nl; l++) {
-    tcount[l] = m_level[l] > 256 ? 256u : m_level[l];
-    tjobs[l] = m_level[l] / tcount[l];
-    slab += 2 * (size_t)nsets_total * m_level[l] + (size_t)nsets_total * tjobs[l];
+    j.tcount[l] = j.m_level[l] > 256 ? 256u : j.m_level[l];
+    j.tjobs[l] = j.m_level[l] / j.tcount[l];
   }
-  TP_TRY(ensure(ctx, ctx->msm_seg, slab * sizeof(G1Xyzz)));
-  TP_TRY(ensure(ctx, ctx->msm_winsums, (size_t)nsets_total * total_masks * sizeof(G1Xyzz)));
-  if ((size_t)nsets_total * total_masks * sizeof(G1Xyzz) > ctx->pinned_cap)
-    return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
+}
+
+// ---- stage 3: bucket reduction -- running-sum levels on the accumulate stream, tree sums on the tail stream -------
+static int job_reduce(tp_ctx* ctx, MsmPipe* p, MsmJob& j) {
+  j.reduce_queued = true;
+  if (j.empty) return TP_OK;
+  MsmLane& ln = p->lane[j.lane];
+  const unsigned nsets_total = j.nsets_total;
+  const int nl = j.nl;
+  const unsigned rows = j.rows, cols = j.cols, bD = j.bD, bC = j.bC, total_masks = j.total_masks;
+  const unsigned m_rc = j.m_level[nl];
+  size_t slab = (size_t)nsets_total * (rows + cols);
+  for (int l = 1; l <= nl; l++) slab += 2 * (size_t)nsets_total * j.m_level[l] + (size_t)nsets_total * j.tjobs[l];
+  TP_TRY(ensure_idle(ctx, ln.seg, slab * sizeof(G1Xyzz)));
+  G1Xyzz* cursor = (G1Xyzz*)ln.seg.p;
+  const G1Xyzz* cur_in = (const G1Xyzz*)ln.buckets.p;
+  const unsigned* cur_hist = (const unsigned*)ln.hist.p;
+  const G1Xyzz* t_arr[WSUM_MAX_LEVELS + 1] = {nullptr};
+  {
+    StreamSwap sw(ctx, pipe_acc_stream(ctx, p));
+    TP_TRY(pipe_wait(ctx, p, ctx->stream, ln.ev_fix));
+    {
+      ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
+      for (int l = 1; l <= nl; l++) {
+        const unsigned total_out = nsets_total * j.m_level[l];
+        G1Xyzz* r_out = cursor;
+        G1Xyzz* t_out = cursor + total_out;
+        cursor += 2 * (size_t)total_out;
+        k_msm_wsum_level<<<(total_out + 127) / 128, 128, 0, ctx->stream>>>(cur_in, cur_hist, j.m_level[l - 1], j.seg_level[l],
+                                                                           total_out, r_out, t_out);
+        TP_LAUNCH(ctx, "k_msm_wsum_level");
+        cur_in = r_out;
+        cur_hist = nullptr;
+        t_arr[l] = t_out;
+      }
+    }
+    if (nl > 0) TP_TRY(pipe_record(ctx, p, ln.ev_wsum, ctx->stream));
+  }
+  StreamSwap sw(ctx, pipe_tail_stream(ctx, p));
+  TP_TRY(pipe_wait(ctx, p, ctx->stream, nl > 0 ? ln.ev_wsum : ln.ev_fix));
   {
     ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
-    if (m_total == 0) {
-      // a sharded rank that owns none of the digits: its buckets are all empty (the histogram says so)
-    } else if (pair_path) {
-      k_msm_pair_fixup<<<(nchunks + 127) / 128, 128, 0, ctx->stream>>>((const unsigned*)ctx->msm_part_keys.p,
-                                                                       (const G1Xyzz*)ctx->msm_part_pts.p, nchunks, buckets);
-      TP_LAUNCH(ctx, "k_msm_pair_fixup");
-    } else {
-      unsigned* ka = (unsigned*)ctx->msm_part_keys.p;
-      G1Xyzz* pa = (G1Xyzz*)ctx->msm_part_pts.p;
-      unsigned* kb = ka + 2 * (size_t)nchunks;
-      G1Xyzz* pb = pa + 2 * (size_t)nchunks;
-      unsigned nslots = 2 * nchunks;
-      while (nslots > 2 * MERGE_B) {
-        unsigned nth = (nslots + MERGE_B - 1) / MERGE_B;
-        k_msm_merge_level<<<(nth + 127) / 128, 128, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 0);
-        TP_LAUNCH(ctx, "k_msm_merge_level");
-        std::swap(ka, kb);
-        std::swap(pa, pb);
-        nslots = 2 * nth;
-      }
-      k_msm_merge_level<<<1, 32, 0, ctx->stream>>>(ka, pa, nslots, buckets, kb, pb, 1);
-      TP_LAUNCH(ctx, "k_msm_merge_level");
-    }
-    G1Xyzz* cursor = (G1Xyzz*)ctx->msm_seg.p;
-    const G1Xyzz* cur_in = buckets;
-    const unsigned* cur_hist = hist;
-    const G1Xyzz* t_arr[WSUM_MAX_LEVELS + 1] = {nullptr};
-    for (int l = 1; l <= nl; l++) {
-      const unsigned total_out = nsets_total * m_level[l];
-      G1Xyzz* r_out = cursor;
-      G1Xyzz* t_out = cursor + total_out;
-      cursor += 2 * (size_t)total_out;
-      k_msm_wsum_level<<<(total_out + 127) / 128, 128, 0, ctx->stream>>>(cur_in, cur_hist, m_level[l - 1], seg_level[l],
-                                                                         total_out, r_out, t_out);
-      TP_LAUNCH(ctx, "k_msm_wsum_level");
-      cur_in = r_out;
-      cur_hist = nullptr;
-      t_arr[l] = t_out;
-    }
     G1Xyzz* D = cursor;
     G1Xyzz* C = D + (size_t)nsets_total * rows;
     cursor = C + (size_t)nsets_total * cols;
     G1Xyzz* TPs[WSUM_MAX_LEVELS + 1] = {nullptr};
     for (int l = 1; l <= nl; l++) {
       TPs[l] = cursor;
-      cursor += (size_t)nsets_total * tjobs[l];
+      cursor += (size_t)nsets_total * j.tjobs[l];
     }
     auto add_task = [](TreeTasks& tt, const G1Xyzz* src, const unsigned* h, G1Xyzz* dst, size_t set_stride, unsigned dst_set_stride,
                        unsigned njobs, unsigned job_stride, unsigned count, unsigned stride, int bit) {
@@ -1428,18 +1681,17 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     memset(&ta, 0, sizeof(ta));
     add_task(ta, cur_in, cur_hist, D, m_rc, rows, rows, cols, cols, 1, -1);
     add_task(ta, cur_in, cur_hist, C, m_rc, cols, cols, 1, rows, cols, -1);
-    for (int l = 1; l <= nl; l++) add_task(ta, t_arr[l], nullptr, TPs[l], m_level[l], tjobs[l], tjobs[l], tcount[l], tcount[l], 1, -1);
+    for (int l = 1; l <= nl; l++) add_task(ta, t_arr[l], nullptr, TPs[l], j.m_level[l], j.tjobs[l], j.tjobs[l], j.tcount[l], j.tcount[l], 1, -1);
     k_msm_treesum<<<dim3(ta.first[ta.ntasks], nsets_total), TS_THREADS, 0, ctx->stream>>>(ta);
     TP_LAUNCH(ctx, "k_msm_treesum");
-    // stage B: one slot each -- P, the bit sums of D and of C, the totals of the t arrays.  The bit sums are single jobs
-
-    G1Xyzz* fin = (G1Xyzz*)ctx->msm_winsums.p;
+    // stage B: one slot each -- P, the bit sums of D and of C, the totals of the t arrays
+    G1Xyzz* fin = (G1Xyzz*)ctx->msm_winsums.p + j.win_off;
     struct Slot { const G1Xyzz* src; size_t set_stride; unsigned count; int bit; };
     std::vector<Slot> slots;
     slots.push_back({D, rows, rows, -1});
     for (unsigned k = 0; k < bD; k++) slots.push_back({D, rows, rows, (int)k});
     for (unsigned k = 0; k < bC; k++) slots.push_back({C, cols, cols, (int)k});
-    for (int l = 1; l <= nl; l++) slots.push_back({TPs[l], tjobs[l], tjobs[l], -1});
+    for (int l = 1; l <= nl; l++) slots.push_back({TPs[l], j.tjobs[l], j.tjobs[l], -1});
     for (size_t s0 = 0; s0 < slots.size(); s0 += TS_MAX_TASKS) {
       TreeTasks tb;
       memset(&tb, 0, sizeof(tb));
@@ -1449,26 +1701,127 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
       TP_LAUNCH(ctx, "k_msm_treesum");
     }
   }
-  // Sharded: the ranks' reduction outputs meet on the device -- all-gather on the stream, one combine kernel -- and the
-  // host reads back one buffer, as on a single GPU.  Row of a set: [slots 1.. summed over ranks | P of every rank].
-  const unsigned width = world > 1 ? total_masks - 1 + world : total_masks;
-  const G1Xyzz* final_dev = (const G1Xyzz*)ctx->msm_winsums.p;
-  if (world > 1) {
-    ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
-    const size_t per_rank = (size_t)nsets_total * total_masks * sizeof(G1Xyzz);
-    TP_TRY(ensure(ctx, ctx->msm_gather, per_rank * world + (size_t)nsets_total * width * sizeof(G1Xyzz)));
-    G1Xyzz* gathered = (G1Xyzz*)ctx->msm_gather.p;
-    G1Xyzz* combined = gathered + (size_t)world * nsets_total * total_masks;
-    TP_TRY(comm_allgather(ctx, ctx->msm_winsums.p, gathered, per_rank));
-    k_msm_combine<<<nsets_total * total_masks, 32, 0, ctx->stream>>>(gathered, world, nsets_total, total_masks, combined);
-    TP_LAUNCH(ctx, "k_msm_combine");
-    final_dev = combined;
+  TP_TRY(pipe_record(ctx, p, ln.ev_done, ctx->stream));
+  return TP_OK;
+}
+
+static int pipe_submit(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, int batch, size_t len) {
+  MsmPipe* p = nullptr;
+  TP_TRY(pipe_get(ctx, &p));
+  if (batch <= 0 || batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: bad batch size");
+  if (p->results + batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many results queued");
+  if (len >= ((size_t)1 << 27)) return fail(ctx, TP_ERR_INVALID_ARG, "msm: more than 2^27 points per call");
+  const unsigned world = ctx->world > 1 ? (unsigned)ctx->world : 1u;
+  const MsmPlan pl = msm_plan(srs, world);
+  if ((size_t)pl.nwin * len * batch >= ((size_t)1 << 31) || (size_t)pl.nsets * pl.nbuck * batch >= ((size_t)1 << 30)) {
+    if (batch == 1) return fail(ctx, TP_ERR_INVALID_ARG, "msm: too many window entries");
+    const int half = batch / 2;  // split the batch until the entry count fits 31 bits
+    TP_TRY(pipe_submit(ctx, srs, scalars, half, len));
+    return pipe_submit(ctx, srs, scalars + half, batch - half, len);
   }
-  if ((size_t)nsets_total * width * sizeof(G1Xyzz) > ctx->pinned_cap) return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
-  TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, final_dev, (size_t)nsets_total * width * sizeof(G1Xyzz), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-  TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  // serial tail on the host
+  if (p->jobs.empty()) {   // first job of a batch fixes the mode
+    p->overlap = msm_pipe_overlaps(ctx, len);
+    if (p->overlap) TP_TRY(pipe_streams(ctx, p));
+    p->win_used = 0;
+    p->results = 0;
+    if (!ctx->msm_winsums.p) TP_TRY(ensure(ctx, ctx->msm_winsums, ctx->pinned_cap));
+  }
+  MsmJob j;
+  j.lane = p->next_lane;
+  p->next_lane = (p->next_lane + 1) % MSM_LANES;
+  j.batch = batch;
+  j.len = len;
+  j.srs = srs;
+  j.pl = pl;
+  j.nsets_total = pl.nsets * (unsigned)batch;
+  j.nkeys = (size_t)j.nsets_total * pl.nbuck;
+  j.first_result = p->results;
+  p->results += batch;
+  job_plan_reduce(ctx, j);
+  j.win_off = p->win_used;
+  p->win_used += (size_t)j.nsets_total * j.total_masks;
+  // sharded, the host reads [slots 1.. summed over ranks | P of every rank] per set: world - 1 slots more than a rank writes
+  size_t host_slots = 0;
+  for (auto& q : p->jobs) host_slots += (size_t)q.nsets_total * (q.total_masks - 1 + world);
+  j.host_off = world > 1 ? host_slots : j.win_off;
+  host_slots += (size_t)j.nsets_total * (j.total_masks - 1 + world);
+  if (p->win_used * sizeof(G1Xyzz) > ctx->msm_winsums.cap || host_slots * sizeof(G1Xyzz) > ctx->pinned_cap)
+    return fail(ctx, TP_ERR_INVALID_ARG, "msm: staging buffer too small");
+  if (len == 0) {
+    j.empty = true;
+    j.reduce_queued = true;
+    p->jobs.push_back(j);
+    return TP_OK;
+  }
+  MsmLane& ln = p->lane[j.lane];
+  if (p->overlap) {
+    // the scalars are final on the context's stream; the lane's buffers are free once its previous job has finished
+    TP_CUDA_OK(ctx, cudaEventRecord(p->ev_in, ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamWaitEvent(p->s_sort, p->ev_in, 0));
+    if (ln.busy) TP_CUDA_OK(ctx, cudaStreamWaitEvent(p->s_sort, ln.ev_done, 0));
+  }
+  TP_TRY(job_sort(ctx, p, j, scalars));
+  if (p->overlap) TP_CUDA_OK(ctx, cudaEventSynchronize(ln.ev_sorted));
+  else TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  j.m_total = p->counts[2 * j.lane];
+  j.max_bucket = p->counts[2 * j.lane + 1];
+  if (j.m_total == 0 && world == 1) {   // all scalars zero (a sharded rank still takes part in the exchange)
+    j.empty = true;
+    j.reduce_queued = true;
+    p->jobs.push_back(j);
+    return TP_OK;
+  }
+  TP_TRY(job_accumulate(ctx, p, j));
+  ln.busy = p->overlap;
+  // the reduction of the job before this one goes behind this job's accumulation (see the timeline above)
+  if (p->overlap) {
+    for (auto& q : p->jobs)
+      if (!q.reduce_queued) TP_TRY(job_reduce(ctx, p, q));
+  } else {
+    TP_TRY(job_reduce(ctx, p, j));
+  }
+  p->jobs.push_back(j);
+  return TP_OK;
+}
+
+static int pipe_finish(tp_ctx* ctx, tph::HG1* results, int count) {
+  MsmPipe* p = ctx->msm_pipe;
+  if (!p || p->results != count) return fail(ctx, TP_ERR_INVALID_ARG, "msm: finish does not match what was submitted");
+  for (int b = 0; b < count; b++) results[b] = tph::HG1::identity();
+  const unsigned world = ctx->world > 1 ? (unsigned)ctx->world : 1u;
+  for (auto& q : p->jobs)
+    if (!q.reduce_queued) TP_TRY(job_reduce(ctx, p, q));
+  bool any = false;
+  for (auto& q : p->jobs) any = any || !q.empty;
+  if (any) {
+    StreamSwap sw(ctx, pipe_tail_stream(ctx, p));
+    // Sharded: the ranks' reduction outputs meet on the device -- one all-gather on the stream for the whole batch, one
+    // combine kernel per job -- and the host reads back one buffer, as on a single GPU.
+    const G1Xyzz* final_dev = (const G1Xyzz*)ctx->msm_winsums.p;
+    size_t final_slots = p->win_used;
+    if (world > 1) {
+      ProfScope prof(ctx, TP_PHASE_MSM_REDUCE);
+      const size_t per_rank = p->win_used * sizeof(G1Xyzz);
+      size_t host_slots = 0;
+      for (auto& q : p->jobs) host_slots += (size_t)q.nsets_total * (q.total_masks - 1 + world);
+      TP_TRY(ensure_idle(ctx, ctx->msm_gather, per_rank * world + host_slots * sizeof(G1Xyzz)));
+      G1Xyzz* gathered = (G1Xyzz*)ctx->msm_gather.p;
+      G1Xyzz* combined = gathered + (size_t)world * p->win_used;
+      TP_TRY(comm_allgather(ctx, ctx->msm_winsums.p, gathered, per_rank));
+      for (auto& q : p->jobs) {
+        if (q.empty) continue;
+        k_msm_combine<<<q.nsets_total * q.total_masks, 32, 0, ctx->stream>>>(gathered + q.win_off, world, (unsigned)p->win_used,
+                                                                             q.total_masks, combined + q.host_off);
+        TP_LAUNCH(ctx, "k_msm_combine");
+      }
+      final_dev = combined;
+      final_slots = host_slots;
+    }
+    TP_CUDA_OK(ctx, cudaMemcpyAsync(ctx->pinned, final_dev, final_slots * sizeof(G1Xyzz), cudaMemcpyDeviceToHost, ctx->stream));
+    TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  for (auto& l : p->lane) l.busy = false;   // the tail stream has seen every job's last kernel
+  // serial tails on the host
   const uint8_t* ws = (const uint8_t*)ctx->pinned;
   auto raw_point = [&](size_t index) {
     const uint8_t* q = ws + index * 192;
@@ -1479,11 +1832,14 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
     memcpy(zzz.v, q + 144, 48);
     return tph::g1_from_xyzz(x, y, zz, zzz);
   };
-  // slot >= 1 of a set (summed over ranks when sharded)
-  auto point = [&](unsigned set, unsigned slot) { return raw_point((size_t)set * width + (world > 1 ? slot - 1 : slot)); };
   // one bucket set's tail is ~40 dependent group operations of single-thread host arithmetic (~0.1 ms); the sets of a
-  // batch are independent, so every batch element beyond the first gets its own thread
-  auto tail = [&](int b) {
+  // batch are independent, so every result beyond the first gets its own thread
+  auto tail = [&](const MsmJob* jp, int b) {
+    const MsmJob& j = *jp;
+    const MsmPlan& pl = j.pl;
+    const unsigned width = world > 1 ? j.total_masks - 1 + world : j.total_masks;
+    // slot >= 1 of a set (summed over ranks when sharded)
+    auto point = [&](unsigned set, unsigned slot) { return raw_point(j.host_off + (size_t)set * width + (world > 1 ? slot - 1 : slot)); };
     tph::HG1 acc = tph::HG1::identity();
     for (int q = (int)pl.nsets - 1; q >= 0; q--) {
       if (q != (int)pl.nsets - 1)
@@ -1499,15 +1855,15 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
         }
         return v;
       };
-      tph::HG1 f = bits(1, bD);
-      for (unsigned d = 0; d < bC; d++) f = tph::g1_dbl(f);
-      f = tph::g1_add(f, bits(1 + bD, bC));
-      for (int l = nl; l >= 1; l--) {  // F(level l-1) = T_l + S_l * F(level l)
-        for (unsigned d = 1; d < seg_level[l]; d <<= 1) f = tph::g1_dbl(f);
-        f = tph::g1_add(f, point(set, 1 + bD + bC + (unsigned)(l - 1)));
+      tph::HG1 f = bits(1, j.bD);
+      for (unsigned d = 0; d < j.bC; d++) f = tph::g1_dbl(f);
+      f = tph::g1_add(f, bits(1 + j.bD, j.bC));
+      for (int l = j.nl; l >= 1; l--) {  // F(level l-1) = T_l + S_l * F(level l)
+        for (unsigned d = 1; d < j.seg_level[l]; d <<= 1) f = tph::g1_dbl(f);
+        f = tph::g1_add(f, point(set, 1 + j.bD + j.bC + (unsigned)(l - 1)));
       }
       if (world == 1) {
-        f = tph::g1_add(f, raw_point((size_t)set * width));   // V = F + P
+        f = tph::g1_add(f, raw_point(j.host_off + (size_t)set * width));   // V = F + P
       } else {
         // local bucket j of rank r is global bucket world * j + r, which counts (world * j + r + 1) times:
         // V = world * F(summed over ranks) + sum_r (r + 1) P_r, the latter by running sums
@@ -1518,37 +1874,118 @@ static int msm_local(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars, i
         }
         tph::HG1 run = tph::HG1::identity(), pw = tph::HG1::identity();
         for (int r = (int)world - 1; r >= 0; r--) {
-          run = tph::g1_add(run, raw_point((size_t)set * width + (total_masks - 1) + (unsigned)r));
+          run = tph::g1_add(run, raw_point(j.host_off + (size_t)set * width + (j.total_masks - 1) + (unsigned)r));
           pw = tph::g1_add(pw, run);
         }
         f = tph::g1_add(wf, pw);
       }
       acc = tph::g1_add(acc, f);
     }
-    results[b] = acc;
+    results[j.first_result + b] = acc;
   };
+  std::vector<std::pair<const MsmJob*, int>> work;
+  for (auto& q : p->jobs)
+    if (!q.empty)
+      for (int b = 0; b < q.batch; b++) work.push_back({&q, b});
   std::vector<std::future<void>> others;
-  int b_next = 1;
+  size_t w_next = 1;
   try {
-    for (; b_next < batch; b_next++) others.push_back(std::async(std::launch::async, tail, b_next));
+    for (; w_next < work.size(); w_next++) others.push_back(std::async(std::launch::async, tail, work[w_next].first, work[w_next].second));
   } catch (const std::system_error&) {  // no more threads to be had: the rest runs here
   }
-  tail(0);
-  for (int b = b_next; b < batch; b++) tail(b);
+  if (!work.empty()) tail(work[0].first, work[0].second);
+  for (size_t w = w_next; w < work.size(); w++) tail(work[w].first, work[w].second);
   for (auto& f : others) f.get();
+  p->jobs.clear();
+  p->win_used = 0;
+  p->results = 0;
   return TP_OK;
 }
 
+int msm_pipe_submit(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len) {
+  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
+  if (ctx->world > 1 && !comm_ready(ctx)) return fail(ctx, TP_ERR_COLLECTIVE, "msm: sharded context without a communicator");
+  MsmPipe* p = nullptr;
+  TP_TRY(pipe_get(ctx, &p));
+  const bool first = p->jobs.empty();
+  const bool overlap = first ? msm_pipe_overlaps(ctx, len) : p->overlap;
+  int rc;
+  if (overlap) {   // the work spreads over the pipe's streams: the total runs from here to the end of finish
+    if (first && ctx->prof && !p->total) p->total = new ProfScope(ctx, TP_PHASE_MSM_TOTAL);
+    rc = pipe_submit(ctx, srs, scalars_dev, batch, len);
+  } else {
+    ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
+    rc = pipe_submit(ctx, srs, scalars_dev, batch, len);
+  }
+  if (rc != TP_OK) pipe_abort(ctx);
+  return rc;
+}
+int msm_pipe_finish(tp_ctx* ctx, uint8_t (*out)[TP_G1_BYTES], int count) {
+  if (count < 0 || count > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: bad result count");
+  tph::HG1 res[MSM_MAX_BATCH];
+  MsmPipe* p = ctx->msm_pipe;
+  int rc;
+  if (p && p->total) {
+    rc = pipe_finish(ctx, res, count);   // ends with the host waiting for the tail stream: everything has run
+    delete p->total;
+    p->total = nullptr;
+  } else {
+    ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
+    rc = pipe_finish(ctx, res, count);
+  }
+  if (rc != TP_OK) {
+    pipe_abort(ctx);
+    return rc;
+  }
+  encode_g1_batch(res, out, count);
+  return TP_OK;
+}
+
+// Sub-batch sizes of a batch run in one call: at most three jobs, the first the smallest (its sort is the one nothing
+// covers).  TP_MSM_PIPE_PARTS=a,b,c overrides for sweeps (missing or short: equal parts).
+static int msm_split(int batch, int parts[MSM_LANES]) {
+  static const char* env = getenv("TP_MSM_PIPE_PARTS");
+  int n = batch < MSM_LANES ? batch : MSM_LANES;
+  for (int i = 0; i < n; i++) parts[i] = batch / n + (i >= n - batch % n ? 1 : 0);
+  if (env && *env) {
+    int v[MSM_LANES] = {0, 0, 0}, sum = 0, cnt = 0;
+    const char* s = env;
+    while (*s && cnt < MSM_LANES) {
+      v[cnt] = (int)strtol(s, (char**)&s, 10);
+      sum += v[cnt] > 0 ? v[cnt] : 0;
+      if (v[cnt] > 0) cnt++;
+      if (*s == ',') s++;
+      else break;
+    }
+    if (sum == batch && cnt > 0) {
+      for (int i = 0; i < cnt; i++) parts[i] = v[i];
+      n = cnt;
+    }
+  }
+  return n;
+}
+
+// `batch` MSMs over the first `len` bases: out[b] = sum_i scalars[b][i] * srs[i].  Overlapped, the batch is cut into
+// sub-batches (see "pipeline"); otherwise all scalar vectors share one sort / accumulate / merge / reduce pass (bucket
+// set index = b * nsets + q), which amortises the latency-bound reduction tail and the launch overhead.  On a sharded
+// context (world > 1) this rank handles the buckets it owns, the ranks' reduction outputs are all-gathered and combined
+// on the device (comm.cu, k_msm_combine) and every rank returns the complete sums.
 int msm_batch_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars_dev, int batch, size_t len,
                   uint8_t (*out)[TP_G1_BYTES]) {
-  if (len > srs->len) return fail(ctx, TP_ERR_SRS_TOO_SHORT, "commit: polynomial longer than the SRS");
   if (batch <= 0 || batch > MSM_MAX_BATCH) return fail(ctx, TP_ERR_INVALID_ARG, "msm: bad batch size");
-  ProfScope prof(ctx, TP_PHASE_MSM_TOTAL);
-  if (ctx->world > 1 && !comm_ready(ctx)) return fail(ctx, TP_ERR_COLLECTIVE, "msm: sharded context without a communicator");
-  tph::HG1 res[MSM_MAX_BATCH];
-  TP_TRY(msm_local(ctx, srs, scalars_dev, batch, len, res));
-  encode_g1_batch(res, out, batch);
-  return TP_OK;
+  if (ctx->msm_pipe && !ctx->msm_pipe->jobs.empty()) return fail(ctx, TP_ERR_INVALID_ARG, "msm: a submitted batch is still open");
+  if (msm_pipe_overlaps(ctx, len) && batch > 1) {
+    int parts[MSM_LANES];
+    const int n = msm_split(batch, parts);
+    int at = 0;
+    for (int i = 0; i < n; i++) {
+      TP_TRY(msm_pipe_submit(ctx, srs, scalars_dev + at, parts[i], len));
+      at += parts[i];
+    }
+  } else {
+    TP_TRY(msm_pipe_submit(ctx, srs, scalars_dev, batch, len));
+  }
+  return msm_pipe_finish(ctx, out, batch);
 }
 
 int msm_dev(tp_ctx* ctx, const tp_srs* srs, const Fr* scalars_dev, size_t len, uint8_t out[TP_G1_BYTES]) {
