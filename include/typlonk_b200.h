@@ -104,10 +104,11 @@ int tp_ctx_group_size(const tp_ctx* ctx, int* ndev, int* uses_nccl);
  *       points before the XYZZ accumulation (kept for comparison; see profiles/);
  *   "msm_reduce_l1" (0 = by size, 1 = never, 2 = whenever possible): whether the bucket reduction runs a level of
  *       16-bucket running sums before its row / column tree sums (big bucket sets: yes; small / sharded ones: no);
- *   "msm_pipeline" (0 = never, 1 = on sharded contexts [default], 2 = always; $TP_MSM_PIPELINE): run a batch of MSMs as
+ *   "msm_pipeline" (0 = never [default], 1 = on sharded contexts, 2 = always; $TP_MSM_PIPELINE): run a batch of MSMs as
  *       sub-batches on three streams of the library's own, so that the sort and the latency-bound reduction tails of
  *       one sub-batch run under the accumulation of its neighbours; "msm_pipe_min_log" (default 15): only for inputs
- *       of at least 2^this points;
+ *       of at least 2^this points.  Measured slower than the one-stream order on 1 and on 8 B200s (the accumulation
+ *       fills every SM's register file, a second kernel only gets slots as its blocks retire): kept as an experiment;
  *   "msm_acc_staged" (0/1): the accumulation kernel fetches the next table point into shared memory with cp.async
  *       while the current addition runs;
  *   "quotient_all_cosets" (0/1): evaluate the quotient numerator on all four cosets of the 4n domain even when it is

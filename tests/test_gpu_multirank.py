@@ -150,9 +150,7 @@ def test_msm_pipeline_same_bytes(ctx, world):
     n = 1 << log_n
     plain = synthetic.mul_chain_direct(ctx, log_n)
     cols = [F.fr_vec_to_bytes(c) for c in synthetic.mul_chain_witness(n - 3, n)]
-    ctx.set_option("msm_pipeline", 0)
     want = plain.handle.prove(cols, bytes(32 * n))
-    ctx.set_option("msm_pipeline", 1)
     g = ctx if world == 1 else Context.multi([0] * world)
     try:
         circuit = plain if world == 1 else synthetic.mul_chain_direct(g, log_n)
@@ -172,14 +170,13 @@ def test_msm_pipeline_same_bytes(ctx, world):
         rnd = random.Random(11)
         vecs = {"zeros": [0] * m, "same": [12345] * m, "top": [F.R_MOD - 1] * m,
                 "uniform": [rnd.randrange(F.R_MOD) for _ in range(m)]}
-        ctx.set_option("msm_pipeline", 0)
         expect = {name: ctx.commit(ref, F.fr_vec_to_bytes(vec)) for name, vec in vecs.items()}
         g.set_option("msm_pipeline", 2)
         g.set_option("msm_pipe_min_log", 0)
         for name, vec in vecs.items():
             assert g.commit(srs, F.fr_vec_to_bytes(vec)) == expect[name], name
     finally:
-        g.set_option("msm_pipeline", 1)
+        g.set_option("msm_pipeline", 0)
         g.set_option("msm_pipe_min_log", 15)
         g.set_option("msm_acc_staged", 0)
         if world != 1:

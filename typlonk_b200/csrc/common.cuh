@@ -56,8 +56,8 @@ struct tp_ctx {
   unsigned msm_affine_chains = 0;  // bucket accumulation in affine coordinates with per-thread batched inversion (msm.cu 4c)
   unsigned msm_reduce_l1 = 0;     // bucket reduction's running-sum level: 0 by size, 1 never, 2 whenever the set allows it
   unsigned quotient_all_cosets = 0;  // 1: evaluate the quotient numerator on all four cosets even when it is known to vanish on H
-  unsigned msm_pipeline = 1;      // MSM batches as overlapped sub-batches on the pipe's own streams (msm.cu, "pipeline"):
-                                  // 0 never, 1 on sharded contexts, 2 always
+  unsigned msm_pipeline = 0;      // MSM batches as overlapped sub-batches on the pipe's own streams (msm.cu, "pipeline"):
+                                  // 0 never (default: measured slower on 1 and on 8 GPUs), 1 on sharded contexts, 2 always
   unsigned msm_pipe_min_log = 15; // ... for inputs of at least 2^this points (tests lower it to reach the path with small circuits)
   unsigned msm_acc_staged = 0;    // 1: the accumulation stages the next table point in shared memory with cp.async
   // work counters (tp_ctx_get_stat)

@@ -1277,10 +1277,11 @@ bool msm_pipe_overlaps(const tp_ctx* ctx, size_t len) {
   const unsigned min_log = env_min_log ? env_min_log : ctx->msm_pipe_min_log;
   static const bool env_off = getenv("TP_MSM_PIPELINE") && *getenv("TP_MSM_PIPELINE") == '0';
   static const bool env_all = getenv("TP_MSM_PIPELINE") && *getenv("TP_MSM_PIPELINE") == '2';
-  // On one GPU the accumulation fills every SM's register file: a second kernel only gets slots as accumulation blocks
-  // retire, so the "overlapped" sort runs no sooner than it would alone, and the smaller sub-batches reduce less
-  // efficiently (2^20: 84.2 ms against 82.2, profiles/r2_summary.md I).  A sharded rank's accumulation leaves SMs free
-  // and the latency-bound stages are a larger share: there the pipe is on by default (1); 2 forces it everywhere.
+  // Off unless asked for.  The accumulation fills every SM's register file (3 x 128 threads x 168 registers) and the
+  // planner sizes a sharded rank's chunks so that its smaller grid still covers the whole GPU: a second kernel only
+  // gets slots as accumulation blocks retire, so the "overlapped" sort runs no sooner than it would alone, while the
+  // smaller sub-batches reduce less efficiently.  2^20 gates: 84.2 ms against 82.2 on one B200, 18.1 against 16.7 on
+  // eight; 2^22 on eight: 54.2 against 52.4 (profiles/r2_summary.md I).
   const bool want = ctx->msm_pipeline == 2 || env_all || (ctx->msm_pipeline == 1 && ctx->world > 1);
   return want && !env_off && ctx->msm_aff_rounds == 0 && ctx->msm_affine_chains == 0 && len >= ((size_t)1 << min_log);
 }
@@ -1727,8 +1728,10 @@ static int pipe_submit(tp_ctx* ctx, const tp_srs* srs, const Fr* const* scalars,
     if (!ctx->msm_winsums.p) TP_TRY(ensure(ctx, ctx->msm_winsums, ctx->pinned_cap));
   }
   MsmJob j;
-  j.lane = p->next_lane;
-  p->next_lane = (p->next_lane + 1) % MSM_LANES;
+  // one stream: a job has left its lane's buffers behind (in stream order) by the time the next one is queued, so
+  // lane 0 serves them all -- the other lanes are only ever allocated by an overlapped batch
+  j.lane = p->overlap ? p->next_lane : 0;
+  if (p->overlap) p->next_lane = (p->next_lane + 1) % MSM_LANES;
   j.batch = batch;
   j.len = len;
   j.srs = srs;
