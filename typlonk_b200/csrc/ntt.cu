@@ -124,9 +124,9 @@ static __device__ __noinline__ Fr ntt_mul(Fr a, Fr b) { return fr_mul(a, b); }
 __device__ __forceinline__ Fr ntt_mul(const Fr& a, const Fr& b) { return fr_mul(a, b); }
 #endif
 
-template <int D0, int NST, bool TRIV>
+template <int D0, int NST, bool TRIV, bool INVERSE>
 __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw, unsigned A, unsigned sh, unsigned L,
-                                          bool inverse, unsigned half_n) {
+                                          unsigned half_n) {
 #pragma unroll
   for (int d = D0; d < D0 + NST; d++) {
     const unsigned base_idx = A << (sh - d);
@@ -141,12 +141,11 @@ __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw,
         x[e1] = fr_sub(u, v);
       } else {
         const unsigned idx = base_idx + (q << (L - d - 1));
-        const Fr w = fr_load(tw + (inverse ? half_n - idx : idx));
+        const Fr w = fr_load(tw + (INVERSE ? half_n - idx : idx));
         const Fr t = ntt_mul(w, x[e1]);
         const Fr u = x[e0];
-        const Fr p = fr_add(u, t), m = fr_sub(u, t);
-        x[e0] = inverse ? m : p;   // mirrored table entry is -omega^-idx
-        x[e1] = inverse ? p : m;
+        x[e0] = INVERSE ? fr_sub(u, t) : fr_add(u, t);   // mirrored table entry is -omega^-idx
+        x[e1] = INVERSE ? fr_add(u, t) : fr_sub(u, t);
       }
     }
   }
@@ -155,6 +154,11 @@ __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw,
 #define NTT_MAX_TILE_LOG 11
 #define NTT_SMEM_BYTES ((2u << NTT_MAX_TILE_LOG) * 16u)
 
+// FIRST: first pass of a transform (bit-reversed gather, coset scaling on the way in, trivial twiddles in the first
+// round); INVERSE: mirrored twiddles, scaling on the way out.  Compile-time, so that a kernel carries ONE copy of the
+// full three-stage round in its round loop (12 butterflies; the first pass also its 5-product first round) instead of
+// one per place a round is used, and no per-limb selects on the direction.
+template <bool FIRST, bool INVERSE>
 __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
   extern __shared__ uint4 ntt_sh[];
   const unsigned T = 1u << (a.k + a.cw);
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
   Fr* out = a.out[blockIdx.y];
   const Fr* coset = a.coset[blockIdx.y];
   unsigned base = 0, lo_val = 0;
-  if (!a.first) {
+  if (!FIRST) {
     const unsigned hi_idx = blockIdx.x >> (a.s0 - a.cw);
     const unsigned lo_grp = blockIdx.x & ((1u << (a.s0 - a.cw)) - 1);
     base = (hi_idx << (a.s0 + a.k)) + (lo_grp << a.cw) + l;
@@ -176,66 +180,70 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
     base = (blockIdx.x << a.cw) + l;
   }
   Fr x[8];
-  // ---- first round: operands straight from global memory (field base 0: m = rho * 8 + e) ----
-#pragma unroll
-  for (int e = 0; e < 8; e++) {
-    const unsigned m = (rho << 3) | e;
-    const unsigned g = a.first ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
-    x[e] = fr_load(in + g);
-    if (a.first && coset && !a.inverse) x[e] = fr_mul(x[e], fr_load(coset + g));
-  }
-  if (a.first)
-    ntt_round<0, 3, true>(x, a.tw, 0u, a.L - 1, a.L, a.inverse, half_n);
-  else
-    ntt_round<0, 3, false>(x, a.tw, lo_val, a.L - a.s0 - 1, a.L, a.inverse, half_n);
-  // ---- further rounds: exchange through shared memory ----
   const unsigned rem = a.k % 3;
   unsigned f_prev = 0;
-  for (unsigned f = 3; f < a.k; f += 3) {
+  for (unsigned f = 0; f < a.k; f += 3) {
     const bool tail = f + 3 > a.k;          // fewer than three stages left: field sits at the top
     const unsigned fb = tail ? a.k - 3 : f;
-    {
-      const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
-      const unsigned i0 = (((m_hi << (f_prev + 3)) | m_lo) << a.cw) | l;
-      if (f_prev != 0) __syncthreads();     // the previous exchange has been read by everyone
+    if (f == 0) {
+      // ---- first round: operands straight from global memory (field base 0: m = rho * 8 + e) ----
 #pragma unroll
       for (int e = 0; e < 8; e++) {
-        const unsigned p = ntt_swz(i0 | ((unsigned)e << (f_prev + a.cw)));
-        s_lo[p] = make_uint4(x[e].v[0], x[e].v[1], x[e].v[2], x[e].v[3]);
-        s_hi[p] = make_uint4(x[e].v[4], x[e].v[5], x[e].v[6], x[e].v[7]);
+        const unsigned m = (rho << 3) | e;
+        const unsigned g = FIRST ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
+        x[e] = fr_load(in + g);
+        if (FIRST && !INVERSE && coset) x[e] = ntt_mul(x[e], fr_load(coset + g));
       }
-      __syncthreads();
-    }
-    const unsigned m_lo = rho & ((1u << fb) - 1), m_hi = rho >> fb;
-    const unsigned i0 = (((m_hi << (fb + 3)) | m_lo) << a.cw) | l;
+      if (FIRST) {
+        ntt_round<0, 3, true, INVERSE>(x, a.tw, 0u, a.L - 1, a.L, half_n);
+        continue;
+      }
+    } else {
+      // ---- further rounds: exchange through shared memory ----
+      {
+        const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
+        const unsigned i0 = (((m_hi << (f_prev + 3)) | m_lo) << a.cw) | l;
+        if (f_prev != 0) __syncthreads();     // the previous exchange has been read by everyone
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
-      const unsigned p = ntt_swz(i0 | ((unsigned)e << (fb + a.cw)));
-      const uint4 lo = s_lo[p], hi = s_hi[p];
-      x[e].v[0] = lo.x; x[e].v[1] = lo.y; x[e].v[2] = lo.z; x[e].v[3] = lo.w;
-      x[e].v[4] = hi.x; x[e].v[5] = hi.y; x[e].v[6] = hi.z; x[e].v[7] = hi.w;
+        for (int e = 0; e < 8; e++) {
+          const unsigned p = ntt_swz(i0 | ((unsigned)e << (f_prev + a.cw)));
+          s_lo[p] = make_uint4(x[e].v[0], x[e].v[1], x[e].v[2], x[e].v[3]);
+          s_hi[p] = make_uint4(x[e].v[4], x[e].v[5], x[e].v[6], x[e].v[7]);
+        }
+        __syncthreads();
+      }
+      const unsigned m_lo = rho & ((1u << fb) - 1), m_hi = rho >> fb;
+      const unsigned i0 = (((m_hi << (fb + 3)) | m_lo) << a.cw) | l;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const unsigned p = ntt_swz(i0 | ((unsigned)e << (fb + a.cw)));
+        const uint4 lo = s_lo[p], hi = s_hi[p];
+        x[e].v[0] = lo.x; x[e].v[1] = lo.y; x[e].v[2] = lo.z; x[e].v[3] = lo.w;
+        x[e].v[4] = hi.x; x[e].v[5] = hi.y; x[e].v[6] = hi.z; x[e].v[7] = hi.w;
+      }
     }
+    const unsigned m_lo = rho & ((1u << fb) - 1);
     const unsigned A = (m_lo << a.s0) + lo_val;
     const unsigned sh = a.L - a.s0 - fb - 1;
     if (!tail)
-      ntt_round<0, 3, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+      ntt_round<0, 3, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
     else if (rem == 1)
-      ntt_round<2, 1, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+      ntt_round<2, 1, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
     else
-      ntt_round<1, 2, false>(x, a.tw, A, sh, a.L, a.inverse, half_n);
+      ntt_round<1, 2, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
     f_prev = fb;
   }
   // ---- store from the last round's field ----
   {
     const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
     const unsigned m0 = (m_hi << (f_prev + 3)) | m_lo;
-    const unsigned obase = a.first ? (bitrev(base, a.L - a.k) << a.k) : base;
+    const unsigned obase = FIRST ? (bitrev(base, a.L - a.k) << a.k) : base;
 #pragma unroll
     for (int e = 0; e < 8; e++) {
       const unsigned m = m0 | ((unsigned)e << f_prev);
-      const unsigned g = a.first ? obase + m : obase + (m << a.s0);
+      const unsigned g = FIRST ? obase + m : obase + (m << a.s0);
       Fr y = x[e];
-      if (a.last && a.inverse) y = fr_mul(y, coset ? fr_load(coset + g) : a.ninv);
+      if (INVERSE && a.last) y = ntt_mul(y, coset ? fr_load(coset + g) : a.ninv);
       fr_store(out + g, y);
     }
   }
@@ -352,7 +360,10 @@ int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64
   }
   static bool smem_attr = false;
   if (!smem_attr) {
-    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
     smem_attr = true;
   }
   unsigned ks[8];
@@ -388,7 +399,12 @@ int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64
     a.last = (p == npass - 1);
     const unsigned T = 1u << (a.k + a.cw);
     const unsigned grid = (unsigned)(n >> (a.k + a.cw));
-    k_ntt_r8<<<dim3(grid, (unsigned)count), T / 8, 2 * T * sizeof(uint4), ctx->stream>>>(a);
+    const dim3 g3(grid, (unsigned)count);
+    const size_t smem = 2 * T * sizeof(uint4);
+    if (a.first && inverse) k_ntt_r8<true, true><<<g3, T / 8, smem, ctx->stream>>>(a);
+    else if (a.first) k_ntt_r8<true, false><<<g3, T / 8, smem, ctx->stream>>>(a);
+    else if (inverse) k_ntt_r8<false, true><<<g3, T / 8, smem, ctx->stream>>>(a);
+    else k_ntt_r8<false, false><<<g3, T / 8, smem, ctx->stream>>>(a);
     TP_LAUNCH(ctx, "k_ntt_r8");
     for (int i = 0; i < count; i++) src[i] = a.out[i];
     s0 += a.k;
