@@ -369,7 +369,7 @@ def main():
 
     # library tunables A/B-ed in this very process (same box, same clocks, same circuit): each variant is warmed up,
     # timed like the headline, byte-checked, and the defaults are restored
-    DEFAULTS = {"msm_pipeline": 0, "msm_acc_staged": 0, "msm_reduce_l1": 0, "quotient_all_cosets": 0}
+    DEFAULTS = {"ntt_radix_log": 2, "msm_pipeline": 0, "msm_acc_staged": 0, "msm_reduce_l1": 0, "quotient_all_cosets": 0}
     ab = []
     for spec in args.ab:
         opts = {k: int(v) for k, v in (kv.split("=") for kv in spec.split(","))}

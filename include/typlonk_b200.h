@@ -109,6 +109,9 @@ int tp_ctx_group_size(const tp_ctx* ctx, int* ndev, int* uses_nccl);
  *       one sub-batch run under the accumulation of its neighbours; "msm_pipe_min_log" (default 15): only for inputs
  *       of at least 2^this points.  Measured slower than the one-stream order on 1 and on 8 B200s (the accumulation
  *       fills every SM's register file, a second kernel only gets slots as its blocks retire): kept as an experiment;
+ *   "ntt_radix_log" (2 [default] or 3): butterfly stages a thread runs on the elements it holds in registers between
+ *       two trips through shared memory -- 2: four elements per thread, 1024-element tiles, three blocks per SM;
+ *       3: eight elements, 2048-element tiles, two blocks per SM (the round-1 shape);
  *   "msm_acc_staged" (0/1): the accumulation kernel fetches the next table point into shared memory with cp.async
  *       while the current addition runs;
  *   "quotient_all_cosets" (0/1): evaluate the quotient numerator on all four cosets of the 4n domain even when it is

@@ -11,6 +11,7 @@ from typlonk_b200.ffi import TyplonkError
 from typlonk_b200.kzg import KzgScheme, Srs
 
 pytestmark = pytest.mark.gpu
+NTT_RADIX_DEFAULT = 2   # tp_ctx option "ntt_radix_log" as the library ships it
 R = fields.R_MOD
 
 
@@ -46,10 +47,12 @@ def test_coset_ntt_round_trip(ctx, log_n):
     assert F.fr_vec_from_bytes(back) == data
 
 
+@pytest.mark.parametrize("radix_log", [3, 2])
 @pytest.mark.parametrize("log_n", list(range(1, 23)))
-def test_ntt_every_pass_geometry_vs_c_oracle(ctx, log_n):
-    """Every pass plan of the radix-8 kernel (1-3 passes, 1-3 rounds per pass, remainders 0/1/2)
-    against the C++ oracle's radix-2 NTT, forward and inverse, bit-exact."""
+def test_ntt_every_pass_geometry_vs_c_oracle(ctx, log_n, radix_log):
+    """Every pass plan of the register-round kernel -- eight elements per thread (rounds of 3 stages, remainders 0/1/2)
+    and four (rounds of 2, remainders 0/1); 1-3 passes -- against the C++ oracle's radix-2 NTT, forward, inverse and
+    on a coset, bit-exact."""
     import numpy as np
     from oracle import coracle
     n = 1 << log_n
@@ -57,8 +60,18 @@ def test_ntt_every_pass_geometry_vs_c_oracle(ctx, log_n):
     raw = rs.randint(0, 2**32, size=(n, 8), dtype=np.uint64).astype(np.uint32)
     raw[:, 7] &= 0x3FFFFFFF
     data = raw.tobytes()
-    assert ctx.ntt(data, log_n) == coracle.ntt(data, log_n)
-    assert ctx.ntt(data, log_n, inverse=True) == coracle.ntt(data, log_n, inverse=True)
+    g = F.fr_to_bytes(7)
+    ctx.set_option("ntt_radix_log", 3)
+    want_coset = ctx.ntt(data, log_n, coset_mont=g) if radix_log == 2 else None
+    ctx.set_option("ntt_radix_log", radix_log)
+    try:
+        assert ctx.ntt(data, log_n) == coracle.ntt(data, log_n)
+        assert ctx.ntt(data, log_n, inverse=True) == coracle.ntt(data, log_n, inverse=True)
+        if want_coset is not None:   # both round shapes agree on a coset, and the inverse coset transform undoes it
+            assert ctx.ntt(data, log_n, coset_mont=g) == want_coset
+            assert ctx.ntt(want_coset, log_n, inverse=True, coset_mont=g) == data
+    finally:
+        ctx.set_option("ntt_radix_log", NTT_RADIX_DEFAULT)
 
 
 @pytest.mark.parametrize("log_n", [1, 2, 5, 12, 15, 19])

@@ -173,6 +173,11 @@ int tp_ctx_set_option(tp_ctx* ctx, const char* name, long value) {
     ctx->msm_pipe_min_log = (unsigned)value;
     return TP_OK;
   }
+  if (strcmp(name, "ntt_radix_log") == 0) {
+    if (value < 2 || value > 3) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: ntt_radix_log must be 2 or 3");
+    ctx->ntt_radix_log = (unsigned)value;
+    return TP_OK;
+  }
   if (strcmp(name, "msm_acc_staged") == 0) {
     if (value < 0 || value > 1) return fail(ctx, TP_ERR_INVALID_ARG, "set_option: msm_acc_staged must be 0 or 1");
     ctx->msm_acc_staged = (unsigned)value;

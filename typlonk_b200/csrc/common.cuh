@@ -59,6 +59,7 @@ struct tp_ctx {
   unsigned msm_pipeline = 0;      // MSM batches as overlapped sub-batches on the pipe's own streams (msm.cu, "pipeline"):
                                   // 0 never (default: measured slower on 1 and on 8 GPUs), 1 on sharded contexts, 2 always
   unsigned msm_pipe_min_log = 15; // ... for inputs of at least 2^this points (tests lower it to reach the path with small circuits)
+  unsigned ntt_radix_log = 2;     // butterfly stages per trip through registers: 3 (eight elements per thread) or 2 (four)
   unsigned msm_acc_staged = 0;    // 1: the accumulation stages the next table point in shared memory with cp.async
   // work counters (tp_ctx_get_stat)
   double stat_msm_entries = 0, stat_msm_calls = 0, stat_msm_c = 0, stat_msm_nwin = 0, stat_msm_levels = 0, stat_msm_chunk = 0;

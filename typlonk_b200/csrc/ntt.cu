@@ -114,24 +114,27 @@ __global__ void __launch_bounds__(512) k_ntt_small(NttPassArgs a) {
 // the column inside its 2^s0 block (0 in the first pass).
 __device__ __forceinline__ unsigned ntt_swz(unsigned i) { return i ^ ((i >> 3) & 7u); }
 
-// The butterfly rounds hold 28 field products (4 round shapes x up to 12).  Inlined they make 210 KB of SASS,
-// more than the instruction cache holds, and small grids stall on instruction fetch (no_instruction 2-6 per
-// issue, profiles/r1_summary.md O); through one shared copy of the multiplier the kernel is 2-7 % faster at
-// every size.  TP_NTT_MUL_INLINE restores the inlined form.
-#ifndef TP_NTT_MUL_INLINE
+// The multiplier is inlined into the butterflies: a kernel instance carries one full round (12 products with eight
+// elements per thread) plus the shorter rounds it needs, ~110 KB of SASS, and ptxas may interleave the independent
+// butterflies of a stage.  TP_NTT_MUL_CALL routes every product through one shared copy instead (36 KB): faster in
+// round 1, when every place a round was used had its own inlined copy (210 KB), 4-9 % slower now
+// (profiles/r2_summary.md L).
+#ifdef TP_NTT_MUL_CALL
 static __device__ __noinline__ Fr ntt_mul(Fr a, Fr b) { return fr_mul(a, b); }
 #else
 __device__ __forceinline__ Fr ntt_mul(const Fr& a, const Fr& b) { return fr_mul(a, b); }
 #endif
 
-template <int D0, int NST, bool TRIV, bool INVERSE>
-__device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw, unsigned A, unsigned sh, unsigned L,
+// One round = B butterfly stages on the E = 2^B elements a thread holds in registers.
+template <int B, int D0, int NST, bool TRIV, bool INVERSE>
+__device__ __forceinline__ void ntt_round(Fr (&x)[1 << B], const Fr* __restrict__ tw, unsigned A, unsigned sh, unsigned L,
                                           unsigned half_n) {
+  constexpr int E = 1 << B;
 #pragma unroll
   for (int d = D0; d < D0 + NST; d++) {
     const unsigned base_idx = A << (sh - d);
 #pragma unroll
-    for (int e0 = 0; e0 < 8; e0++) {
+    for (int e0 = 0; e0 < E; e0++) {
       if (e0 & (1 << d)) continue;
       const int e1 = e0 | (1 << d);
       const unsigned q = e0 & ((1 << d) - 1);
@@ -151,15 +154,21 @@ __device__ __forceinline__ void ntt_round(Fr (&x)[8], const Fr* __restrict__ tw,
   }
 }
 
-#define NTT_MAX_TILE_LOG 11
-#define NTT_SMEM_BYTES ((2u << NTT_MAX_TILE_LOG) * 16u)
+// Tile = 2^tile_log elements = 256 threads x E: 2048 with eight elements per thread (B = 3: 128 registers, two
+// blocks per SM), 1024 with four (B = 2: half the data registers, three blocks per SM -- more warps to cover the
+// multiplier's dependent chains, one more trip through shared memory per six stages).
+#define NTT_TILE_LOG(B) ((B) == 3 ? 11u : 10u)
 
 // FIRST: first pass of a transform (bit-reversed gather, coset scaling on the way in, trivial twiddles in the first
 // round); INVERSE: mirrored twiddles, scaling on the way out.  Compile-time, so that a kernel carries ONE copy of the
-// full three-stage round in its round loop (12 butterflies; the first pass also its 5-product first round) instead of
-// one per place a round is used, and no per-limb selects on the direction.
-template <bool FIRST, bool INVERSE>
-__global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
+// full round in its round loop (the first pass also its cheaper first round) instead of one per place a round is
+// used, and no per-limb selects on the direction.
+#ifndef TP_NTT_B2_BLOCKS
+#define TP_NTT_B2_BLOCKS 3
+#endif
+template <int B, bool FIRST, bool INVERSE>
+__global__ void __launch_bounds__(256, B == 3 ? 2 : TP_NTT_B2_BLOCKS) k_ntt_r8(NttPassArgs a) {
+  constexpr int E = 1 << B;
   extern __shared__ uint4 ntt_sh[];
   const unsigned T = 1u << (a.k + a.cw);
   uint4* s_lo = ntt_sh;
@@ -179,33 +188,33 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
   } else {
     base = (blockIdx.x << a.cw) + l;
   }
-  Fr x[8];
-  const unsigned rem = a.k % 3;
+  Fr x[E];
+  const unsigned rem = a.k % B;
   unsigned f_prev = 0;
-  for (unsigned f = 0; f < a.k; f += 3) {
-    const bool tail = f + 3 > a.k;          // fewer than three stages left: field sits at the top
-    const unsigned fb = tail ? a.k - 3 : f;
+  for (unsigned f = 0; f < a.k; f += B) {
+    const bool tail = f + B > a.k;          // fewer than B stages left: field sits at the top
+    const unsigned fb = tail ? a.k - B : f;
     if (f == 0) {
-      // ---- first round: operands straight from global memory (field base 0: m = rho * 8 + e) ----
+      // ---- first round: operands straight from global memory (field base 0: m = rho * E + e) ----
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const unsigned m = (rho << 3) | e;
+      for (int e = 0; e < E; e++) {
+        const unsigned m = (rho << B) | e;
         const unsigned g = FIRST ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
         x[e] = fr_load(in + g);
         if (FIRST && !INVERSE && coset) x[e] = ntt_mul(x[e], fr_load(coset + g));
       }
       if (FIRST) {
-        ntt_round<0, 3, true, INVERSE>(x, a.tw, 0u, a.L - 1, a.L, half_n);
+        ntt_round<B, 0, B, true, INVERSE>(x, a.tw, 0u, a.L - 1, a.L, half_n);
         continue;
       }
     } else {
       // ---- further rounds: exchange through shared memory ----
       {
         const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
-        const unsigned i0 = (((m_hi << (f_prev + 3)) | m_lo) << a.cw) | l;
+        const unsigned i0 = (((m_hi << (f_prev + B)) | m_lo) << a.cw) | l;
         if (f_prev != 0) __syncthreads();     // the previous exchange has been read by everyone
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
+        for (int e = 0; e < E; e++) {
           const unsigned p = ntt_swz(i0 | ((unsigned)e << (f_prev + a.cw)));
           s_lo[p] = make_uint4(x[e].v[0], x[e].v[1], x[e].v[2], x[e].v[3]);
           s_hi[p] = make_uint4(x[e].v[4], x[e].v[5], x[e].v[6], x[e].v[7]);
@@ -213,9 +222,9 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
         __syncthreads();
       }
       const unsigned m_lo = rho & ((1u << fb) - 1), m_hi = rho >> fb;
-      const unsigned i0 = (((m_hi << (fb + 3)) | m_lo) << a.cw) | l;
+      const unsigned i0 = (((m_hi << (fb + B)) | m_lo) << a.cw) | l;
 #pragma unroll
-      for (int e = 0; e < 8; e++) {
+      for (int e = 0; e < E; e++) {
         const unsigned p = ntt_swz(i0 | ((unsigned)e << (fb + a.cw)));
         const uint4 lo = s_lo[p], hi = s_hi[p];
         x[e].v[0] = lo.x; x[e].v[1] = lo.y; x[e].v[2] = lo.z; x[e].v[3] = lo.w;
@@ -225,21 +234,22 @@ __global__ void __launch_bounds__(256, 2) k_ntt_r8(NttPassArgs a) {
     const unsigned m_lo = rho & ((1u << fb) - 1);
     const unsigned A = (m_lo << a.s0) + lo_val;
     const unsigned sh = a.L - a.s0 - fb - 1;
-    if (!tail)
-      ntt_round<0, 3, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
-    else if (rem == 1)
-      ntt_round<2, 1, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
-    else
-      ntt_round<1, 2, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
+    if (!tail) {
+      ntt_round<B, 0, B, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
+    } else if (rem == 1) {
+      ntt_round<B, B - 1, 1, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
+    } else {
+      if constexpr (B >= 3) ntt_round<B, B - 2, 2, false, INVERSE>(x, a.tw, A, sh, a.L, half_n);
+    }
     f_prev = fb;
   }
   // ---- store from the last round's field ----
   {
     const unsigned m_lo = rho & ((1u << f_prev) - 1), m_hi = rho >> f_prev;
-    const unsigned m0 = (m_hi << (f_prev + 3)) | m_lo;
+    const unsigned m0 = (m_hi << (f_prev + B)) | m_lo;
     const unsigned obase = FIRST ? (bitrev(base, a.L - a.k) << a.k) : base;
 #pragma unroll
-    for (int e = 0; e < 8; e++) {
+    for (int e = 0; e < E; e++) {
       const unsigned m = m0 | ((unsigned)e << f_prev);
       const unsigned g = FIRST ? obase + m : obase + (m << a.s0);
       Fr y = x[e];
@@ -287,26 +297,44 @@ static int get_coset_table(tp_ctx* ctx, unsigned log_n, const tph::HFr& g, bool 
   return TP_OK;
 }
 
-// Pass plan: as few passes as the 2048-element tile allows (k <= 9 with four columns per tile),
-// every pass at least three stages, and as many of them as possible a multiple of three.  The
-// first pass has four columns per tile (its rows are far apart: 128-byte runs); later passes with
-// fewer stages widen the tile instead (2^(11-k) adjacent columns), so every CTA has 256 threads.
-static int ntt_plan(unsigned log_n, unsigned* ks) {
-  if (log_n <= NTT_MAX_TILE_LOG) {
+// Pass plan: as few passes as the tile allows (k <= tile_log - 2 with four columns per tile), every pass at least B
+// stages.  The first pass has four columns per tile (its rows are far apart: 128-byte runs); later passes with
+// fewer stages widen the tile instead (2^(tile_log - k) adjacent columns), so every CTA has 256 threads.
+static int ntt_plan(unsigned log_n, unsigned* ks, unsigned tile_log, unsigned B) {
+  if (log_n <= tile_log) {
     ks[0] = log_n;
     return 1;
   }
-  const unsigned kmax = NTT_MAX_TILE_LOG - 2;
+  const unsigned kmax = tile_log - 2;
   int npass = (int)((log_n + kmax - 1) / kmax);
   unsigned left = log_n;
   for (int i = 0; i < npass; i++) {
     unsigned passes_after = (unsigned)(npass - 1 - i);
     unsigned k = left < kmax ? left : kmax;
-    if (left - k < 3 * passes_after) k = left - 3 * passes_after;  // leave >= 3 stages for each later pass
+    if (left - k < B * passes_after) k = left - B * passes_after;  // leave >= B stages for each later pass
     ks[i] = k;
     left -= k;
   }
   return npass;
+}
+
+template <int B>
+static int ntt_launch(tp_ctx* ctx, const NttPassArgs& a, dim3 grid, unsigned threads, size_t smem, bool inverse) {
+  static bool smem_attr = false;
+  if (!smem_attr) {
+    const int cap = (int)((2u << NTT_TILE_LOG(B)) * 16u);
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+    smem_attr = true;
+  }
+  if (a.first && inverse) k_ntt_r8<B, true, true><<<grid, threads, smem, ctx->stream>>>(a);
+  else if (a.first) k_ntt_r8<B, true, false><<<grid, threads, smem, ctx->stream>>>(a);
+  else if (inverse) k_ntt_r8<B, false, true><<<grid, threads, smem, ctx->stream>>>(a);
+  else k_ntt_r8<B, false, false><<<grid, threads, smem, ctx->stream>>>(a);
+  TP_LAUNCH(ctx, "k_ntt_r8");
+  return TP_OK;
 }
 
 // `count` transforms of size 2^log_n in one set of launches; coset[i] (Montgomery generator, may be
@@ -358,16 +386,12 @@ int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64
     TP_LAUNCH(ctx, "k_ntt_small");
     return TP_OK;
   }
-  static bool smem_attr = false;
-  if (!smem_attr) {
-    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
-    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
-    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
-    TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NTT_SMEM_BYTES));
-    smem_attr = true;
-  }
+  // elements per thread: 8 (B = 3) or 4 (B = 2); tp_ctx_set_option("ntt_radix_log", 2 | 3) / $TP_NTT_B
+  static const char* env_b = getenv("TP_NTT_B");
+  const unsigned B = (env_b && (*env_b == '2' || *env_b == '3')) ? (unsigned)(*env_b - '0') : ctx->ntt_radix_log;
+  const unsigned tile_log = NTT_TILE_LOG(B);
   unsigned ks[8];
-  const int npass = ntt_plan(log_n, ks);
+  const int npass = ntt_plan(log_n, ks, tile_log, B);
   // the first pass of a multi-pass transform is out of place: in-place entries go through scratch
   Fr* scratch = nullptr;
   if (npass > 1) {
@@ -394,18 +418,15 @@ int ntt_batch_dev(tp_ctx* ctx, const Fr* const* in, Fr* const* out, const uint64
     }
     a.s0 = s0;
     a.k = ks[p];
-    a.cw = npass == 1 ? 0 : (p == 0 ? 2 : NTT_MAX_TILE_LOG - a.k);
+    a.cw = npass == 1 ? 0 : (p == 0 ? 2 : tile_log - a.k);
     a.first = (p == 0);
     a.last = (p == npass - 1);
     const unsigned T = 1u << (a.k + a.cw);
     const unsigned grid = (unsigned)(n >> (a.k + a.cw));
     const dim3 g3(grid, (unsigned)count);
     const size_t smem = 2 * T * sizeof(uint4);
-    if (a.first && inverse) k_ntt_r8<true, true><<<g3, T / 8, smem, ctx->stream>>>(a);
-    else if (a.first) k_ntt_r8<true, false><<<g3, T / 8, smem, ctx->stream>>>(a);
-    else if (inverse) k_ntt_r8<false, true><<<g3, T / 8, smem, ctx->stream>>>(a);
-    else k_ntt_r8<false, false><<<g3, T / 8, smem, ctx->stream>>>(a);
-    TP_LAUNCH(ctx, "k_ntt_r8");
+    if (B == 3) TP_TRY(ntt_launch<3>(ctx, a, g3, T >> 3, smem, inverse));
+    else TP_TRY(ntt_launch<2>(ctx, a, g3, T >> 2, smem, inverse));
     for (int i = 0; i < count; i++) src[i] = a.out[i];
     s0 += a.k;
   }
