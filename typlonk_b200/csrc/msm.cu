@@ -979,7 +979,10 @@ __global__ void __launch_bounds__(128) k_msm_merge_level(const unsigned* __restr
 #define WSUM_S_FIRST 16      // segment length of the first running-sum level (where the work is)
 #define WSUM_S_NEXT 8        // and of the later ones
 #define WSUM_MAX_LEVELS 4
-__global__ void __launch_bounds__(128) k_msm_wsum_level(const G1Xyzz* __restrict__ in, const unsigned* __restrict__ hist,
+#ifndef TP_WSUM_MIN_BLOCKS
+#define TP_WSUM_MIN_BLOCKS 3   // 168 registers; 4 blocks (128 registers, 36 bytes of spills): reduce +0.27 ms, 5: +0.7 (profiles r2 J)
+#endif
+__global__ void __launch_bounds__(128, TP_WSUM_MIN_BLOCKS) k_msm_wsum_level(const G1Xyzz* __restrict__ in, const unsigned* __restrict__ hist,
                                                         unsigned m_in, unsigned seg, unsigned total_out,
                                                         G1Xyzz* __restrict__ r_out, G1Xyzz* __restrict__ t_out) {
   unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
