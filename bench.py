@@ -260,9 +260,9 @@ def main():
 
     # a non-default torch stream: its handle is what the library launches on, so torch.cuda.Event
     # timings bracket the library's kernels (the legacy default stream has handle 0 = "make your own")
-    # (priority -1: above the lowest-priority stream the library's MSM pipe accumulates on, so the scans and transforms
-    # the prover queues between two sub-batches are not stuck behind the accumulation's pending blocks)
-    tstream = torch.cuda.Stream(device=dev, priority=-1)
+    # ($TP_BENCH_STREAM_PRIORITY=-1 puts it above the lowest-priority stream the library's optional MSM pipe
+    # accumulates on; the default stays an ordinary stream)
+    tstream = torch.cuda.Stream(device=dev, priority=int(os.environ.get("TP_BENCH_STREAM_PRIORITY", "0")))
     torch.cuda.set_stream(tstream)
     ctx = Context(local_rank, tstream.cuda_stream)
 
@@ -332,7 +332,8 @@ def main():
         if log_n >= 18 else "working set may fit L2 at this size"
 
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:   # one poller per job: the line carries rank 0's clocks, and NVML queries take a driver lock
+        sampler.start()
     ctx.prof_reset()
     ctx.prof_enable(True)
     l0 = ctx.launch_count()
@@ -341,10 +342,18 @@ def main():
     prof = ctx.prof_get()
     msms, entries = ctx.get_stat("msm_calls"), ctx.get_stat("msm_entries")   # of the K timed steps only
     ctx.prof_enable(False)
-    for _ in range(1):
+    for _ in range(args.warmup):   # the first sharded uploads also set up their NCCL transfers
         step_e2e()
-    ms_e2e, proof_e2e = timed(step_e2e, args.steps)
+    e2e_wall = []
+
+    def step_e2e_logged():   # host wall clock per step (the call returns with the proof): shows outliers, adds no barrier
+        t1 = time.perf_counter()
+        out = step_e2e()
+        e2e_wall.append(round((time.perf_counter() - t1) * 1e3, 3))
+        return out
+    ms_e2e, proof_e2e = timed(step_e2e_logged, args.steps)
     clocks = sampler.stop()
+    e2e_sample = [round(timed(step_e2e, 1)[0], 3) for _ in range(3)]   # three more, each timed alone (diagnostic)
     assert proof == proof_e2e, "resident and host-buffer proofs differ"
     parity = _parity(proof, log_n)
     if world > 1:   # every rank must hold the same bytes
@@ -456,7 +465,8 @@ def main():
         "e2e": {"value": ms_e2e / args.steps, "unit": UNIT, "h2d_bytes_per_step": 3 * 32 * n + 32 * world,
                 "inputs": "3 witness columns of n Fr + the 1-element public-input vector, pinned host memory"
                           + (" (each rank uploads its 1/%d row slice; slices exchanged over NVLink)" % world if world > 1 else ""),
-                "d2h_bytes_per_step": 1472},
+                "d2h_bytes_per_step": 1472, "single_step_sample_ms": e2e_sample, "step_wall_ms": e2e_wall,
+                "median_step_wall_ms": sorted(e2e_wall)[len(e2e_wall) // 2] if e2e_wall else None},
         "gpu_launches": launches,
         "clocks": clocks,
         "parity": parity,

@@ -1046,15 +1046,14 @@ static int prove_from_host(tp_ctx* ctx, tp_circuit* c, const uint64_t* const adv
   const size_t world = (size_t)ctx->world;
   if (comm_ready(ctx) && c->n % world == 0 && c->n / world >= 64) {
     // Sharded upload: every rank holds the same host columns, so each one sends only its row slice over PCIe
-    // and the slices are exchanged over NVLink (one device broadcast per rank), then scattered into the columns.
+    // and the slices are exchanged over NVLink (one all-gather), then scattered into the columns.
     const size_t rows = c->n / world, slice = rows * sizeof(Fr);
     uint8_t* stage = (uint8_t*)c->buf4[0];                       // [rank][column][rows], at most 4n Fr in total
     for (int j = 0; j < ncols; j++)
       TP_TRY(h2d(ctx, stage + ((size_t)ctx->rank * ncols + j) * slice, (const uint8_t*)cols[j] + (size_t)ctx->rank * slice, slice));
-    TP_TRY(comm_group_begin(ctx));
-    for (int r = 0; r < ctx->world; r++)
-      TP_TRY(comm_bcast(ctx, stage + (size_t)r * ncols * slice, ncols * slice, r));
-    TP_TRY(comm_group_end(ctx));
+    // [rank][column][rows] is exactly what an in-place all-gather of the ranks' blocks leaves behind: one collective
+    // (round 2 started with one broadcast per rank in a group)
+    TP_TRY(comm_allgather(ctx, stage + (size_t)ctx->rank * ncols * slice, stage, ncols * slice));
     for (int j = 0; j < ncols; j++)
       TP_CUDA_OK(ctx, cudaMemcpy2DAsync(dst[j], slice, stage + (size_t)j * slice, ncols * slice, slice, world,
                                         cudaMemcpyDeviceToDevice, ctx->stream));

@@ -90,9 +90,10 @@ struct LocalGroup {
 
 // ---- collectives the prover calls ----------------------------------------------------------------------
 // All ranks call with the same sizes.  NCCL: enqueued on ctx->stream.  Local: returns with the data in place.
+// In place (send_dev == recv_dev + rank * bytes) is allowed on every transport.
 int comm_allgather(tp_ctx* ctx, const void* send_dev, void* recv_dev, size_t bytes) {
   if (ctx->world <= 1) {
-    TP_CUDA_OK(ctx, cudaMemcpyAsync(recv_dev, send_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (recv_dev != send_dev) TP_CUDA_OK(ctx, cudaMemcpyAsync(recv_dev, send_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
     return TP_OK;
   }
   if (ctx->nccl) {
@@ -104,8 +105,11 @@ int comm_allgather(tp_ctx* ctx, const void* send_dev, void* recv_dev, size_t byt
     TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));   // my send buffer is final, my receive buffer idle
     g->ptr[ctx->rank] = recv_dev;
     g->barrier();
-    for (int p = 0; p < ctx->world; p++)
-      TP_CUDA_OK(ctx, cudaMemcpyAsync((char*)g->ptr[p] + (size_t)ctx->rank * bytes, send_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    for (int p = 0; p < ctx->world; p++) {
+      char* dst = (char*)g->ptr[p] + (size_t)ctx->rank * bytes;
+      if (dst != (const char*)send_dev)   // in place: my own block is already where it belongs
+        TP_CUDA_OK(ctx, cudaMemcpyAsync(dst, send_dev, bytes, cudaMemcpyDefault, ctx->stream));
+    }
     TP_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
     g->barrier();
     return TP_OK;
