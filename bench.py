@@ -451,6 +451,8 @@ def main():
     roofline_int = {"bound": "fma-heavy pipe (IMAD.WIDE.U32.X)", "kernel": kernel, "achieved": prod_rate,
                     "peak": imad_wide, "unit": "wide multiply-adds/s", "frac": (prod_rate / imad_wide) if prod_rate else None,
                     "additions_per_step": entries / args.steps, "wide_products_per_addition": per_add,
+                    # algorithmic count (8M + 2S); the kernel executes 2604: Y3 = R (Q - X3) - Y1 PPP shares one reduction
+                    "wide_products_executed_per_addition": None if affine else 6 * 288 + 2 * 222 + 432,
                     "window_bits": ctx.get_stat("msm_window_bits"), "windows": ctx.get_stat("msm_windows"),
                     "table_levels": ctx.get_stat("msm_table_levels"),
                     "note": "per rank: additions_per_step counts the bucket additions THIS rank issued"}
