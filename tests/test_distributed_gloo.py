@@ -139,6 +139,63 @@ def test_bucket_ownership_covers_every_digit_once():
                         assert world * (b // world) + (b % world) + 1 == abs(d)
 
 
+def _sharded_digit_pass(s, c, nwin, world, rank):
+    """k_msm_digits_sharded (msm.cu) restated: ONE walk over the windows records which digits this rank owns and the
+    carry that entered each of them (two bit masks), the emit pass revisits the owned windows only and recomputes
+    each digit from its c-bit field and the saved carry.  Ownership: bucket b = |digit| - 1 belongs to rank b % world as
+    local bucket b // world -- a mask and a shift when world is a power of two.  Returns [(window, local bucket, neg)]."""
+    half, full = 1 << (c - 1), 1 << c
+    pow2 = world & (world - 1) == 0
+    shift = world.bit_length() - 1
+
+    def field(w):
+        return (s >> (w * c)) & (full - 1) if w * c < 256 else 0
+
+    def mine(b):
+        return (b & (world - 1)) == rank if pow2 else b % world == rank
+
+    own_mask = carry_mask = carry = 0
+    for w in range(nwin):
+        raw, cin = field(w) + carry, carry
+        carry = 1 if raw > half else 0
+        if raw == 0 or raw == full:
+            continue
+        mag = full - raw if carry else raw
+        if mine(mag - 1):
+            own_mask |= 1 << w
+            carry_mask |= cin << w
+    out = []
+    while own_mask:
+        w = (own_mask & -own_mask).bit_length() - 1
+        own_mask &= own_mask - 1
+        raw = field(w) + ((carry_mask >> w) & 1)
+        neg = raw > half
+        mag = full - raw if neg else raw
+        out.append((w, (mag - 1) >> shift if pow2 else (mag - 1) // world, neg))
+    return out
+
+
+def test_sharded_digit_pass_partitions_the_signed_digits():
+    """Every non-zero signed digit of a scalar is emitted by exactly one rank, with the sign and the local bucket that
+    map back to it; power-of-two and general rank counts, window sizes with and without a carry window on top."""
+    import random
+    rnd = random.Random(9)
+    R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    for c in (8, 15, 16, 20):
+        nwin = _windows_for(c)
+        assert nwin <= 32   # the masks of the kernel's fast path
+        for world in (2, 3, 4, 5, 8):
+            for s in [0, 1, R - 1, (1 << 255) - 1 & (R - 1)] + [rnd.randrange(R) for _ in range(40)]:
+                want = {w: d for w, d in enumerate(_signed_digits(s, c, nwin)) if d}
+                got = {}
+                for rank in range(world):
+                    for w, local, neg in _sharded_digit_pass(s, c, nwin, world, rank):
+                        assert w not in got, "a digit emitted by two ranks"
+                        mag = local * world + rank + 1
+                        got[w] = -mag if neg else mag
+                assert got == want, (c, world, hex(s))
+
+
 # ---- quotient sharded by coset (api.cu prove_resident, comm_bcast) ------------------------------
 def _coset_owner(k, world):
     return k % world if world < 4 else k * (world // 4)   # typlonk_b200/csrc/api.cu: owner(k)
