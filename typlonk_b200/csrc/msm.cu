@@ -1304,9 +1304,9 @@ static int job_sort(tp_ctx* ctx, MsmPipe* p, MsmJob& j, const Fr* const* scalars
   unsigned* offsets = (unsigned*)ln.offsets.p;
   uint2* sorted = (uint2*)ln.sorted.p;
   const bool compact = world > 1 && !env_uint("TP_MSM_NO_COMPACT", 0);
-  if (compact) {
-    TP_TRY(ensure_idle(ctx, ctx->msm_compact, total * sizeof(MsmEntry) + 16));
-  } else {   // keys / ranks live from the digit pass to the scatter only: one copy, all sorts run on one stream
+  if (compact) TP_TRY(ensure_idle(ctx, ctx->msm_compact, total * sizeof(MsmEntry) + 16));
+  if (!compact || ctx->msm_aff_rounds) {   // keys / ranks live from the digit pass to the scatter only: one copy, all sorts run
+                                           // on one stream (the opt-in affine rounds reuse the key array as a counter array)
     TP_TRY(ensure_idle(ctx, ctx->msm_keys, total * sizeof(unsigned)));
     TP_TRY(ensure_idle(ctx, ctx->msm_ranks, total * sizeof(unsigned)));
   }
@@ -1456,10 +1456,10 @@ static int job_accumulate(tp_ctx* ctx, MsmPipe* p, MsmJob& j) {
     TP_TRY(ensure(ctx, ctx->msm_aff_rec, (bound[0] / 2 + 1) * sizeof(uint4)));
     uint4* rec = (uint4*)ctx->msm_aff_rec.p;
     size_t region = 0;
-    static bool smem_attr = false;
-    if (!smem_attr) {
+    static bool smem_attr[64] = {false};   // a function attribute belongs to a device: a group context has one rank per device
+    if (!smem_attr[ctx->device & 63]) {
       TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_aff_round, cudaFuncAttributeMaxDynamicSharedMemorySize, AFF_SMEM));
-      smem_attr = true;
+      smem_attr[ctx->device & 63] = true;
     }
     for (int r = 0; r < rounds; r++) {
       unsigned* cnt_out = (r & 1) ? cnt_alt : cnts[1];

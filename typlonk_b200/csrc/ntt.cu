@@ -320,14 +320,14 @@ static int ntt_plan(unsigned log_n, unsigned* ks, unsigned tile_log, unsigned B)
 
 template <int B>
 static int ntt_launch(tp_ctx* ctx, const NttPassArgs& a, dim3 grid, unsigned threads, size_t smem, bool inverse) {
-  static bool smem_attr = false;
-  if (!smem_attr) {
+  static bool smem_attr[64] = {false};   // per device: the ranks of a device group launch from their own devices
+  if (!smem_attr[ctx->device & 63]) {
     const int cap = (int)((2u << NTT_TILE_LOG(B)) * 16u);
     TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
     TP_CUDA_OK(ctx, cudaFuncSetAttribute(k_ntt_r8<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-    smem_attr = true;
+    smem_attr[ctx->device & 63] = true;
   }
   if (a.first && inverse) k_ntt_r8<B, true, true><<<grid, threads, smem, ctx->stream>>>(a);
   else if (a.first) k_ntt_r8<B, true, false><<<grid, threads, smem, ctx->stream>>>(a);
