@@ -2,6 +2,7 @@
 circuit generator, proof framing) against the oracle, and the C-ABI library's exported surface.
 No compute calls -- there is no GPU here and the library has no CPU fallback."""
 import os
+import sys
 import re
 
 import pytest
@@ -254,3 +255,16 @@ def test_library_stdrng_matches_the_rand_crates_own_constants():
         key += struct.pack("<I", ((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF)
     assert int.from_bytes(key[:8], "little") == 5029875928683246316
     assert ffi.stdrng_words(40, seed_u64=0) == ffi.stdrng_words(40, seed32=key)
+
+
+def test_generated_montgomery_header_is_current_and_its_carry_chains_check(tmp_path):
+    """typlonk_b200/csrc/mont_gen.cuh is exactly what tools/gen_mont.py emits, and the generator's CPU simulator
+    accepts every carry chain (random and edge operands against big-integer arithmetic) before emitting."""
+    import subprocess
+    out = tmp_path / "mont_gen.cuh"
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_mont.py"), "--out", str(out)],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert "separated forms ok" in res.stdout and "Fq:" in res.stdout
+    with open(os.path.join(ROOT, "typlonk_b200", "csrc", "mont_gen.cuh")) as f:
+        assert out.read_text() == f.read(), "mont_gen.cuh is stale: run python tools/gen_mont.py"

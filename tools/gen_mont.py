@@ -12,7 +12,7 @@ Multiplication is an interleaved (CIOS-style) Montgomery product over two accumu
 arrays ("even"/"odd" columns) so that every 32x32->64 product is a mad.lo.cc/madc.hi.cc
 pair on an aligned register pair -- the pattern ptxas fuses into IMAD.WIDE.U32(.X).
 
-Usage: python tools/gen_mont.py [--check-only]
+Usage: python tools/gen_mont.py [--check-only] [--out PATH]
 """
 import random
 import sys
@@ -680,6 +680,8 @@ def main():
         out.append(emit_fn("%s_add_ptx" % name, build_add(mod, n), n))
         out.append(emit_fn("%s_sub_ptx" % name, build_sub(mod, n), n))
     dst = Path(__file__).resolve().parent.parent / "typlonk_b200" / "csrc" / "mont_gen.cuh"
+    if "--out" in sys.argv:   # somewhere else (tests compare it with the committed header)
+        dst = Path(sys.argv[sys.argv.index("--out") + 1])
     dst.parent.mkdir(parents=True, exist_ok=True)
     dst.write_text("\n\n".join(out) + "\n")
     print("wrote", dst)
