@@ -4,7 +4,8 @@
 // n independent double-and-add scalar multiplications folded with `Sum`.  The affine result of
 // a group sum is unique, so the bucket method is bit-exact with it.
 //
-// Pipeline (all on the ctx stream):
+// Stages (in order on the ctx stream; the opt-in "pipeline" mode near the end of this file spreads the stages of
+// consecutive sub-batches over three streams instead):
 //   1. k_msm_digits   : scalar Montgomery -> canonical, signed-digit windows of c bits; each
 //                       non-zero digit takes a rank in its bucket with one atomicAdd
 //                       (histogram and within-bucket rank in a single pass)
