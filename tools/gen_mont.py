@@ -239,6 +239,90 @@ def build_sub(mod, n):
     return pr
 
 
+# ---- lazy Fr arithmetic for the NTT butterflies: values stay in [0, 2r) -----------------------------------------------
+# r = 0.905 * 2^255, so 2r < 2^256 (and 4r is not: Harvey's [0, 4p) butterfly does not fit).  A Montgomery product of
+# x < 2r by a reduced twiddle w < r is (x w + m r) / R < r (2r / R + 1) < 2r WITHOUT the final conditional subtraction,
+# and sums / differences are reduced modulo 2r instead of r: the product's subtraction is what a butterfly saves; the
+# transform's last store brings the values back to [0, r).
+def build_add2(mod, n):
+    """r = a + b reduced once by 2p; a, b < 2p, 2p < 2^(32 n) <= 4p possible: the sum may carry out of n limbs"""
+    m2 = limbs(2 * mod, n)
+    pr = Prog()
+    a = ["a%d" % i for i in range(n)]
+    b = ["b%d" % i for i in range(n)]
+    t = ["e%d" % i for i in range(n)]
+    d = ["o%d" % i for i in range(n)]
+    for i in range(n):
+        pr.emit("add.cc.u32" if i == 0 else "addc.cc.u32", t[i], a[i], b[i])
+    pr.emit("addc.u32", "mi", 0, 0)                      # the carry: bit 32 n of the sum
+    for i in range(n):
+        pr.emit("sub.cc.u32" if i == 0 else "subc.cc.u32", d[i], t[i], m2[i])
+    pr.emit("subc.u32", "brw", "mi", 0)                  # carry - borrow: non-zero exactly when the sum is below 2p
+    pr.emit("setp.ne.u32", "%pb", "brw", 0)
+    for i in range(n):
+        pr.emit("selp.u32", "r%d" % i, t[i], d[i], "%pb")
+    return pr
+
+
+def build_condsub(mod, n, mults):
+    """r = a reduced by one conditional subtraction of k p for every k in `mults`"""
+    pr = Prog()
+    # the selects below read their operand limb by limb while writing the result: work on a copy, the asm outputs are
+    # not early-clobber and may share registers with the inputs (ptxas folds the moves away)
+    cur = ["c%d" % i for i in range(n)]
+    pr.temps = list(cur) + ["d%d" % i for i in range(n)]
+    for i in range(n):
+        pr.emit("mov.u32", cur[i], "a%d" % i)
+    for step, k in enumerate(mults):
+        last = step == len(mults) - 1
+        out = ["r%d" % i for i in range(n)] if last else ["d%d" % i for i in range(n)]
+        cond_sub_p(pr, cur, ["o%d" % i for i in range(n)], out, k * mod, n)
+        cur = out
+    return pr
+
+
+def check_lazy(mod, n, trials=3000):
+    R = 1 << (32 * n)
+    assert 2 * mod < R
+    rinv = pow(R, -1, mod)
+    rnd = random.Random(4242)
+    mul = build_mul(mod, n, reduce_final=False, m0_reg=True, special=True)
+    mulfull = build_mul(mod, n, m0_reg=True, special=True)
+    add2 = build_add2(mod, n)
+    sub2 = build_sub(2 * mod, n)
+    norm2 = build_condsub(mod, n, (1,))
+
+    def run(pr, **vals):
+        env = {"m0": (-pow(mod, -1, 1 << 32)) & MASK}
+        for nm, v in vals.items():
+            for i, l in enumerate(limbs(v, n)):
+                env["%s%d" % (nm, i)] = l
+        o = pr.run(env)
+        return sum(o["r%d" % i] << (32 * i) for i in range(n))
+
+    big = [0, 1, mod - 1, mod, mod + 1, 2 * mod - 2, 2 * mod - 1, R - 2 * mod, (R - 1) % (2 * mod),
+           (1 << 255) - 1, 1 << 255, (1 << 255) + 1]
+    small = [0, 1, 2, mod - 1, mod - 2, (mod - 1) // 2, R % mod]
+    cases = [(x, w) for x in big for w in small] + [(rnd.randrange(2 * mod), rnd.randrange(mod)) for _ in range(trials)]
+    for x, w in cases:
+        # The reduced operand goes FIRST: it is the one whose limbs form the rows' multiplicand, and the interleaved
+        # form's no-carry shortcut needs that one below 2^255; the second operand's limbs are only row multipliers and
+        # may be anything below 2^256 (the other order fails the simulator's carry asserts, as it should).
+        t = run(mul, a=w, b=x)
+        assert t < 2 * mod and t % mod == x * w * rinv % mod, ("lazy mul", hex(x), hex(w))
+        # the full product (last store of an inverse transform) takes a lazy operand and returns a canonical value
+        assert run(mulfull, a=w, b=x) == x * w * rinv % mod
+    cases = [(u, t) for u in big for t in big] + [(rnd.randrange(2 * mod), rnd.randrange(2 * mod)) for _ in range(trials)]
+    for u, t in cases:
+        s = run(add2, a=u, b=t)
+        d = run(sub2, a=u, b=t)
+        assert s < 2 * mod and s % mod == (u + t) % mod, ("add2", hex(u), hex(t))
+        assert d < 2 * mod and d % mod == (u - t) % mod, ("sub2", hex(u), hex(t))
+    for u in big + [rnd.randrange(2 * mod) for _ in range(trials)]:
+        assert run(norm2, a=u) == u % mod
+    print("%d-limb lazy forms ok" % n)
+
+
 # appended section for tools/gen_mont.py: separated-form (wide product + reduction) builders
 class Cols:
     """Column accumulators in two alignments over absolute limb positions: E holds 64-bit pairs at
@@ -639,6 +723,7 @@ def check_sep(mod, n, trials=300):
 def main():
     check_sep(R_MOD, 8)
     check_sep(Q_MOD, 12)
+    check_lazy(R_MOD, 8)
     check("Fr", R_MOD, 8)
     check("Fr(mod in regs)", R_MOD, 8, mod_regs=True)
     check("Fr(m0 in a register)", R_MOD, 8, m0_reg=True)
@@ -667,6 +752,12 @@ def main():
     for name, mod, n in (("fr", R_MOD, 8), ("fq", Q_MOD, 12)):
         if name == "fr":
             out.append(emit_fn("fr_mul_ptx", build_mul(mod, n, m0_reg=True, special=True), n, m0_sym="TP_FR_M0"))
+            # lazy forms for the NTT butterflies (see build_add2): values in [0, 2r)
+            out.append(emit_fn("fr_mul_lazy_ptx", build_mul(mod, n, reduce_final=False, m0_reg=True, special=True), n,
+                               m0_sym="TP_FR_M0"))
+            out.append(emit_fn("fr_add2_ptx", build_add2(mod, n), n))
+            out.append(emit_fn("fr_sub2_ptx", build_sub(2 * mod, n), n))
+            out.append(emit_fn_ops("fr_norm2_ptx", build_condsub(mod, n, (1,)), n, ["a"]))
         else:
             out.append(emit_fn("%s_mul_ptx" % name, build_mul(mod, n), n))
             # lazy pair a*b + c*d with one shared reduction (interleaved form: 432 products instead of 576)

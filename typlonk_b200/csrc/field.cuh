@@ -51,6 +51,29 @@ __device__ __forceinline__ Fr fr_sub(const Fr& a, const Fr& b) {
   return r;
 }
 __device__ __forceinline__ Fr fr_neg(const Fr& a) { return fr_sub(fr_zero(), a); }
+// Lazy forms (values in [0, 2r), 2r < 2^256; tools/gen_mont.py build_add2): the product keeps its result unreduced --
+// `w` must be the REDUCED operand (< r), `x` may be lazy -- sums and differences are taken modulo 2r, fr_norm2 returns
+// to [0, r).  fr_mul(w, x) with a lazy x is also fine and returns a canonical value.
+__device__ __forceinline__ Fr fr_mul_lazy(const Fr& w, const Fr& x) {
+  Fr r;
+  fr_mul_lazy_ptx(r.v, w.v, x.v);
+  return r;
+}
+__device__ __forceinline__ Fr fr_add2(const Fr& a, const Fr& b) {
+  Fr r;
+  fr_add2_ptx(r.v, a.v, b.v);
+  return r;
+}
+__device__ __forceinline__ Fr fr_sub2(const Fr& a, const Fr& b) {
+  Fr r;
+  fr_sub2_ptx(r.v, a.v, b.v);
+  return r;
+}
+__device__ __forceinline__ Fr fr_norm2(const Fr& a) {
+  Fr r;
+  fr_norm2_ptx(r.v, a.v);
+  return r;
+}
 __device__ __forceinline__ Fr fr_dbl(const Fr& a) { return fr_add(a, a); }
 __device__ __forceinline__ bool fr_is_zero(const Fr& a) {
   uint32_t o = 0;

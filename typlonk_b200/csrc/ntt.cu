@@ -124,6 +124,22 @@ static __device__ __noinline__ Fr ntt_mul(Fr a, Fr b) { return fr_mul(a, b); }
 #else
 __device__ __forceinline__ Fr ntt_mul(const Fr& a, const Fr& b) { return fr_mul(a, b); }
 #endif
+// Lazy butterflies (default; -DTP_NTT_NO_LAZY restores canonical values throughout: 3-4.5 % slower, profiles/r2_summary.md L):
+// the values a transform carries between its first load and its last store live in [0, 2r) -- the
+// twiddle product skips its final conditional subtraction (fr_mul_lazy: reduced twiddle first, lazy value second), sums
+// and differences are reduced modulo 2r, the last store normalises (forward) or multiplies by n^-1 / the coset table
+// with a full reduction (inverse).  Saves the product's 17-instruction subtraction per butterfly.
+#ifndef TP_NTT_NO_LAZY
+__device__ __forceinline__ Fr bf_mul(const Fr& w, const Fr& x) { return fr_mul_lazy(w, x); }
+__device__ __forceinline__ Fr bf_add(const Fr& a, const Fr& b) { return fr_add2(a, b); }
+__device__ __forceinline__ Fr bf_sub(const Fr& a, const Fr& b) { return fr_sub2(a, b); }
+__device__ __forceinline__ Fr bf_out(const Fr& a) { return fr_norm2(a); }
+#else
+__device__ __forceinline__ Fr bf_mul(const Fr& w, const Fr& x) { return ntt_mul(w, x); }
+__device__ __forceinline__ Fr bf_add(const Fr& a, const Fr& b) { return fr_add(a, b); }
+__device__ __forceinline__ Fr bf_sub(const Fr& a, const Fr& b) { return fr_sub(a, b); }
+__device__ __forceinline__ Fr bf_out(const Fr& a) { return a; }
+#endif
 
 // One round = B butterfly stages on the E = 2^B elements a thread holds in registers.
 template <int B, int D0, int NST, bool TRIV, bool INVERSE>
@@ -140,15 +156,15 @@ __device__ __forceinline__ void ntt_round(Fr (&x)[1 << B], const Fr* __restrict_
       const unsigned q = e0 & ((1 << d) - 1);
       if (TRIV && q == 0) {  // A == 0 and q == 0: twiddle 1 in both directions
         const Fr u = x[e0], v = x[e1];
-        x[e0] = fr_add(u, v);
-        x[e1] = fr_sub(u, v);
+        x[e0] = bf_add(u, v);
+        x[e1] = bf_sub(u, v);
       } else {
         const unsigned idx = base_idx + (q << (L - d - 1));
         const Fr w = fr_load(tw + (INVERSE ? half_n - idx : idx));
-        const Fr t = ntt_mul(w, x[e1]);
+        const Fr t = bf_mul(w, x[e1]);
         const Fr u = x[e0];
-        x[e0] = INVERSE ? fr_sub(u, t) : fr_add(u, t);   // mirrored table entry is -omega^-idx
-        x[e1] = INVERSE ? fr_add(u, t) : fr_sub(u, t);
+        x[e0] = INVERSE ? bf_sub(u, t) : bf_add(u, t);   // mirrored table entry is -omega^-idx
+        x[e1] = INVERSE ? bf_add(u, t) : bf_sub(u, t);
       }
     }
   }
@@ -201,7 +217,7 @@ __global__ void __launch_bounds__(256, B == 3 ? 2 : TP_NTT_B2_BLOCKS) k_ntt_r8(N
         const unsigned m = (rho << B) | e;
         const unsigned g = FIRST ? (bitrev(m, a.k) << (a.L - a.k)) + base : base + (m << a.s0);
         x[e] = fr_load(in + g);
-        if (FIRST && !INVERSE && coset) x[e] = ntt_mul(x[e], fr_load(coset + g));
+        if (FIRST && !INVERSE && coset) x[e] = bf_mul(fr_load(coset + g), x[e]);
       }
       if (FIRST) {
         ntt_round<B, 0, B, true, INVERSE>(x, a.tw, 0u, a.L - 1, a.L, half_n);
@@ -253,7 +269,8 @@ __global__ void __launch_bounds__(256, B == 3 ? 2 : TP_NTT_B2_BLOCKS) k_ntt_r8(N
       const unsigned m = m0 | ((unsigned)e << f_prev);
       const unsigned g = FIRST ? obase + m : obase + (m << a.s0);
       Fr y = x[e];
-      if (INVERSE && a.last) y = ntt_mul(y, coset ? fr_load(coset + g) : a.ninv);
+      if (INVERSE && a.last) y = ntt_mul(coset ? fr_load(coset + g) : a.ninv, y);   // reduced factor first: y may be lazy
+      else if (a.last) y = bf_out(y);
       fr_store(out + g, y);
     }
   }
