@@ -268,3 +268,22 @@ def test_generated_montgomery_header_is_current_and_its_carry_chains_check(tmp_p
     assert "separated forms ok" in res.stdout and "Fq:" in res.stdout
     with open(os.path.join(ROOT, "typlonk_b200", "csrc", "mont_gen.cuh")) as f:
         assert out.read_text() == f.read(), "mont_gen.cuh is stale: run python tools/gen_mont.py"
+
+
+def test_every_tunable_is_documented_in_the_header_and_the_integration_guide():
+    """tp_ctx_set_option: the names the library accepts (api.cu) are the names include/typlonk_b200.h documents and
+    INTEGRATION.md lists."""
+    with open(os.path.join(ROOT, "typlonk_b200", "csrc", "api.cu")) as f:
+        src = f.read()
+    body = src[src.index("int tp_ctx_set_option("):src.index("int tp_ctx_get_stat(")]
+    accepted = set(re.findall(r'strcmp\(name, "([a-z0-9_]+)"\)', body))
+    assert len(accepted) >= 8
+    with open(os.path.join(ROOT, "include", "typlonk_b200.h")) as f:
+        hdr = f.read()
+    doc = hdr[hdr.index("Tunables of the MSM"):hdr.index("int tp_ctx_set_option(")]
+    documented = set(re.findall(r'"([a-z0-9_]+)"', doc))
+    assert accepted == documented, (sorted(accepted - documented), sorted(documented - accepted))
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        guide = f.read()
+    for name in accepted:
+        assert '"%s"' % name in guide, name
